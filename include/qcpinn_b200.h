@@ -1,0 +1,124 @@
+/* qcpinn_b200 -- C-ABI of the B200 (sm_100a) QCPINN training hot path.
+ *
+ * This is the drop-in boundary: the reference's hot path is pure Python that calls PennyLane's
+ * ``default.qubit`` through a QNode (reference nn/DVQuantumLayer.py:143-154) and differentiates it
+ * with nested torch autograd (reference nn/pde.py:53-72).  A maintainer of the reference would
+ * bind these entry points with ctypes from ``DVQuantumLayer.forward`` /
+ * ``DVPDESolver.forward`` / ``nn.pde.diffusion_operator``.
+ *
+ * Conventions
+ *   - every function returns 0 on success; otherwise qcp_last_error() describes the failure
+ *     (the Python host raises RuntimeError with that text).
+ *   - all data pointers are DEVICE pointers borrowed from the caller (contiguous, 16-byte
+ *     aligned); the library never frees or retains them beyond the call.  ``stream`` is a
+ *     cudaStream_t passed as void* (torch's current stream); all work is stream-ordered.
+ *   - ``dtype`` fixes the arithmetic AND the element type of every data pointer of a plan:
+ *     QCP_F32 (float / complex64-equivalent) or QCP_F64 (double / complex128-equivalent).
+ *   - a plan is not thread-safe; one host thread per process, one process per GPU.
+ *   - there is NO CPU fallback: every entry point fails when no CUDA device is usable.
+ */
+#ifndef QCPINN_B200_H_
+#define QCPINN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qcp_plan qcp_plan_t;
+
+/* Gate kinds of the batch-shared circuit program.  Semantics follow PennyLane's public gate
+ * definitions as used by reference nn/DVQuantumLayer.py:246-371 (wire 0 = most significant bit). */
+enum qcp_gate_kind {
+  QCP_GATE_RX = 0,   /* (wire, -, theta_index)            */
+  QCP_GATE_RY = 1,
+  QCP_GATE_RZ = 2,
+  QCP_GATE_CRX = 3,  /* (control, target, theta_index)    */
+  QCP_GATE_CRZ = 4,
+  QCP_GATE_CNOT = 5, /* (control, target, -1)             */
+  QCP_GATE_H = 6,    /* (wire, -, -1)                     */
+  QCP_GATE_U4 = 7    /* (wire_hi, wire_lo, const_index): fixed 4x4 unitary (the Haar blocks,
+                        reference nn/DVQuantumLayer.py:203-209) */
+};
+
+enum qcp_encoding {
+  QCP_ENC_ANGLE = 0,     /* AngleEmbedding(rotation="X"), reference nn/DVQuantumLayer.py:182   */
+  QCP_ENC_AMPLITUDE = 1  /* AmplitudeEmbedding(normalize=True, pad_with=0), reference :178-180 */
+};
+
+enum qcp_dtype { QCP_F32 = 0, QCP_F64 = 1 };
+
+enum qcp_mode {
+  QCP_MODE_VALUE = 1,    /* u only            (DVPDESolver.forward, reference nn/DVPDESolver.py:81) */
+  QCP_MODE_RESIDUAL = 6  /* u, u_t, u_x, u_y, u_xx, u_yy Taylor streams (reference nn/pde.py:53-72)  */
+};
+
+/* Pre / post MLP tensors of DVPDESolver (reference nn/DVPDESolver.py:28-51), torch layouts. */
+typedef struct qcp_mlp {
+  void* w1; /* [H,3]  preprocessor.0.weight  */
+  void* b1; /* [H]    preprocessor.0.bias    */
+  void* w2; /* [n,H]  preprocessor.2.weight  */
+  void* b2; /* [n]    preprocessor.2.bias    */
+  void* w3; /* [H,n]  postprocessor.0.weight */
+  void* b3; /* [H]    postprocessor.0.bias   */
+  void* w4; /* [1,H]  postprocessor.2.weight */
+  void* b4; /* [1]    postprocessor.2.bias   */
+} qcp_mlp_t;
+
+const char* qcp_last_error(void);
+int qcp_version(void);
+
+/* Number of usable CUDA devices (0 => every other call fails). */
+int qcp_device_count(void);
+
+/* Plan = compiled circuit program + device workspaces for one (n, encoding, dtype, hidden).
+ * ``ops`` is a HOST array [n_ops][4] of (kind, a, b, p); ``consts`` a HOST array of n_consts 4x4
+ * complex128 matrices, row-major, interleaved (re, im).  Replaces the QNode construction of
+ * reference nn/DVQuantumLayer.py:143-149. */
+int qcp_plan_create(qcp_plan_t** out, int n_qubits, int encoding, int dtype, int hidden,
+                    const int32_t* ops, int n_ops, const double* consts, int n_consts, int n_theta);
+int qcp_plan_destroy(qcp_plan_t* plan);
+int qcp_plan_num_features(const qcp_plan_t* plan);
+
+/* Evaluate the batch-shared part of the circuit for the current angles ``theta`` [n_theta]:
+ * V(theta) = H_last . Haar . ansatz layers, O_i = V^dag Z_i V, and the real feature matrix C with
+ * <Z_i>(z) = sum_s C[i,s] phi_s(z).  Must precede forward calls whenever theta changed. */
+int qcp_prepare(qcp_plan_t* plan, const void* theta, void* stream);
+
+/* Debug / test: copy the feature matrix to the HOST as double [n_qubits][num_features]. */
+int qcp_feature_matrix(qcp_plan_t* plan, double* out_host, void* stream);
+
+/* DVQuantumLayer.forward (reference nn/DVQuantumLayer.py:151-154): z [B,n] -> q [n,B]. */
+int qcp_layer_forward(qcp_plan_t* plan, const void* z, long long batch, void* q, void* stream);
+
+/* Its reverse mode: grad_q [n,B] -> grad_z [B,n] (may be NULL) and grad_theta [n_theta]. */
+int qcp_layer_backward(qcp_plan_t* plan, const void* theta, const void* z, const void* grad_q,
+                       long long batch, void* grad_z, void* grad_theta, void* stream);
+
+/* Fused DVPDESolver forward (reference nn/DVPDESolver.py:81-110) and, in QCP_MODE_RESIDUAL, the
+ * convection-diffusion residual of reference nn/pde.py:53-72 in Taylor mode:
+ *   r = c[0] u_t + c[1] u_x + c[2] u_y + c[3] u_xx + c[4] u_yy        (coeffs = HOST double[5]).
+ * X [B,3] -> u [B], r [B] (NULL in value mode), streams [B,6] (optional, may be NULL). */
+int qcp_solver_forward(qcp_plan_t* plan, const qcp_mlp_t* weights, const void* X, long long batch,
+                       int mode, const double* coeffs, void* u, void* r, void* streams,
+                       void* stream);
+
+/* Reverse mode of the above: given grad_u / grad_r [B] (either may be NULL) write (overwrite, not
+ * accumulate) the gradient of every weight tensor, of theta [n_theta], and optionally of X [B,3]
+ * (value mode only; NULL otherwise).  Replaces loss.backward() through the nested-autograd graph
+ * (reference trainer/diffusion_train.py:81). */
+int qcp_solver_backward(qcp_plan_t* plan, const qcp_mlp_t* weights, const void* theta,
+                        const void* X, const void* grad_u, const void* grad_r, long long batch,
+                        int mode, const double* coeffs, const qcp_mlp_t* grads, void* grad_theta,
+                        void* grad_X, void* stream);
+
+/* FMA-pipe micro-benchmark used as the roofline denominator: runs
+ * ``iters`` dependent-chain FMA rounds on every SM and returns achieved FLOP/s. */
+int qcp_bench_fma(int dtype, int iters, double* flops_per_s, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* QCPINN_B200_H_ */

@@ -1,0 +1,85 @@
+"""Build ``libqcpinn_b200.so`` (sm_100a only) in-tree with nvcc.
+
+Usage: ``python qcpinn-convection-diffusion-qiskit_b200/build.py [--force] [--verbose]``.
+The shared library is a plain C-ABI (include/qcpinn_b200.h); it does not link against torch.
+"""
+
+from __future__ import annotations
+
+import argparse
+import concurrent.futures as cf
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC = PKG_DIR / "csrc"
+BUILD_DIR = PKG_DIR / "csrc" / "build"
+LIB_PATH = PKG_DIR / "libqcpinn_b200.so"
+SOURCES = ["qcp_plan.cu", "qcp_point_f32.cu", "qcp_point_f64.cu", "qcp_state.cu"]
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = ARCH_FLAGS + [
+    "-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
+]
+
+
+def _nvcc() -> str:
+    cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(cand):
+        raise RuntimeError("nvcc not found; the qcpinn_b200 CUDA library cannot be built")
+    return cand
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    files = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh"))
+    files.append(PKG_DIR.parent / "include" / "qcpinn_b200.h")
+    for f in files:
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _compile(src: str, verbose: bool) -> Path:
+    obj = BUILD_DIR / (Path(src).stem + ".o")
+    cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed on {src}:\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        (BUILD_DIR / (Path(src).stem + ".ptxas.txt")).write_text(res.stderr)
+    return obj
+
+
+def build_library(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every CUDA source for sm_100a and link the shared library (idempotent)."""
+    BUILD_DIR.mkdir(parents=True, exist_ok=True)
+    stamp = BUILD_DIR / "digest.txt"
+    digest = _digest()
+    if not force and LIB_PATH.exists() and stamp.exists() and stamp.read_text() == digest:
+        return LIB_PATH
+    sources = [s for s in SOURCES if (CSRC / s).exists()]
+    with cf.ThreadPoolExecutor(max_workers=min(8, len(sources))) as pool:
+        objs = list(pool.map(lambda s: _compile(s, verbose), sources))
+    cmd = [_nvcc(), *ARCH_FLAGS, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-lcudart"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    stamp.write_text(digest)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--verbose", action="store_true", help="keep ptxas -v output in csrc/build/")
+    ns = ap.parse_args()
+    print(build_library(force=ns.force, verbose=ns.verbose))
+    sys.exit(0)

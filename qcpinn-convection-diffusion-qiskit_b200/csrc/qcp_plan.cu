@@ -1,0 +1,723 @@
+// qcpinn_b200 -- plans, the batch-shared circuit kernels and the C-ABI entry points.
+//
+// The trainable part of the DV circuit (reference nn/DVQuantumLayer.py:184-212: L ansatz layers,
+// optional Haar 4x4 blocks, Hadamard on the last wire) does not depend on the collocation point.
+// qcp_prepare() therefore simulates it ONCE per parameter update on the 2^n computational basis
+// states (columns of V), forms the Heisenberg observables O_i = V^dag Z_i V and projects them on
+// the encoding's feature basis -> the real matrix C consumed by the per-point kernels.
+// theta_grad_kernel() is its adjoint: C-bar -> Lambda = sum_i Z_i V R_i -> reverse gate sweep with
+// the generator trick  dL/dtheta_k = Im sum_a <lambda_a| H_k |psi_a>  (adjoint differentiation).
+// Both run in complex128 whatever the plan dtype; they cost microseconds.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "qcp_common.cuh"
+
+namespace qcp {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+#define QCP_CUDA(expr)                                                                    \
+  do {                                                                                    \
+    cudaError_t e_ = (expr);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return 1;                                                                           \
+    }                                                                                     \
+  } while (0)
+
+constexpr int kSetupThreads = 256;
+
+// ---------------------------------------------------------------------------------------------
+// complex helpers (double2 = re, im)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+
+struct Mat2 {
+  double2 m[4];   // row-major 2x2
+};
+
+__device__ inline Mat2 dagger(const Mat2& u) {
+  Mat2 r;
+  r.m[0] = cconj(u.m[0]); r.m[1] = cconj(u.m[2]);
+  r.m[2] = cconj(u.m[1]); r.m[3] = cconj(u.m[3]);
+  return r;
+}
+
+// 2x2 block of a (possibly controlled) gate, PennyLane conventions
+__device__ inline Mat2 gate_mat2(int kind, double theta) {
+  Mat2 u;
+  double s, c;
+  sincos(0.5 * theta, &s, &c);
+  const double2 z = make_double2(0.0, 0.0);
+  switch (kind) {
+    case QCP_GATE_RX: case QCP_GATE_CRX:
+      u.m[0] = make_double2(c, 0); u.m[1] = make_double2(0, -s);
+      u.m[2] = make_double2(0, -s); u.m[3] = make_double2(c, 0);
+      break;
+    case QCP_GATE_RY:
+      u.m[0] = make_double2(c, 0); u.m[1] = make_double2(-s, 0);
+      u.m[2] = make_double2(s, 0); u.m[3] = make_double2(c, 0);
+      break;
+    case QCP_GATE_RZ: case QCP_GATE_CRZ:
+      u.m[0] = make_double2(c, -s); u.m[1] = z; u.m[2] = z; u.m[3] = make_double2(c, s);
+      break;
+    case QCP_GATE_CNOT:
+      u.m[0] = z; u.m[1] = make_double2(1, 0); u.m[2] = make_double2(1, 0); u.m[3] = z;
+      break;
+    default: {  // Hadamard
+      const double h = 0.70710678118654752440;
+      u.m[0] = make_double2(h, 0); u.m[1] = make_double2(h, 0);
+      u.m[2] = make_double2(h, 0); u.m[3] = make_double2(-h, 0);
+    }
+  }
+  return u;
+}
+
+__device__ __forceinline__ int insert_zero_bit(int r, int pos) {
+  const int lo = r & ((1 << pos) - 1);
+  return ((r >> pos) << (pos + 1)) | lo;
+}
+
+// Apply one program op (or its dagger) to `ncol` state columns of length M = 2^n stored at
+// A[col*M + k].  Wire w <-> bit position n-1-w (wire 0 = most significant bit).
+template <typename TH>
+__device__ void apply_op(double2* A, int ncol, int n, const GateOp op, const TH* theta,
+                         const double2* consts, bool dag) {
+  const int M = 1 << n;
+  if (op.kind == QCP_GATE_U4) {
+    const int pa = n - 1 - op.a, pb = n - 1 - op.b;
+    const int plo = pa < pb ? pa : pb, phi = pa < pb ? pb : pa;
+    const double2* U = consts + 16 * op.p;
+    const int items = ncol * (M >> 2);
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int col = it / (M >> 2);
+      int r = it % (M >> 2);
+      int k = insert_zero_bit(insert_zero_bit(r, plo), phi);
+      double2* base = A + (size_t)col * M;
+      const int idx[4] = {k, k | (1 << pb), k | (1 << pa), k | (1 << pa) | (1 << pb)};
+      double2 v[4], o[4];
+      for (int j = 0; j < 4; ++j) v[j] = base[idx[j]];
+      for (int i = 0; i < 4; ++i) {
+        double2 acc = make_double2(0, 0);
+        for (int j = 0; j < 4; ++j) {
+          const double2 uij = dag ? cconj(U[j * 4 + i]) : U[i * 4 + j];
+          acc = cadd(acc, cmul(uij, v[j]));
+        }
+        o[i] = acc;
+      }
+      for (int j = 0; j < 4; ++j) base[idx[j]] = o[j];
+    }
+  } else {
+    const bool ctl = op.kind == QCP_GATE_CRX || op.kind == QCP_GATE_CRZ || op.kind == QCP_GATE_CNOT;
+    const int wt = ctl ? op.b : op.a;
+    const int pt = n - 1 - wt;
+    const int pc = ctl ? n - 1 - op.a : -1;
+    const double th = op.p >= 0 ? (double)theta[op.p] : 0.0;
+    Mat2 u = gate_mat2(op.kind, th);
+    if (dag) u = dagger(u);
+    const int items = ncol * (M >> 1);
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int col = it / (M >> 1);
+      const int k0 = insert_zero_bit(it % (M >> 1), pt);
+      if (ctl && !((k0 >> pc) & 1)) continue;
+      double2* base = A + (size_t)col * M;
+      const double2 v0 = base[k0], v1 = base[k0 | (1 << pt)];
+      base[k0] = cadd(cmul(u.m[0], v0), cmul(u.m[1], v1));
+      base[k0 | (1 << pt)] = cadd(cmul(u.m[2], v0), cmul(u.m[3], v1));
+    }
+  }
+  __syncthreads();
+}
+
+template <typename TH>
+__device__ void simulate_columns(double2* V, int n, const GateOp* ops, int n_ops, const TH* theta,
+                                 const double2* consts) {
+  const int M = 1 << n;
+  for (int i = threadIdx.x; i < M * M; i += blockDim.x)
+    V[i] = make_double2((i / M) == (i % M) ? 1.0 : 0.0, 0.0);
+  __syncthreads();
+  for (int g = 0; g < n_ops; ++g) apply_op(V, M, n, ops[g], theta, consts, false);
+}
+
+__device__ __forceinline__ int trit_of(int s, int j, int n) {
+  int d = 1;
+  for (int t = 0; t < n - 1 - j; ++t) d *= 3;
+  return (s / d) % 3;
+}
+
+// ---------------------------------------------------------------------------------------------
+// prepare: theta -> V -> O_i -> C
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kSetupThreads)
+prepare_kernel(int n, int enc, const GateOp* ops, int n_ops, const T* theta, const double2* consts,
+               double2* V, double2* O, double* C64, T* CT) {
+  const int M = 1 << n;
+  simulate_columns(V, n, ops, n_ops, theta, consts);
+
+  // O_i[b,a] = sum_k conj(V[k,b]) z_i(k) V[k,a]
+  for (int it = threadIdx.x; it < n * M * M; it += blockDim.x) {
+    const int i = it / (M * M), b = (it / M) % M, a = it % M;
+    const int pos = n - 1 - i;
+    double2 acc = make_double2(0, 0);
+    for (int k = 0; k < M; ++k) {
+      const double2 t = cmul(cconj(V[b * M + k]), V[a * M + k]);
+      const double sgn = ((k >> pos) & 1) ? -1.0 : 1.0;
+      acc.x += sgn * t.x; acc.y += sgn * t.y;
+    }
+    O[it] = acc;
+  }
+  __syncthreads();
+
+  const int F = num_features(n, enc);
+  for (int it = threadIdx.x; it < F * kCStride; it += blockDim.x) {
+    const int s = it / kCStride, i = it % kCStride;
+    double val = 0.0;
+    if (i < n) {
+      const double2* Oi = O + (size_t)i * M * M;
+      if (enc == QCP_ENC_ANGLE) {
+        // C[i,s] = 2^-n sum_a coef(s,a) O_i[b(a), a],  P_s[a,b] = prod_j sigma_{s_j}[a_j,b_j]
+        int ymask = 0, zmask = 0;
+        for (int j = 0; j < n; ++j) {
+          const int t = trit_of(s, j, n);
+          if (t == 1) ymask |= 1 << (n - 1 - j);
+          if (t == 2) zmask |= 1 << (n - 1 - j);
+        }
+        for (int a = 0; a < M; ++a) {
+          const int b = a ^ ymask;
+          // phase i^e: Z with a_j=1 -> -1 (e+=2); Y with a_j=0 -> -i (e+=3); Y with a_j=1 -> +i (e+=1)
+          const int e = 2 * __popc(a & zmask) + 3 * __popc(~a & ymask) + __popc(a & ymask);
+          const double2 o = Oi[b * M + a];
+          switch (e & 3) {
+            case 0: val += o.x; break;
+            case 1: val -= o.y; break;
+            case 2: val -= o.x; break;
+            default: val += o.y;
+          }
+        }
+        val /= (double)M;
+      } else {
+        // pair index s -> (a <= b); C = Re O[a,a] or 2 Re O[a,b]
+        int a = 0, rem = s;
+        while (rem >= n - a) { rem -= n - a; ++a; }
+        const int b = a + rem;
+        val = (a == b ? 1.0 : 2.0) * Oi[a * M + b].x;
+      }
+    }
+    C64[it] = val;
+    CT[it] = (T)val;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// reduce the per-block partial sums and scatter them to the caller's gradient tensors
+// ---------------------------------------------------------------------------------------------
+struct ScatterArgs {
+  void *w1, *b1, *w2, *b2, *w3, *b3, *w4, *b4;
+  double* Cbar;   // [F][n]
+  int n, H, F, grid, nacc;
+};
+
+template <typename T>
+__global__ void reduce_solver_kernel(const T* __restrict__ partials, const ScatterArgs a) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.nacc) return;
+  double s = 0.0;
+  for (int g = 0; g < a.grid; ++g) s += (double)partials[(size_t)g * a.nacc + idx];
+  const int n = a.n, H = a.H;
+  int r = idx;
+  if (r == 0) { static_cast<T*>(a.b4)[0] = (T)s; return; }
+  r -= 1;
+  if (r < H * (n + 2)) {
+    const int k = r / (n + 2), j = r % (n + 2);
+    if (j < n) static_cast<T*>(a.w3)[k * n + j] = (T)s;
+    else if (j == n) static_cast<T*>(a.b3)[k] = (T)s;
+    else static_cast<T*>(a.w4)[k] = (T)s;
+    return;
+  }
+  r -= H * (n + 2);
+  if (r < a.F * n) { a.Cbar[r] = s; return; }
+  r -= a.F * n;
+  if (r < n) { static_cast<T*>(a.b2)[r] = (T)s; return; }
+  r -= n;
+  {
+    const int k = r / (4 + n), j = r % (4 + n);
+    if (j < 3) static_cast<T*>(a.w1)[k * 3 + j] = (T)s;
+    else if (j == 3) static_cast<T*>(a.b1)[k] = (T)s;
+    else static_cast<T*>(a.w2)[(j - 4) * H + k] = (T)s;
+  }
+}
+
+template <typename T>
+__global__ void reduce_layer_kernel(const T* __restrict__ partials, double* Cbar, int grid, int nacc) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nacc) return;
+  double s = 0.0;
+  for (int g = 0; g < grid; ++g) s += (double)partials[(size_t)g * nacc + idx];
+  Cbar[idx] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// theta gradient: C-bar -> R_i -> Lambda -> reverse sweep
+// ---------------------------------------------------------------------------------------------
+__device__ double block_sum(double v, double* scratch) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += scratch[w];
+  return s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kSetupThreads)
+theta_grad_kernel(int n, int enc, const GateOp* ops, int n_ops, const T* theta, int n_theta,
+                  const double2* consts, const double* Cbar, double2* V, double2* R, double2* Lam,
+                  T* gtheta) {
+  __shared__ double scratch[kSetupThreads / 32];
+  const int M = 1 << n;
+  simulate_columns(V, n, ops, n_ops, theta, consts);
+
+  // R_i[b,a] = sum_s Cbar[i,s] E_s[b,a]
+  for (int it = threadIdx.x; it < n * M * M; it += blockDim.x) {
+    const int i = it / (M * M), b = (it / M) % M, a = it % M;
+    double2 acc = make_double2(0, 0);
+    if (enc == QCP_ENC_ANGLE) {
+      const int diff = a ^ b;
+      for (int m = 0; m < M; ++m) {
+        if (m & diff) continue;               // m marks the Z positions among a_j == b_j
+        int s = 0;
+        for (int j = 0; j < n; ++j) {
+          const int bit = 1 << (n - 1 - j);
+          const int t = (diff & bit) ? 1 : ((m & bit) ? 2 : 0);
+          s = s * 3 + t;
+        }
+        // P_s[b,a]: Z -> (-1)^{a_j}; Y -> sigma_Y[b_j,a_j] = -i if (b_j,a_j)=(0,1), +i if (1,0)
+        const int e = 2 * __popc(a & m) + 3 * __popc(a & ~b & diff) + __popc(b & ~a & diff);
+        const double c = Cbar[s * n + i];
+        switch (e & 3) {
+          case 0: acc.x += c; break;
+          case 1: acc.y += c; break;
+          case 2: acc.x -= c; break;
+          default: acc.y -= c;
+        }
+      }
+      acc.x /= (double)M; acc.y /= (double)M;
+    } else {
+      if (a < n && b < n) {
+        const int lo = a < b ? a : b, hi = a < b ? b : a;
+        const int s = lo * n - lo * (lo - 1) / 2 + (hi - lo);
+        acc.x = Cbar[s * n + i];
+      }
+    }
+    R[it] = acc;
+  }
+  __syncthreads();
+
+  // Lambda[:,a] = sum_i Z_i V R_i[:,a]
+  for (int it = threadIdx.x; it < M * M; it += blockDim.x) {
+    const int a = it / M, k = it % M;
+    double2 acc = make_double2(0, 0);
+    for (int i = 0; i < n; ++i) {
+      const double sgn = ((k >> (n - 1 - i)) & 1) ? -1.0 : 1.0;
+      double2 t = make_double2(0, 0);
+      const double2* Ri = R + (size_t)i * M * M;
+      for (int b = 0; b < M; ++b) t = cadd(t, cmul(V[b * M + k], Ri[b * M + a]));
+      acc.x += sgn * t.x; acc.y += sgn * t.y;
+    }
+    Lam[it] = acc;
+  }
+  __syncthreads();
+
+  for (int p = threadIdx.x; p < n_theta; p += blockDim.x) gtheta[p] = (T)0;
+  __syncthreads();
+
+  for (int g = n_ops - 1; g >= 0; --g) {
+    const GateOp op = ops[g];
+    if (op.p >= 0 && op.kind != QCP_GATE_U4) {
+      // dL/dtheta = Im sum_cols <lambda| H |psi>, both taken AFTER the gate
+      const bool ctl = op.kind == QCP_GATE_CRX || op.kind == QCP_GATE_CRZ;
+      const int pt = n - 1 - (ctl ? op.b : op.a);
+      const int pc = ctl ? n - 1 - op.a : -1;
+      double part = 0.0;
+      for (int it = threadIdx.x; it < M * M; it += blockDim.x) {
+        const int k = it % M;
+        if (ctl && !((k >> pc) & 1)) continue;
+        const size_t col = (size_t)(it / M) * M;
+        const int bit = (k >> pt) & 1;
+        double2 hpsi;
+        if (op.kind == QCP_GATE_RX || op.kind == QCP_GATE_CRX) {
+          hpsi = V[col + (k ^ (1 << pt))];
+        } else if (op.kind == QCP_GATE_RY) {
+          const double2 o = V[col + (k ^ (1 << pt))];
+          hpsi = bit ? make_double2(-o.y, o.x) : make_double2(o.y, -o.x);   // +i o : -i o
+        } else {
+          const double2 o = V[col + k];
+          hpsi = bit ? make_double2(-o.x, -o.y) : o;
+        }
+        const double2 l = Lam[col + k];
+        part += l.x * hpsi.y - l.y * hpsi.x;   // Im(conj(l) * hpsi)
+      }
+      const double tot = block_sum(part, scratch);
+      if (threadIdx.x == 0) gtheta[op.p] = (T)((double)gtheta[op.p] + tot);
+    }
+    apply_op(V, M, n, op, theta, consts, true);
+    apply_op(Lam, M, n, op, theta, consts, true);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FMA-pipe micro-benchmark (roofline denominator)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void fma_bench_kernel(T* out, int iters, T b, T c) {
+  T a[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) a[j] = T(threadIdx.x + j) * T(1e-3);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = fma(a[j], b, c);
+  }
+  T s = T(0);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s += a[j];
+  if (s == T(-1.2345)) out[0] = s;   // never true; keeps the chain alive
+}
+
+}  // namespace qcp
+
+// =============================================================================================
+// C-ABI
+// =============================================================================================
+using namespace qcp;
+
+struct qcp_plan {
+  int n, enc, dtype, H, n_ops, n_consts, n_theta, F, M;
+  int num_sms;
+  GateOp* d_ops;
+  double2* d_consts;
+  double2 *d_V, *d_O, *d_Lam;
+  double* d_C64;
+  void* d_C;
+  double* d_Cbar;
+  void* d_partials;
+  size_t partials_elems;
+  int grid_cache[2];   // persistent grid of the backward kernel per mode (0: value, 1: residual)
+  bool prepared;
+};
+
+static size_t elem_size(int dtype) { return dtype == QCP_F64 ? sizeof(double) : sizeof(float); }
+
+static int ensure_partials(qcp_plan* p, size_t elems) {
+  if (elems <= p->partials_elems) return 0;
+  if (p->d_partials) cudaFree(p->d_partials);
+  p->d_partials = nullptr;
+  p->partials_elems = 0;
+  QCP_CUDA(cudaMalloc(&p->d_partials, elems * elem_size(p->dtype)));
+  p->partials_elems = elems;
+  return 0;
+}
+
+extern "C" {
+
+const char* qcp_last_error(void) { return g_error; }
+
+int qcp_version(void) { return 100; }
+
+int qcp_device_count(void) {
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return c;
+}
+
+int qcp_plan_create(qcp_plan_t** out, int n_qubits, int encoding, int dtype, int hidden,
+                    const int32_t* ops, int n_ops, const double* consts, int n_consts,
+                    int n_theta) {
+  if (!out) { set_error("qcp_plan_create: out is NULL"); return 1; }
+  *out = nullptr;
+  if (n_qubits < 2 || n_qubits > kMaxQubitsFused) {
+    set_error("qcp_plan_create: fused engine supports 2..%d qubits, got %d", kMaxQubitsFused, n_qubits);
+    return 1;
+  }
+  if (encoding != QCP_ENC_ANGLE && encoding != QCP_ENC_AMPLITUDE) {
+    set_error("qcp_plan_create: bad encoding %d", encoding); return 1;
+  }
+  if (dtype != QCP_F32 && dtype != QCP_F64) { set_error("qcp_plan_create: bad dtype %d", dtype); return 1; }
+  if (hidden < 1 || hidden > kMaxHidden) {
+    set_error("qcp_plan_create: hidden width %d outside 1..%d", hidden, kMaxHidden); return 1;
+  }
+  if (n_ops < 0 || (n_ops > 0 && !ops)) { set_error("qcp_plan_create: bad ops"); return 1; }
+  for (int g = 0; g < n_ops; ++g) {
+    const int32_t* o = ops + 4 * g;
+    const int kind = o[0];
+    const bool two = kind == QCP_GATE_CRX || kind == QCP_GATE_CRZ || kind == QCP_GATE_CNOT || kind == QCP_GATE_U4;
+    const bool par = kind == QCP_GATE_RX || kind == QCP_GATE_RY || kind == QCP_GATE_RZ ||
+                     kind == QCP_GATE_CRX || kind == QCP_GATE_CRZ;
+    if (kind < 0 || kind > QCP_GATE_U4 || o[1] < 0 || o[1] >= n_qubits ||
+        (two && (o[2] < 0 || o[2] >= n_qubits || o[2] == o[1])) ||
+        (par && (o[3] < 0 || o[3] >= n_theta)) ||
+        (kind == QCP_GATE_U4 && (o[3] < 0 || o[3] >= n_consts))) {
+      set_error("qcp_plan_create: op %d (%d,%d,%d,%d) is invalid", g, o[0], o[1], o[2], o[3]);
+      return 1;
+    }
+  }
+  int dev = 0;
+  QCP_CUDA(cudaGetDevice(&dev));
+  qcp_plan* p = new (std::nothrow) qcp_plan();
+  if (!p) { set_error("qcp_plan_create: out of host memory"); return 1; }
+  memset(p, 0, sizeof(*p));
+  p->n = n_qubits; p->enc = encoding; p->dtype = dtype; p->H = hidden;
+  p->n_ops = n_ops; p->n_consts = n_consts; p->n_theta = n_theta;
+  p->F = num_features(n_qubits, encoding);
+  p->M = 1 << n_qubits;
+  cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t MM = (size_t)p->M * p->M;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes ? bytes : 16); };
+  alloc((void**)&p->d_ops, sizeof(GateOp) * n_ops);
+  alloc((void**)&p->d_consts, sizeof(double2) * 16 * n_consts);
+  alloc((void**)&p->d_V, sizeof(double2) * MM);
+  alloc((void**)&p->d_O, sizeof(double2) * MM * n_qubits);
+  alloc((void**)&p->d_Lam, sizeof(double2) * MM);
+  alloc((void**)&p->d_C64, sizeof(double) * p->F * kCStride);
+  alloc((void**)&p->d_C, elem_size(dtype) * p->F * kCStride);
+  alloc((void**)&p->d_Cbar, sizeof(double) * p->F * n_qubits);
+  if (e == cudaSuccess && n_ops) e = cudaMemcpy(p->d_ops, ops, sizeof(GateOp) * n_ops, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && n_consts)
+    e = cudaMemcpy(p->d_consts, consts, sizeof(double2) * 16 * n_consts, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    set_error("qcp_plan_create: CUDA allocation/copy failed: %s", cudaGetErrorString(e));
+    qcp_plan_destroy(p);
+    return 1;
+  }
+  *out = p;
+  return 0;
+}
+
+int qcp_plan_destroy(qcp_plan_t* p) {
+  if (!p) return 0;
+  cudaFree(p->d_ops); cudaFree(p->d_consts); cudaFree(p->d_V); cudaFree(p->d_O); cudaFree(p->d_Lam);
+  cudaFree(p->d_C64); cudaFree(p->d_C); cudaFree(p->d_Cbar); cudaFree(p->d_partials);
+  delete p;
+  return 0;
+}
+
+int qcp_plan_num_features(const qcp_plan_t* p) { return p ? p->F : -1; }
+
+int qcp_prepare(qcp_plan_t* p, const void* theta, void* stream) {
+  if (!p || (!theta && p->n_theta > 0)) { set_error("qcp_prepare: NULL argument"); return 1; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p->dtype == QCP_F64)
+    prepare_kernel<double><<<1, kSetupThreads, 0, s>>>(p->n, p->enc, p->d_ops, p->n_ops,
+        static_cast<const double*>(theta), p->d_consts, p->d_V, p->d_O, p->d_C64,
+        static_cast<double*>(p->d_C));
+  else
+    prepare_kernel<float><<<1, kSetupThreads, 0, s>>>(p->n, p->enc, p->d_ops, p->n_ops,
+        static_cast<const float*>(theta), p->d_consts, p->d_V, p->d_O, p->d_C64,
+        static_cast<float*>(p->d_C));
+  QCP_CUDA(cudaGetLastError());
+  p->prepared = true;
+  return 0;
+}
+
+int qcp_feature_matrix(qcp_plan_t* p, double* out_host, void* stream) {
+  if (!p || !out_host) { set_error("qcp_feature_matrix: NULL argument"); return 1; }
+  if (!p->prepared) { set_error("qcp_feature_matrix: qcp_prepare() has not run"); return 1; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t cnt = (size_t)p->F * kCStride;
+  double* tmp = new double[cnt];
+  cudaError_t e = cudaMemcpyAsync(tmp, p->d_C64, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) {
+    delete[] tmp;
+    set_error("qcp_feature_matrix: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  for (int i = 0; i < p->n; ++i)
+    for (int f = 0; f < p->F; ++f) out_host[(size_t)i * p->F + f] = tmp[(size_t)f * kCStride + i];
+  delete[] tmp;
+  return 0;
+}
+
+static int forward_grid(const qcp_plan* p, long long B) {
+  long long blocks = (B + kThreads - 1) / kThreads;
+  const long long cap = (long long)p->num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+int qcp_layer_forward(qcp_plan_t* p, const void* z, long long B, void* q, void* stream) {
+  if (!p || !z || !q) { set_error("qcp_layer_forward: NULL argument"); return 1; }
+  if (!p->prepared) { set_error("qcp_layer_forward: qcp_prepare() has not run"); return 1; }
+  if (B <= 0) return 0;
+  LayerArgs a{};
+  a.z = z; a.C = p->d_C; a.q = q; a.B = B;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return p->dtype == QCP_F64 ? launch_layer_forward<double>(p->n, p->enc, a, forward_grid(p, B), s)
+                             : launch_layer_forward<float>(p->n, p->enc, a, forward_grid(p, B), s);
+}
+
+static int run_theta_grad(qcp_plan* p, const void* theta, void* gtheta, cudaStream_t s) {
+  if (p->dtype == QCP_F64)
+    theta_grad_kernel<double><<<1, kSetupThreads, 0, s>>>(p->n, p->enc, p->d_ops, p->n_ops,
+        static_cast<const double*>(theta), p->n_theta, p->d_consts, p->d_Cbar, p->d_V, p->d_O,
+        p->d_Lam, static_cast<double*>(gtheta));
+  else
+    theta_grad_kernel<float><<<1, kSetupThreads, 0, s>>>(p->n, p->enc, p->d_ops, p->n_ops,
+        static_cast<const float*>(theta), p->n_theta, p->d_consts, p->d_Cbar, p->d_V, p->d_O,
+        p->d_Lam, static_cast<float*>(gtheta));
+  QCP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int qcp_layer_backward(qcp_plan_t* p, const void* theta, const void* z, const void* grad_q,
+                       long long B, void* grad_z, void* grad_theta, void* stream) {
+  if (!p || !theta || !z || !grad_q || !grad_theta) { set_error("qcp_layer_backward: NULL argument"); return 1; }
+  if (!p->prepared) { set_error("qcp_layer_backward: qcp_prepare() has not run"); return 1; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int nacc = p->F * p->n;
+  if (B <= 0) {
+    QCP_CUDA(cudaMemsetAsync(grad_theta, 0, elem_size(p->dtype) * p->n_theta, s));
+    return 0;
+  }
+  long long blocks = (B + kThreads - 1) / kThreads;
+  if (blocks > (long long)p->num_sms * 4) blocks = (long long)p->num_sms * 4;
+  const int grid = (int)blocks;
+  if (ensure_partials(p, (size_t)grid * nacc)) return 1;
+  LayerArgs a{};
+  a.z = z; a.C = p->d_C; a.gq = grad_q; a.gz = grad_z; a.partials = p->d_partials; a.B = B;
+  int rc = p->dtype == QCP_F64 ? launch_layer_backward<double>(p->n, p->enc, a, grid, s)
+                               : launch_layer_backward<float>(p->n, p->enc, a, grid, s);
+  if (rc) return rc;
+  const int rb = (nacc + 127) / 128;
+  if (p->dtype == QCP_F64)
+    reduce_layer_kernel<double><<<rb, 128, 0, s>>>(static_cast<const double*>(p->d_partials), p->d_Cbar, grid, nacc);
+  else
+    reduce_layer_kernel<float><<<rb, 128, 0, s>>>(static_cast<const float*>(p->d_partials), p->d_Cbar, grid, nacc);
+  QCP_CUDA(cudaGetLastError());
+  return run_theta_grad(p, theta, grad_theta, s);
+}
+
+static void fill_solver_args(SolverArgs& a, const qcp_plan* p, const qcp_mlp_t* w, const void* X,
+                             long long B, const double* c) {
+  a.X = X; a.w1 = w->w1; a.b1 = w->b1; a.w2 = w->w2; a.b2 = w->b2;
+  a.w3 = w->w3; a.b3 = w->b3; a.w4 = w->w4; a.b4 = w->b4;
+  a.C = p->d_C; a.B = B; a.H = p->H;
+  if (c) { a.pde.ct = c[0]; a.pde.cx = c[1]; a.pde.cy = c[2]; a.pde.cxx = c[3]; a.pde.cyy = c[4]; }
+}
+
+static int check_mode(int mode, const double* coeffs, const char* who) {
+  if (mode != QCP_MODE_VALUE && mode != QCP_MODE_RESIDUAL) { set_error("%s: bad mode %d", who, mode); return 1; }
+  if (mode == QCP_MODE_RESIDUAL && !coeffs) { set_error("%s: residual mode needs coeffs", who); return 1; }
+  return 0;
+}
+
+int qcp_solver_forward(qcp_plan_t* p, const qcp_mlp_t* w, const void* X, long long B, int mode,
+                       const double* coeffs, void* u, void* r, void* streams, void* stream) {
+  if (!p || !w || !X || !u) { set_error("qcp_solver_forward: NULL argument"); return 1; }
+  if (!p->prepared) { set_error("qcp_solver_forward: qcp_prepare() has not run"); return 1; }
+  if (check_mode(mode, coeffs, "qcp_solver_forward")) return 1;
+  if (B <= 0) return 0;
+  SolverArgs a{};
+  fill_solver_args(a, p, w, X, B, coeffs);
+  a.u = u; a.r = r; a.streams = streams;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = forward_grid(p, B);
+  return p->dtype == QCP_F64 ? launch_solver_forward<double>(p->n, p->enc, mode, a, grid, s)
+                             : launch_solver_forward<float>(p->n, p->enc, mode, a, grid, s);
+}
+
+int qcp_solver_backward(qcp_plan_t* p, const qcp_mlp_t* w, const void* theta, const void* X,
+                        const void* grad_u, const void* grad_r, long long B, int mode,
+                        const double* coeffs, const qcp_mlp_t* g, void* grad_theta, void* grad_X,
+                        void* stream) {
+  if (!p || !w || !theta || !X || !g || !grad_theta) { set_error("qcp_solver_backward: NULL argument"); return 1; }
+  if (!p->prepared) { set_error("qcp_solver_backward: qcp_prepare() has not run"); return 1; }
+  if (check_mode(mode, coeffs, "qcp_solver_backward")) return 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int nacc = nacc_solver(p->n, p->enc, p->H);
+  int& cached = p->grid_cache[mode == QCP_MODE_RESIDUAL ? 1 : 0];
+  if (cached == 0)
+    cached = p->dtype == QCP_F64
+                 ? solver_backward_max_grid<double>(p->n, p->enc, mode, p->H, p->num_sms)
+                 : solver_backward_max_grid<float>(p->n, p->enc, mode, p->H, p->num_sms);
+  long long blocks = (B + kThreads - 1) / kThreads;
+  if (blocks > cached) blocks = cached;
+  if (blocks < 1) blocks = 1;
+  const int grid = (int)blocks;
+  if (ensure_partials(p, (size_t)grid * nacc)) return 1;
+  SolverArgs a{};
+  fill_solver_args(a, p, w, X, B > 0 ? B : 0, coeffs);
+  a.gu = grad_u; a.gr = grad_r; a.gX = grad_X; a.partials = p->d_partials;
+  if (B > 0) {
+    int rc = p->dtype == QCP_F64 ? launch_solver_backward<double>(p->n, p->enc, mode, a, grid, s)
+                                 : launch_solver_backward<float>(p->n, p->enc, mode, a, grid, s);
+    if (rc) return rc;
+  } else {
+    QCP_CUDA(cudaMemsetAsync(p->d_partials, 0, elem_size(p->dtype) * (size_t)grid * nacc, s));
+  }
+  ScatterArgs sc{};
+  sc.w1 = g->w1; sc.b1 = g->b1; sc.w2 = g->w2; sc.b2 = g->b2;
+  sc.w3 = g->w3; sc.b3 = g->b3; sc.w4 = g->w4; sc.b4 = g->b4;
+  sc.Cbar = p->d_Cbar; sc.n = p->n; sc.H = p->H; sc.F = p->F; sc.grid = grid; sc.nacc = nacc;
+  const int rb = (nacc + 127) / 128;
+  if (p->dtype == QCP_F64)
+    reduce_solver_kernel<double><<<rb, 128, 0, s>>>(static_cast<const double*>(p->d_partials), sc);
+  else
+    reduce_solver_kernel<float><<<rb, 128, 0, s>>>(static_cast<const float*>(p->d_partials), sc);
+  QCP_CUDA(cudaGetLastError());
+  return run_theta_grad(p, theta, grad_theta, s);
+}
+
+int qcp_bench_fma(int dtype, int iters, double* flops_per_s, void* stream) {
+  if (!flops_per_s || iters < 1) { set_error("qcp_bench_fma: bad argument"); return 1; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 0;
+  QCP_CUDA(cudaGetDevice(&dev));
+  QCP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  void* out = nullptr;
+  QCP_CUDA(cudaMalloc(&out, 64));
+  cudaEvent_t e0, e1;
+  QCP_CUDA(cudaEventCreate(&e0));
+  QCP_CUDA(cudaEventCreate(&e1));
+  const int blocks = sms * 8, threads = 256;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, s);
+    if (dtype == QCP_F64)
+      fma_bench_kernel<double><<<blocks, threads, 0, s>>>(static_cast<double*>(out), iters, 1.0000001, 1e-9);
+    else
+      fma_bench_kernel<float><<<blocks, threads, 0, s>>>(static_cast<float*>(out), iters, 1.0000001f, 1e-9f);
+    cudaEventRecord(e1, s);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) { set_error("qcp_bench_fma: %s", cudaGetErrorString(e)); cudaFree(out); return 1; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 16.0 * (double)iters * blocks * threads / (ms * 1e-3);
+    if (rep > 0 && fl > best) best = fl;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  *flops_per_s = best;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+"""Collocation samplers and the analytic convection-diffusion target (reference
+data/diffusion_dataset.py:5-56).  Cheap element-wise torch work that stays on the model's device.
+
+Gaussian pulse ``u = exp(-100((x-.5)^2 + (y-.5)^2)) exp(-t)``; forcing
+``r = u_t + v_x u_x + v_y u_y - D (u_xx + u_yy)`` in closed form.
+"""
+
+import torch
+
+default_D = 0.01
+default_v_x = 1.0
+default_v_y = 1.0
+
+
+class Sampler:
+    """Uniform points in the axis-aligned box ``coords`` (2, dim) with targets ``func(points)``."""
+
+    def __init__(self, dim, coords, func, name=None, device="cpu"):
+        self.dim = dim
+        self.coords = coords
+        self.func = func
+        self.name = name
+        self.device = device
+
+    def sample(self, N):
+        lo, hi = self.coords[0:1, :], self.coords[1:2, :]
+        pts = torch.rand(N, self.dim, device=self.device)
+        pts = lo + (hi - lo) * pts
+        return pts, self.func(pts.to(self.device))
+
+
+def _pulse(txy):
+    dx = txy[:, 1:2] - 0.5
+    dy = txy[:, 2:3] - 0.5
+    return dx, dy, torch.exp(-100 * (dx ** 2 + dy ** 2)) * torch.exp(-txy[:, 0:1])
+
+
+def u(txy):
+    return _pulse(txy)[2]
+
+
+def u_t(txy):
+    return -u(txy)
+
+
+def u_x(txy):
+    dx, _, val = _pulse(txy)
+    return -200 * dx * val
+
+
+def u_y(txy):
+    _, dy, val = _pulse(txy)
+    return -200 * dy * val
+
+
+def u_xx(txy):
+    dx, _, val = _pulse(txy)
+    return (40000 * dx ** 2 - 400) * val
+
+
+def u_yy(txy):
+    _, dy, val = _pulse(txy)
+    return (40000 * dy ** 2 - 400) * val
+
+
+def r(txy, Diffusion=default_D, v_x=default_v_x, v_y=default_v_y):
+    dx, dy, val = _pulse(txy)
+    lap = (40000 * dx ** 2 - 400) * val + (40000 * dy ** 2 - 400) * val
+    return -val + v_x * (-200 * dx * val) + v_y * (-200 * dy * val) - Diffusion * lap
+
+
+def _box(lo, hi, device):
+    return torch.tensor([lo, hi], dtype=torch.float32, device=device)
+
+
+def training_boxes(device):
+    """The four boxes of reference trainer/diffusion_train.py:9-20 (t, x, y order)."""
+    return {
+        "ics": _box([0.0, 0.0, 0.0], [0.0, 1.0, 1.0], device),
+        "bc1": _box([0.0, 0.0, 0.0], [1.0, 0.0, 1.0], device),
+        "bc2": _box([0.0, 1.0, 0.0], [1.0, 1.0, 1.0], device),
+        "dom": _box([0.0, 0.0, 0.0], [1.0, 1.0, 1.0], device),
+    }
+
+
+def generate_training_dataset(device):
+    b = training_boxes(device)
+    ics_sampler = Sampler(3, b["ics"], u, name="Initial Condition", device=device)
+    bc1 = Sampler(3, b["bc1"], u, name="Dirichlet BC1", device=device)
+    bc2 = Sampler(3, b["bc2"], u, name="Dirichlet BC2", device=device)
+    res_sampler = Sampler(3, b["dom"], r, name="Forcing", device=device)
+    return [ics_sampler, [bc1, bc2], res_sampler]

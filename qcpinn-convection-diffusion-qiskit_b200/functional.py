@@ -1,0 +1,287 @@
+"""Plans and ``torch.autograd.Function`` wrappers over the C-ABI (PyTorch is plumbing only).
+
+``Plan`` owns one ``qcp_plan_t`` (compiled gate program + device workspaces).  The three autograd
+functions mirror the three ways the reference enters its hot path:
+
+* ``layer_apply``      -- ``DVQuantumLayer.forward``            (reference nn/DVQuantumLayer.py:151-154)
+* ``solver_value``     -- ``DVPDESolver.forward``               (reference nn/DVPDESolver.py:81-110)
+* ``solver_residual``  -- ``diffusion_operator(model, t, x, y)`` (reference nn/pde.py:53-72)
+
+Backward passes are hand-written adjoint kernels (first order only: the residual already carries
+the second derivatives forward in Taylor mode, so nothing needs to be differentiated twice).
+"""
+
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from .program import ENC_AMPLITUDE, ENC_ANGLE, CircuitProgram
+
+MODE_VALUE, MODE_RESIDUAL = 1, 6
+_DTYPE_CODE = {torch.float32: 0, torch.float64: 1}
+MLP_NAMES = ("w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4")
+
+launch_counter = 0   # CUDA kernels launched by this library (bench.py reports it as gpu_launches)
+
+
+def _count(n: int) -> None:
+    global launch_counter
+    launch_counter += n
+
+
+def encoding_code(name) -> int:
+    # reference nn/DVQuantumLayer.py:177-182: anything but "amplitude" (incl. "None") means angle
+    return ENC_AMPLITUDE if name == "amplitude" else ENC_ANGLE
+
+
+class Plan:
+    """One compiled circuit on one device for one dtype."""
+
+    def __init__(self, program: CircuitProgram, encoding: int, dtype: torch.dtype, hidden: int,
+                 device: torch.device):
+        if dtype not in _DTYPE_CODE:
+            raise ValueError(f"qcpinn_b200 supports float32/float64 plans, got {dtype}")
+        self.lib = _lib.require_cuda()
+        self.program = program
+        self.encoding = encoding
+        self.dtype = dtype
+        self.hidden = int(hidden)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError(
+                f"qcpinn_b200 runs on CUDA devices only (got {self.device}); there is no CPU path")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.n = program.n_qubits
+        self.n_theta = program.n_theta
+        self._handle = ctypes.c_void_p()
+        self._key = None
+        ops = np.ascontiguousarray(program.ops, dtype=np.int32)
+        consts = np.ascontiguousarray(program.consts, dtype=np.complex128).view(np.float64)
+        with torch.cuda.device(self.device):
+            rc = self.lib.qcp_plan_create(
+                ctypes.byref(self._handle), self.n, encoding, _DTYPE_CODE[dtype], self.hidden,
+                ops.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ops.shape[0],
+                consts.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), program.consts.shape[0],
+                self.n_theta)
+        _lib.check(rc, "qcp_plan_create")
+        self.num_features = self.lib.qcp_plan_num_features(self._handle)
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        try:
+            if h is not None and h.value:
+                self.lib.qcp_plan_destroy(h)
+                h.value = None
+        except Exception:   # interpreter shutdown: ctypes may already be torn down
+            pass
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _t(self, x: torch.Tensor) -> torch.Tensor:
+        if x.device != self.device:
+            raise RuntimeError(f"tensor on {x.device}, plan on {self.device}")
+        return x.detach().to(self.dtype).contiguous()
+
+    def invalidate(self):
+        self._key = None
+
+    def prepare(self, theta: torch.Tensor, key=None) -> None:
+        """theta (dtype T, n_theta) -> feature matrix C.  ``key`` lets callers skip repeats."""
+        if key is not None and key == self._key:
+            return
+        if theta.numel() != self.n_theta:
+            raise ValueError(f"expected {self.n_theta} circuit angles, got {theta.numel()}")
+        with torch.cuda.device(self.device):
+            rc = self.lib.qcp_prepare(self._handle, ctypes.c_void_p(theta.data_ptr()), self._stream())
+        _lib.check(rc, "qcp_prepare")
+        _count(1)
+        self._key = key
+
+    def feature_matrix(self) -> torch.Tensor:
+        out = np.empty((self.n, self.num_features), dtype=np.float64)
+        with torch.cuda.device(self.device):
+            rc = self.lib.qcp_feature_matrix(
+                self._handle, out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), self._stream())
+        _lib.check(rc, "qcp_feature_matrix")
+        return torch.from_numpy(out)
+
+    def _mlp(self, tensors) -> _lib.QcpMlp:
+        m = _lib.QcpMlp()
+        for name, t in zip(MLP_NAMES, tensors):
+            setattr(m, name, t.data_ptr())
+        return m
+
+    # -- raw calls (tensors already dtype T, contiguous, on device) ----------------------------
+    def layer_forward(self, z):
+        b = z.shape[0]
+        q = torch.empty((self.n, b), dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.qcp_layer_forward(self._handle, ctypes.c_void_p(z.data_ptr()), b,
+                                            ctypes.c_void_p(q.data_ptr()), self._stream())
+        _lib.check(rc, "qcp_layer_forward")
+        _count(1 if b else 0)
+        return q
+
+    def layer_backward(self, theta, z, grad_q, need_gz=True):
+        b = z.shape[0]
+        gz = torch.empty_like(z) if need_gz else None
+        gtheta = torch.empty(self.n_theta, dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.qcp_layer_backward(
+                self._handle, ctypes.c_void_p(theta.data_ptr()), ctypes.c_void_p(z.data_ptr()),
+                ctypes.c_void_p(grad_q.data_ptr()), b,
+                ctypes.c_void_p(gz.data_ptr() if gz is not None else None),
+                ctypes.c_void_p(gtheta.data_ptr()), self._stream())
+        _lib.check(rc, "qcp_layer_backward")
+        _count(3 if b else 1)
+        return gz, gtheta
+
+    def solver_forward(self, X, mlp, mode, coeffs=None, want_streams=False):
+        b = X.shape[0]
+        u = torch.empty(b, dtype=self.dtype, device=self.device)
+        r = torch.empty(b, dtype=self.dtype, device=self.device) if mode == MODE_RESIDUAL else None
+        streams = (torch.empty((b, 6), dtype=self.dtype, device=self.device)
+                   if (want_streams and mode == MODE_RESIDUAL) else None)
+        c = (ctypes.c_double * 5)(*coeffs) if coeffs is not None else None
+        m = self._mlp(mlp)
+        with torch.cuda.device(self.device):
+            rc = self.lib.qcp_solver_forward(
+                self._handle, ctypes.byref(m), ctypes.c_void_p(X.data_ptr()), b, mode, c,
+                ctypes.c_void_p(u.data_ptr()),
+                ctypes.c_void_p(r.data_ptr() if r is not None else None),
+                ctypes.c_void_p(streams.data_ptr() if streams is not None else None),
+                self._stream())
+        _lib.check(rc, "qcp_solver_forward")
+        _count(1 if b else 0)
+        return u, r, streams
+
+    def solver_backward(self, X, mlp, theta, grad_u, grad_r, mode, coeffs=None, need_gx=False):
+        b = X.shape[0]
+        sizes = [t.numel() for t in mlp] + [self.n_theta]
+        flat = torch.empty(sum(sizes), dtype=self.dtype, device=self.device)
+        views, off = [], 0
+        for t, sz in zip(list(mlp) + [theta], sizes):
+            views.append(flat[off:off + sz].view(t.shape))
+            off += sz
+        gx = torch.empty_like(X) if need_gx else None
+        c = (ctypes.c_double * 5)(*coeffs) if coeffs is not None else None
+        m = self._mlp(mlp)
+        g = self._mlp(views[:8])
+        with torch.cuda.device(self.device):
+            rc = self.lib.qcp_solver_backward(
+                self._handle, ctypes.byref(m), ctypes.c_void_p(theta.data_ptr()),
+                ctypes.c_void_p(X.data_ptr()),
+                ctypes.c_void_p(grad_u.data_ptr() if grad_u is not None else None),
+                ctypes.c_void_p(grad_r.data_ptr() if grad_r is not None else None),
+                b, mode, c, ctypes.byref(g), ctypes.c_void_p(views[8].data_ptr()),
+                ctypes.c_void_p(gx.data_ptr() if gx is not None else None), self._stream())
+        _lib.check(rc, "qcp_solver_backward")
+        _count(3)
+        return views, gx
+
+
+def _grad_in(plan: Plan, g, like):
+    if g is None:
+        return None
+    return g.detach().to(plan.dtype).reshape(like).contiguous()
+
+
+class _LayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan: Plan, key, z, theta):
+        zt, tt = plan._t(z), plan._t(theta).reshape(-1)
+        plan.prepare(tt, key)
+        ctx.plan, ctx.key = plan, key
+        ctx.save_for_backward(zt, tt)
+        ctx.in_dtypes = (z.dtype, theta.dtype)
+        ctx.theta_shape = theta.shape
+        return plan.layer_forward(zt)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_q):
+        plan = ctx.plan
+        zt, tt = ctx.saved_tensors
+        plan.prepare(tt, ctx.key)
+        gq = _grad_in(plan, grad_q, (plan.n, zt.shape[0]))
+        gz, gtheta = plan.layer_backward(tt, zt, gq, need_gz=ctx.needs_input_grad[2])
+        gz = gz.to(ctx.in_dtypes[0]) if gz is not None else None
+        gtheta = gtheta.to(ctx.in_dtypes[1]).view(ctx.theta_shape) if ctx.needs_input_grad[3] else None
+        return None, None, gz, gtheta
+
+
+class _SolverFn(torch.autograd.Function):
+    """mode VALUE -> u (B,1);  mode RESIDUAL -> (u, r), both (B,1)."""
+
+    @staticmethod
+    def forward(ctx, plan: Plan, key, mode, coeffs, X, theta, *mlp):
+        Xt = plan._t(X)
+        tt = plan._t(theta).reshape(-1)
+        mt = [plan._t(w) for w in mlp]
+        plan.prepare(tt, key)
+        u, r, _ = plan.solver_forward(Xt, mt, mode, coeffs)
+        ctx.plan, ctx.key, ctx.mode, ctx.coeffs = plan, key, mode, coeffs
+        ctx.save_for_backward(Xt, tt, *mt)
+        ctx.in_dtypes = [X.dtype, theta.dtype] + [w.dtype for w in mlp]
+        ctx.theta_shape = theta.shape
+        if mode == MODE_RESIDUAL:
+            return u.view(-1, 1), r.view(-1, 1)
+        return u.view(-1, 1)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_u, grad_r=None):
+        plan = ctx.plan
+        Xt, tt, *mt = ctx.saved_tensors
+        plan.prepare(tt, ctx.key)
+        b = Xt.shape[0]
+        gu = _grad_in(plan, grad_u, (b,))
+        gr = _grad_in(plan, grad_r, (b,)) if ctx.mode == MODE_RESIDUAL else None
+        need_gx = ctx.needs_input_grad[4] and ctx.mode == MODE_VALUE
+        views, gx = plan.solver_backward(Xt, mt, tt, gu, gr, ctx.mode, ctx.coeffs, need_gx)
+        dt = ctx.in_dtypes
+        gX = gx.to(dt[0]) if gx is not None else None
+        gtheta = views[8].to(dt[1]).view(ctx.theta_shape) if ctx.needs_input_grad[5] else None
+        gm = [v.to(d) if need else None
+              for v, d, need in zip(views[:8], dt[2:], ctx.needs_input_grad[6:])]
+        return (None, None, None, None, gX, gtheta, *gm)
+
+
+def layer_apply(plan: Plan, z, theta, key=None):
+    return _LayerFn.apply(plan, key, z, theta)
+
+
+def solver_value(plan: Plan, X, theta, mlp, key=None):
+    return _SolverFn.apply(plan, key, MODE_VALUE, None, X, theta, *mlp)
+
+
+def solver_residual(plan: Plan, X, theta, mlp, coeffs, key=None):
+    return _SolverFn.apply(plan, key, MODE_RESIDUAL, tuple(float(c) for c in coeffs), X, theta, *mlp)
+
+
+def solver_streams(plan: Plan, X, theta, mlp, coeffs=(1.0, 1.0, 1.0, -0.01, -0.01)):
+    """No-grad helper for tests / evaluation: (u, r, streams[B,6])."""
+    Xt, tt = plan._t(X), plan._t(theta).reshape(-1)
+    mt = [plan._t(w) for w in mlp]
+    plan.prepare(tt, None)
+    return plan.solver_forward(Xt, mt, MODE_RESIDUAL, tuple(coeffs), want_streams=True)
+
+
+def fma_peak(dtype: torch.dtype, device=None, iters: int = 20000) -> float:
+    """Measured FMA-pipe FLOP/s of the current device (roofline denominator)."""
+    lib = _lib.require_cuda()
+    device = torch.device(device if device is not None else "cuda")
+    out = ctypes.c_double(0.0)
+    with torch.cuda.device(device):
+        stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        rc = lib.qcp_bench_fma(_DTYPE_CODE[dtype], iters, ctypes.byref(out), stream)
+    _lib.check(rc, "qcp_bench_fma")
+    return out.value

@@ -1,0 +1,212 @@
+"""``DVPDESolver`` -- drop-in for reference nn/DVPDESolver.py on the fused sm_100a path.
+
+Kept from the reference: constructor signature ``(args, logger, data=None, device=None)``; the
+``args`` keys read (``batch_size, num_qubits, epochs, classic_network, lr`` required;
+``encoding`` optional); submodule names ``preprocessor`` / ``postprocessor`` / ``quantum_layer``
+(so state dicts and ``model.pth`` checkpoints interchange); Adam + ReduceLROnPlateau(0.9, 1000) +
+MSELoss; xavier-normal / zero-bias on the pre MLP only; ``forward(x: (B,3)) -> (B,1)`` float32
+with the "log then re-raise" error convention; ``save_state`` / ``load_state`` dict layout.
+
+Different by design: ``forward`` is ONE fused kernel (pre MLP -> circuit -> post MLP), and
+``taylor_residual`` (used by ``nn.pde.diffusion_operator``) is ONE fused Taylor-mode kernel; both
+have hand-written adjoint kernels.  The whole module, including ``quantum_layer``, must live on a
+CUDA device -- there is no CPU path.
+"""
+
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn as nn
+
+from .. import functional as F
+from ..utils.logger import Logging
+from .DVQuantumLayer import DVQuantumLayer
+
+
+class _RankConsistentPlateau(torch.optim.lr_scheduler.ReduceLROnPlateau):
+    """ReduceLROnPlateau whose metric is averaged over data-parallel ranks, so every rank takes
+    the same LR decisions when the unmodified trainer calls ``scheduler.step(loss)``."""
+
+    _qcp_group = None
+    _qcp_enabled = False
+
+    def step(self, metrics, *a, **kw):
+        if self._qcp_enabled and torch.is_tensor(metrics):
+            import torch.distributed as dist
+
+            m = metrics.detach().clone()
+            dist.all_reduce(m, op=dist.ReduceOp.SUM, group=self._qcp_group)
+            metrics = m / dist.get_world_size(self._qcp_group)
+        return super().step(metrics, *a, **kw)
+
+
+class DVPDESolver(nn.Module):
+    def __init__(self, args, logger: Logging, data=None, device=None):
+        super().__init__()
+        self.logger = logger
+        self.device = device
+        self.args = args
+        self.data = data
+        self.batch_size = self.args["batch_size"]
+        self.num_qubits = self.args["num_qubits"]
+        self.epochs = self.args["epochs"]
+        self.optimizer = None
+        self.scheduler = None
+        self.loss_history = []
+        self.encoding = self.args.get("encoding", "angle")
+        self.draw_quantum_circuit_flag = True
+        self.classic_network = self.args["classic_network"]
+        self.total_training_time = 0
+        self.total_memory_peak = 0
+
+        hidden = self.classic_network[-2]
+        self.preprocessor = nn.Sequential(
+            nn.Linear(self.classic_network[0], hidden),
+            nn.Tanh(),
+            nn.Linear(hidden, self.num_qubits),
+        ).to(self.device)
+        self.postprocessor = nn.Sequential(
+            nn.Linear(self.num_qubits, hidden),
+            nn.Tanh(),
+            nn.Linear(hidden, self.classic_network[-1]),
+        ).to(self.device)
+        self.activation = nn.Tanh()
+
+        # The reference leaves quantum_layer on the CPU (PennyLane moves data itself); the fused
+        # kernels need every parameter on the model's device.
+        self.quantum_layer = DVQuantumLayer(self.args).to(self.device)
+
+        self.optimizer = torch.optim.Adam(
+            [p for p in self.parameters() if p.requires_grad], lr=self.args["lr"])
+        self.scheduler = _RankConsistentPlateau(
+            self.optimizer, mode="min", factor=0.9, patience=1000)
+        self.loss_fn = torch.nn.MSELoss()
+        self.log_path = self.logger.get_output_dir()
+        self._initialize_weights()
+        self._dp = None
+
+    def _initialize_weights(self):
+        for layer in self.preprocessor:
+            if isinstance(layer, nn.Linear):
+                nn.init.xavier_normal_(layer.weight)
+                if layer.bias is not None:
+                    nn.init.zeros_(layer.bias)
+
+    # -- fused path ----------------------------------------------------------------------------
+    def _check_fused(self):
+        net = self.classic_network
+        if net[0] != 3 or net[-1] != 1:
+            raise NotImplementedError(
+                f"fused kernels cover classic_network=[3, H, 1]; got {net}")
+
+    def _mlp_tensors(self):
+        pre, post = self.preprocessor, self.postprocessor
+        return (pre[0].weight, pre[0].bias, pre[2].weight, pre[2].bias,
+                post[0].weight, post[0].bias, post[2].weight, post[2].bias)
+
+    def _plan(self, device) -> F.Plan:
+        self._check_fused()
+        return self.quantum_layer.plan(device, hidden=self.classic_network[-2])
+
+    def _device_of(self, x):
+        dev = self.quantum_layer.params.device
+        if x.device != dev:
+            raise RuntimeError(f"input on {x.device} but model parameters on {dev}")
+        return dev
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        try:
+            if x.dim() != 2:
+                raise ValueError(f"Expected 2D input tensor, got shape {x.shape}")
+            if self.draw_quantum_circuit_flag:
+                self.draw_quantum_circuit(x)
+                self.draw_quantum_circuit_flag = False
+            plan = self._plan(self._device_of(x))
+            u = F.solver_value(plan, x, self.quantum_layer.params, self._mlp_tensors(),
+                               self.quantum_layer.theta_key())
+            return u.to(torch.float32)
+        except Exception as e:
+            self.logger.print(f"Forward pass failed: {str(e)}")
+            raise
+
+    def taylor_residual(self, X: torch.Tensor, coeffs):
+        """(u, r) with r = c0 u_t + c1 u_x + c2 u_y + c3 u_xx + c4 u_yy, each (B,1) float32."""
+        try:
+            if X.dim() != 2:
+                raise ValueError(f"Expected 2D input tensor, got shape {X.shape}")
+            if self.draw_quantum_circuit_flag:
+                self.draw_quantum_circuit(X)
+                self.draw_quantum_circuit_flag = False
+            plan = self._plan(self._device_of(X))
+            u, r = F.solver_residual(plan, X, self.quantum_layer.params, self._mlp_tensors(),
+                                     coeffs, self.quantum_layer.theta_key())
+            return u.to(torch.float32), r.to(torch.float32)
+        except Exception as e:
+            self.logger.print(f"Forward pass failed: {str(e)}")
+            raise
+
+    def taylor_streams(self, X: torch.Tensor):
+        """No-grad evaluation helper: (B,6) = u, u_t, u_x, u_y, u_xx, u_yy."""
+        plan = self._plan(self._device_of(X))
+        with torch.no_grad():
+            return F.solver_streams(plan, X, self.quantum_layer.params, self._mlp_tensors())[2]
+
+    # -- data parallel -------------------------------------------------------------------------
+    def enable_data_parallel(self, process_group=None):
+        """Average gradients over ranks at the end of every backward pass (one flat all-reduce,
+        issued from an autograd-engine callback so an unmodified trainer needs no changes)."""
+        from ..dist import GradientAverager
+
+        self._dp = GradientAverager(self, process_group)
+        self.scheduler._qcp_group = process_group
+        self.scheduler._qcp_enabled = True
+        return self._dp
+
+    # -- checkpoint ----------------------------------------------------------------------------
+    def save_state(self, path=None):
+        state = {
+            "args": self.args,
+            "classic_network": self.classic_network,
+            "quantum_params": self.quantum_layer.state_dict(),
+            "preprocessor": self.preprocessor.state_dict(),
+            "quantum_layer": self.quantum_layer.state_dict(),
+            "postprocessor": self.postprocessor.state_dict(),
+            "optimizer": self.optimizer.state_dict(),
+            "scheduler": self.scheduler.state_dict(),
+            "loss_history": self.loss_history,
+            "log_path": self.log_path,
+        }
+        model_path = os.path.join(self.log_path, "model.pth") if path is None else path
+        with open(model_path, "wb") as f:
+            torch.save(state, f)
+        self.logger.print(f"Model state saved to {model_path}")
+
+    @classmethod
+    def load_state(cls, file_path, map_location=None):
+        if map_location is None:
+            map_location = torch.device("cpu")
+        with open(file_path, "rb") as f:
+            return torch.load(f, map_location=map_location, weights_only=False)
+
+    def restore(self, state):
+        """Load a ``save_state`` dict (ours or the reference's) back into this model."""
+        self.preprocessor.load_state_dict(state["preprocessor"])
+        self.quantum_layer.load_state_dict(state["quantum_layer"])
+        self.postprocessor.load_state_dict(state["postprocessor"])
+        if "optimizer" in state:
+            self.optimizer.load_state_dict(state["optimizer"])
+        if "scheduler" in state:
+            self.scheduler.load_state_dict(state["scheduler"])
+        self.loss_history = list(state.get("loss_history", []))
+        return self
+
+    def draw_quantum_circuit(self, x):
+        # matplotlib / qml.draw_mpl are not part of this stack: log the gate program instead.
+        if self.draw_quantum_circuit_flag:
+            try:
+                self.logger.print("The circuit used in the study:")
+                self.logger.print(self.quantum_layer.describe())
+            except Exception as e:
+                self.logger.print(f"Failed to draw quantum circuit: {str(e)}")
