@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""Benchmark of the QCPINN convection-diffusion train step (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--dtype f64|f32] [--points P]
+    python bench.py --impl reference ...        # the reference algorithm on the host CPU cores
+
+Workload (``config.workload``): BASELINE.json configs[4] -- DVPDESolver, 4-qubit cascade ansatz, one
+quantum layer, angle encoding, Haar blocks off (README quick-start args), ``--points`` = 4 194 304
+residual collocation points per step (plus P//3 initial-condition and P//3 boundary points),
+sharded over the ranks (strong scaling).  One step = sample -> 3 model calls
+-> residual -> weighted MSE loss -> backward -> (gradient all-reduce) -> clip -> Adam ->
+ReduceLROnPlateau -> loss.item(), i.e. exactly ``trainer.diffusion_train.TrainStep``.
+
+Prints ONE JSON line (rank 0).  ``value`` = residual points/s over all ranks with the samplers
+running on the device; ``e2e`` = the same step fed from pinned HOST batches (H2D inside the timed
+region, loss read back).  ``roofline`` is the dominant kernel (the residual backward) against the
+FMA-pipe peak measured in this very run; ``cpu_baseline`` is the CPU oracle (restatement stand-in
+for the reference, NOT PennyLane) timed on this box's cores.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = "cfg5: DVPDESolver 4q cascade L=1 angle, Haar off, hidden 50"
+FULL_POINTS = 4_194_304
+N_QUBITS, N_LAYERS, ANSATZ, HIDDEN = 4, 1, "cascade", 50
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
+                    help="arithmetic of the headline number (the reference's state is complex128)")
+    ap.add_argument("--points", type=int, default=FULL_POINTS,
+                    help="residual collocation points per step over ALL ranks")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the other dtype's line")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-points", type=int, default=65_536)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+def model_args(dtype_name):
+    return {
+        "batch_size": 64, "epochs": 1, "lr": 0.005, "print_every": 10 ** 9,
+        "num_qubits": N_QUBITS, "num_quantum_layers": N_LAYERS, "classic_network": [3, HIDDEN, 1],
+        "q_ansatz": ANSATZ, "problem": "diffusion", "solver": "DV", "encoding": "None",
+        "dtype": {"f64": "float64", "f32": "float32"}[dtype_name],
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    mx.append(float(parts[1]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, parts[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            # "under load" = samples in the upper half of the observed range
+            hi = [v for v in sm if v >= 0.5 * max(sm)]
+            out.update(sm_mhz=statistics.median(hi), sm_max_mhz=max(mx), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def timed_steps(step_fn, steps, warmup, torch, dist, world, device):
+    for _ in range(warmup):
+        step_fn()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        step_fn()
+    e1.record()
+    torch.cuda.synchronize(device)
+    wall = time.perf_counter() - wall0
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0]), float(t[1])
+
+
+def run_ours(ns):
+    import torch
+
+    import qcpinn_b200 as qb
+    from qcpinn_b200.dist import init_from_env
+    from qcpinn_b200.trainer.diffusion_train import TrainStep, _make_averager
+    import torch.distributed as dist
+
+    rank, world, local = init_from_env()
+    if world != ns.gpus and world > 1:
+        raise SystemExit(f"--gpus {ns.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: qcpinn_b200 has no CPU fallback")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    F = qb.functional
+    pts_rank = ns.points // world
+    pts_total = pts_rank * world
+
+    def make(dtype_name):
+        torch.manual_seed(0)                       # identical weights on every rank
+        logger = qb.Logging(os.path.join(tempfile.gettempdir(), f"qcpinn_bench_r{rank}"))
+        model = qb.DVPDESolver(model_args(dtype_name), logger, device=device)
+        step = TrainStep(model, pts_rank, _make_averager(model))
+        return model, step
+
+    def measure(dtype_name, with_e2e):
+        model, step = make(dtype_name)
+        torch.manual_seed(1234 + rank)             # per-rank sampler stream
+        clk = ClockSampler(local)
+        # warm-up outside the clock sampler, then the timed region under it
+        for _ in range(ns.warmup):
+            step()
+        launches0 = F.launch_counter
+        clk.start()
+        ms, wall_ms = timed_steps(step, ns.steps, 0, torch, dist, world, device)
+        clocks = clk.stop()
+        launches = F.launch_counter - launches0
+        res = {"ms": ms, "wall_ms": wall_ms, "clocks": clocks, "launches": launches,
+               "value": pts_total * ns.steps / (ms * 1e-3)}
+
+        # dominant kernel: residual backward, timed alone with CUDA events on the launch stream
+        plan = model._plan(device)
+        X = torch.rand(pts_rank, 3, device=device).to(plan.dtype)
+        gr = torch.rand(pts_rank, device=device).to(plan.dtype)
+        theta = model.quantum_layer.params.detach().to(plan.dtype).reshape(-1).contiguous()
+        mlp = [plan._t(w) for w in model._mlp_tensors()]
+        plan.prepare(theta)
+        coeffs = (1.0, 1.0, 1.0, -0.01, -0.01)
+        for _ in range(2):
+            plan.solver_backward(X, mlp, theta, None, gr, F.MODE_RESIDUAL, coeffs)
+        reps = max(3, min(ns.steps, 10))
+        k0 = torch.cuda.Event(enable_timing=True)
+        k1 = torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(reps):
+            plan.solver_backward(X, mlp, theta, None, gr, F.MODE_RESIDUAL, coeffs)
+        k1.record()
+        torch.cuda.synchronize(device)
+        res["bwd_kernel_ms"] = k0.elapsed_time(k1) / reps
+        k0.record()
+        for _ in range(reps):
+            plan.solver_forward(X, mlp, F.MODE_RESIDUAL, coeffs)
+        k1.record()
+        torch.cuda.synchronize(device)
+        res["fwd_kernel_ms"] = k0.elapsed_time(k1) / reps
+
+        if with_e2e:
+            # host-resident inputs: pinned batches, H2D + loss D2H inside the timed region
+            ring = []
+            for i in range(2):
+                g = torch.Generator().manual_seed(99 + 7 * rank + i)
+                from qcpinn_b200.data.diffusion_dataset import r as r_fn, u as u_fn
+
+                def box(lo, hi, n):
+                    lo = torch.tensor(lo).view(1, 3)
+                    hi = torch.tensor(hi).view(1, 3)
+                    return lo + (hi - lo) * torch.rand(n, 3, generator=g)
+
+                xi = box([0., 0., 0.], [0., 1., 1.], pts_rank // 3)
+                xb = box([0., 0., 0.], [1., 0., 1.], pts_rank // 3)
+                xr = box([0., 0., 0.], [1., 1., 1.], pts_rank)
+                host = (xi, u_fn(xi), xb, u_fn(xb), xr, r_fn(xr))
+                ring.append(tuple(t.contiguous().pin_memory() for t in host))
+            h2d = sum(t.numel() * t.element_size() for t in ring[0])
+            state = {"i": 0}
+
+            def e2e_step():
+                host = ring[state["i"] % len(ring)]
+                state["i"] += 1
+                batch = tuple(t.to(device, non_blocking=True) for t in host)
+                return step(batch)
+
+            ms_e, _ = timed_steps(e2e_step, ns.steps, min(ns.warmup, 3), torch, dist, world, device)
+            res["e2e"] = {"value": pts_total * ns.steps / (ms_e * 1e-3), "unit": "points/s",
+                          "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
+                          "ms_per_step": ms_e / ns.steps}
+        del model, step
+        return res
+
+    primary = measure(ns.dtype, with_e2e=True)
+    other = "f32" if ns.dtype == "f64" else "f64"
+    secondary = None if ns.no_secondary else measure(other, with_e2e=False)
+
+    tdt = {"f64": torch.float64, "f32": torch.float32}
+    peaks = {d: F.fma_peak(tdt[d], device) for d in ("f64", "f32")}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    from oracle.solver import flops_per_point
+
+    fl_pt, f_fwd, f_mlp = flops_per_point(N_QUBITS, N_LAYERS, ANSATZ, haar=False, hidden=HIDDEN)
+    # dominant kernel = adjoint of the 6-stream residual forward: 2 x 6 x (F_fwd + F_mlp) per point
+    bwd_flops_pt = 12 * (f_fwd + f_mlp)
+
+    def roof(res, d):
+        achieved = bwd_flops_pt * pts_rank / (res["bwd_kernel_ms"] * 1e-3)
+        return {"bound": "fma", "kernel": f"solver_backward_kernel<{d},4,angle,residual>",
+                "achieved": achieved / 1e12, "peak": peaks[d] / 1e12, "unit": "TFLOP/s",
+                "frac": achieved / peaks[d], "traffic": None,
+                "peak_source": "qcp_bench_fma measured in this run (FP%s FMA pipe)" % d[1:],
+                "algorithmic_flops_per_point": bwd_flops_pt,
+                "kernel_ms": res["bwd_kernel_ms"], "fwd_kernel_ms": res["fwd_kernel_ms"]}
+
+    def step_roof(res, d):
+        return {"flops_per_point": fl_pt, "achieved_tflops": res["value"] * fl_pt / 1e12,
+                "frac_of_fma_peak": res["value"] * fl_pt / (peaks[d] * world)}
+
+    traffic_file = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    line = {
+        "metric": "PINN train-step collocation points/s (4-qubit cascade)",
+        "value": primary["value"], "unit": "points/s", "n_gpus": world, "steps": ns.steps,
+        "warmup": ns.warmup, "ms_per_step": primary["ms"] / ns.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": ns.dtype, "data": "synthetic",
+        "config": {"workload": WORKLOAD, "residual_points_per_step": pts_total,
+                   "ic_points": (pts_rank // 3) * world, "bc_points": (pts_rank // 3) * world,
+                   "parallelism": f"dp{world}",
+                   "l2": "inputs resampled on the device every step; per-step footprint > 126 MB L2"},
+        "e2e": primary.get("e2e"),
+        "gpu_launches": primary["launches"],
+        "clocks": {k: primary["clocks"][k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
+        "wall_ms_per_step": primary["wall_ms"] / ns.steps,
+        "roofline": roof(primary, ns.dtype),
+        "roofline_step": step_roof(primary, ns.dtype),
+    }
+    try:
+        with open(traffic_file) as f:
+            tr = json.load(f)
+        key = f"{ns.dtype}:{pts_rank}"
+        if key in tr:
+            line["roofline"]["traffic"] = tr[key]
+    except Exception:
+        pass
+    if secondary is not None:
+        line["secondary"] = {
+            "dtype": other, "value": secondary["value"], "ms_per_step": secondary["ms"] / ns.steps,
+            "roofline": roof(secondary, other), "roofline_step": step_roof(secondary, other),
+            "clocks": {k: secondary["clocks"][k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
+        }
+    if world == 1 and not ns.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(ns.cpu_points, ns.cpu_steps)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the only place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------
+def _oracle_trainer(mode="mixed"):
+    import torch
+
+    from oracle import solver as osolver
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = osolver.init_weights(N_QUBITS, N_LAYERS, ANSATZ, hidden=HIDDEN, seed=0)
+    model = osolver.OracleSolver(N_QUBITS, N_LAYERS, ANSATZ, "angle", None, mode).set_weights(w)
+    return osolver, osolver.OracleTrainer(model, lr=0.005)
+
+
+def cpu_baseline(points, steps):
+    """Oracle restatement (float32 MLPs + complex128 state = the reference's own precision) on the
+    host cores: full step incl. sampling, nested-autograd residual, backward, clip, Adam."""
+    import torch
+
+    osolver, trainer = _oracle_trainer("mixed")
+    trainer.step(osolver.make_batches(points, seed=1))          # warm-up
+    t0 = time.perf_counter()
+    for i in range(steps):
+        trainer.step(osolver.make_batches(points, seed=2 + i))
+    dt = time.perf_counter() - t0
+    return {"value": points * steps / dt, "unit": "points/s", "cores": torch.get_num_threads(),
+            "kind": "port", "sample": f"{steps} full train steps of {points} residual points "
+            f"(+2x{points // 3} IC/BC) of the same 4q-cascade workload, complex128 state",
+            "note": "oracle restatement stand-in, not PennyLane (not installable here)",
+            "ms_per_step": dt / steps * 1e3}
+
+
+def run_reference(ns):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    osolver, trainer = _oracle_trainer("mixed")
+    points = min(ns.cpu_points, ns.points)
+    for i in range(ns.warmup):
+        trainer.step(osolver.make_batches(points, seed=100 + i))
+    t0 = time.perf_counter()
+    for i in range(ns.steps):
+        trainer.step(osolver.make_batches(points, seed=200 + i))
+    dt = time.perf_counter() - t0
+    value = points * ns.steps / dt
+    cores = torch.get_num_threads()
+    sample = (f"each step = one full train step on {points} residual points (+2x{points // 3} "
+              f"IC/BC), a bounded sample of the {ns.points}-point workload")
+    line = {
+        "impl": "reference",
+        "metric": "PINN train-step collocation points/s (4-qubit cascade)",
+        "value": value, "unit": "points/s", "n_gpus": ns.gpus, "steps": ns.steps,
+        "warmup": ns.warmup, "ms_per_step": dt / ns.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "residual_points_per_step": points,
+                   "note": "reference algorithm (gate-by-gate default.qubit-style statevector + "
+                           "nested autograd) restated in oracle/; PennyLane is not installable"},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ns = parse_args()
+    if ns.impl == "reference":
+        run_reference(ns)
+        return
+    if ns.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: relaunch under torchrun when called directly with --gpus N
+        port = 29500 + (os.getpid() % 2000)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+               f"--nproc-per-node={ns.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(ns)
+
+
+if __name__ == "__main__":
+    main()

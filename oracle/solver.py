@@ -204,7 +204,7 @@ class OracleTrainer:
         loss.backward()
         torch.nn.utils.clip_grad_norm_(self.params, max_norm=1)
         self.opt.step()
-        self.sched.step(loss)
+        self.sched.step(loss.detach())
         self.loss_history.append(loss.item())
         return self.loss_history[-1]
 

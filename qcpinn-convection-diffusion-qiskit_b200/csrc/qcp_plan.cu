@@ -566,7 +566,7 @@ static int forward_grid(const qcp_plan* p, long long B) {
 }
 
 int qcp_layer_forward(qcp_plan_t* p, const void* z, long long B, void* q, void* stream) {
-  if (!p || !z || !q) { set_error("qcp_layer_forward: NULL argument"); return 1; }
+  if (!p || (B > 0 && (!z || !q))) { set_error("qcp_layer_forward: NULL argument"); return 1; }
   if (!p->prepared) { set_error("qcp_layer_forward: qcp_prepare() has not run"); return 1; }
   if (B <= 0) return 0;
   LayerArgs a{};
@@ -591,7 +591,7 @@ static int run_theta_grad(qcp_plan* p, const void* theta, void* gtheta, cudaStre
 
 int qcp_layer_backward(qcp_plan_t* p, const void* theta, const void* z, const void* grad_q,
                        long long B, void* grad_z, void* grad_theta, void* stream) {
-  if (!p || !theta || !z || !grad_q || !grad_theta) { set_error("qcp_layer_backward: NULL argument"); return 1; }
+  if (!p || !theta || !grad_theta || (B > 0 && (!z || !grad_q))) { set_error("qcp_layer_backward: NULL argument"); return 1; }
   if (!p->prepared) { set_error("qcp_layer_backward: qcp_prepare() has not run"); return 1; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int nacc = p->F * p->n;
@@ -633,7 +633,7 @@ static int check_mode(int mode, const double* coeffs, const char* who) {
 
 int qcp_solver_forward(qcp_plan_t* p, const qcp_mlp_t* w, const void* X, long long B, int mode,
                        const double* coeffs, void* u, void* r, void* streams, void* stream) {
-  if (!p || !w || !X || !u) { set_error("qcp_solver_forward: NULL argument"); return 1; }
+  if (!p || !w || (B > 0 && (!X || !u))) { set_error("qcp_solver_forward: NULL argument"); return 1; }
   if (!p->prepared) { set_error("qcp_solver_forward: qcp_prepare() has not run"); return 1; }
   if (check_mode(mode, coeffs, "qcp_solver_forward")) return 1;
   if (B <= 0) return 0;
@@ -650,7 +650,7 @@ int qcp_solver_backward(qcp_plan_t* p, const qcp_mlp_t* w, const void* theta, co
                         const void* grad_u, const void* grad_r, long long B, int mode,
                         const double* coeffs, const qcp_mlp_t* g, void* grad_theta, void* grad_X,
                         void* stream) {
-  if (!p || !w || !theta || !X || !g || !grad_theta) { set_error("qcp_solver_backward: NULL argument"); return 1; }
+  if (!p || !w || !theta || !g || !grad_theta || (B > 0 && !X)) { set_error("qcp_solver_backward: NULL argument"); return 1; }
   if (!p->prepared) { set_error("qcp_solver_backward: qcp_prepare() has not run"); return 1; }
   if (check_mode(mode, coeffs, "qcp_solver_backward")) return 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -66,16 +66,18 @@ class TrainStep:
         loss = 2.0 * loss_r + 4.0 * loss_bc1 + 2.0 * loss_ics
         return loss, time.time() - start, loss_r, loss_bc1, loss_ics
 
-    def update(self, loss):
+    def update(self, loss, run_backward=True):
         """backward -> (all-reduce) -> clip -> Adam -> plateau scheduler -> loss.item()."""
         model = self.model
-        loss.backward()
+        if run_backward:
+            loss.backward()
         if self.averager is not None:
             # grads and the scheduler metric share one all-reduce
             loss = self.averager.average(extras=[loss])[0].clone()
         torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=self.max_norm)
         if model.optimizer is not None:
             model.optimizer.step()
+        loss = loss.detach()
         if model.scheduler is not None:
             model.scheduler.step(loss)
         value = loss.item()

@@ -1,0 +1,244 @@
+"""GPU tests through the reference-shaped Python surface (DVQuantumLayer / DVPDESolver /
+diffusion_operator / trainer), the golden fixtures, edge cases and full-size properties."""
+
+import glob
+import os
+
+import pytest
+import torch
+
+import qcpinn_b200 as qb
+from helpers import F, TOL, device_weights, make_case, mlp_list, points, rel_err
+from oracle import solver as osolver
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt")))
+DEV = torch.device("cuda", 0)
+
+ARGS = {
+    "batch_size": 64, "epochs": 4, "lr": 0.005, "seed": 1, "print_every": 2,
+    "num_qubits": 4, "num_quantum_layers": 1, "classic_network": [3, 50, 1],
+    "q_ansatz": "cascade", "problem": "diffusion", "solver": "DV", "encoding": "None",
+}
+
+
+def _model(tmp_path, **over):
+    torch.manual_seed(0)
+    args = dict(ARGS, **over)
+    return qb.DVPDESolver(args, qb.Logging(str(tmp_path)), device=DEV)
+
+
+def _weights_of(model):
+    pre, post = model.preprocessor, model.postprocessor
+    return {"w1": pre[0].weight, "b1": pre[0].bias, "w2": pre[2].weight, "b2": pre[2].bias,
+            "theta": model.quantum_layer.params,
+            "w3": post[0].weight, "b3": post[0].bias, "w4": post[2].weight, "b4": post[2].bias}
+
+
+def _oracle_of(model, mode="f64"):
+    a = model.args
+    w = {k: v.detach().cpu() for k, v in _weights_of(model).items()}
+    return osolver.OracleSolver(a["num_qubits"], a["num_quantum_layers"], a["q_ansatz"],
+                                "amplitude" if a.get("encoding") == "amplitude" else "angle",
+                                a.get("seed"), mode).set_weights(w)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-3] for p in GOLDEN])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_cuda_reproduces_golden_fixture(path, dtype):
+    gold = torch.load(path, weights_only=False)
+    m = gold["meta"]
+    prog = qb.program.compile_program(m["ansatz"], m["n"], m["layers"], m["haar_seed"])
+    plan = F.Plan(prog, F.encoding_code(m["encoding"]), dtype, 50, DEV)
+    dw = device_weights(gold["weights"], dtype, DEV, requires_grad=True)
+    tol = TOL[dtype]
+    q = F.layer_apply(plan, gold["z"].to(DEV, dtype), dw["theta"])
+    assert rel_err(q, gold["q"]) < tol
+    b = {k: v.to(DEV, dtype) for k, v in gold["batches"].items()}
+    coeffs = (1.0, 1.0, 1.0, -0.01, -0.01)
+    streams = F.solver_streams(plan, b["X_res"], dw["theta"], mlp_list(dw), coeffs)[2]
+    for c in range(6):
+        assert rel_err(streams[:, c], gold["streams"][:, c]) < tol, c
+    # the trainer's objective, assembled from the three fused calls
+    u_bc = F.solver_value(plan, b["X_bc"], dw["theta"], mlp_list(dw))
+    u_ic = F.solver_value(plan, b["X_ic"], dw["theta"], mlp_list(dw))
+    _, r = F.solver_residual(plan, b["X_res"], dw["theta"], mlp_list(dw), coeffs)
+    mse = lambda a, t: ((a - t) ** 2).mean()
+    loss = 2 * mse(r, b["r_res"]) + 4 * mse(u_bc, b["u_bc"]) + 2 * mse(u_ic, b["u_ic"])
+    loss.backward()
+    assert abs(loss.item() - gold["terms"]["loss"].item()) < tol * abs(gold["terms"]["loss"].item())
+    for k, g in gold["grads"].items():
+        assert rel_err(dw[k].grad, g) < tol, k
+
+
+def test_quantum_layer_module_matches_oracle():
+    layer = qb.DVQuantumLayer({"num_qubits": 4, "num_quantum_layers": 2, "q_ansatz": "cross_mesh",
+                               "problem": "diffusion", "seed": 1}).to(DEV)
+    x = torch.randn(19, 4, device=DEV)
+    out = layer(x)
+    assert out.shape == (4, 19) and out.dtype == torch.float64      # (n, B) float64 like PennyLane
+    from oracle import circuits as oc
+    want = oc.quantum_layer(x.cpu().double(), layer.params.detach().cpu().double(), "cross_mesh",
+                            4, "angle", oc.haar_for(1, 4))
+    assert rel_err(out, want) < 1e-10
+    out.sum().backward()
+    assert layer.params.grad is not None and layer.params.grad.shape == (2, 28)
+    single = layer(x[0])
+    assert single.shape == (4,) and rel_err(single, want[:, 0]) < 1e-10
+
+
+def test_solver_module_forward_and_residual_match_oracle(tmp_path):
+    model = _model(tmp_path)
+    oracle = _oracle_of(model)
+    X = points(40).float().to(DEV)
+    u = model(X)
+    assert u.shape == (40, 1) and u.dtype == torch.float32
+    assert rel_err(u, oracle.forward(X.cpu().double())) < 1e-6      # float32 cast of the output
+    t, x, y = (X[:, i:i + 1].clone() for i in range(3))
+    uu, r = qb.diffusion_operator(model, t, x, y)
+    assert t.requires_grad and x.requires_grad and y.requires_grad
+    Xc = X.cpu().double()
+    uo, ro = osolver.diffusion_operator(oracle, Xc[:, 0:1].clone(), Xc[:, 1:2].clone(), Xc[:, 2:3].clone())
+    assert rel_err(uu, uo) < 1e-6 and rel_err(r, ro) < 1e-6
+    assert rel_err(model.taylor_streams(X), osolver.diffusion_streams(oracle, Xc)) < 1e-10
+    log = open(os.path.join(model.log_path, "output.log")).read()
+    assert "The circuit used in the study:" in log and "CRX[3,0] theta[8]" in log
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_train_step_loss_and_gradients_match_oracle(tmp_path, dtype):
+    """One objective of the trainer (3 model calls + weighted MSE) against the oracle's step."""
+    from qcpinn_b200.trainer.diffusion_train import TrainStep
+
+    model = _model(tmp_path, dtype=dtype)
+    oracle = _oracle_of(model)
+    batches = osolver.make_batches(96, seed=11)
+    terms, grads = osolver.loss_and_grads(oracle, batches)
+    step = TrainStep(model, 96)
+    batch = tuple(batches[k].to(DEV) for k in ("X_ic", "u_ic", "X_bc", "u_bc", "X_res", "r_res"))
+    loss, _, lr_, lbc, lic = step.objective(batch)
+    loss.backward()
+    tol = 2e-5 if dtype == "float32" else 2e-6       # outputs/loss pass through float32
+    assert abs(loss.item() - terms["loss"].item()) < tol * terms["loss"].item()
+    assert abs(lr_.item() - terms["loss_r"].item()) < tol * terms["loss_r"].item()
+    for k, p in _weights_of(model).items():
+        assert rel_err(p.grad, grads[k]) < 10 * tol, k
+    assert batch[0].grad is not None      # X_ics.requires_grad_(True) in the trainer gets a grad
+
+
+def test_trainer_runs_and_matches_oracle_trajectory(tmp_path):
+    """Five optimisation steps on fixed batches: the loss history follows the CPU oracle."""
+    from qcpinn_b200.trainer.diffusion_train import TrainStep
+
+    model = _model(tmp_path, seed=None)
+    oracle = _oracle_of(model, "f64")
+    otr = osolver.OracleTrainer(oracle, lr=0.005)
+    step = TrainStep(model, 48)
+    for i in range(5):
+        b = osolver.make_batches(48, seed=100 + i)
+        want = otr.step(b)
+        got = step(tuple(b[k].to(DEV) for k in ("X_ic", "u_ic", "X_bc", "u_bc", "X_res", "r_res")))
+        assert abs(got - want) < 5e-5 * abs(want), (i, got, want)
+    assert len(model.loss_history) == 5
+
+
+def test_train_function_end_to_end(tmp_path):
+    from qcpinn_b200.trainer import diffusion_train
+
+    model = _model(tmp_path)
+    before = [p.detach().clone() for p in model.parameters()]
+    diffusion_train.train(model, batch_size=128)
+    assert len(model.loss_history) == model.epochs + 1
+    assert all(torch.isfinite(torch.tensor(model.loss_history)))
+    assert any(not torch.equal(a, b) for a, b in zip(before, model.parameters()))
+    assert os.path.exists(os.path.join(model.log_path, "model.pth"))      # print_every checkpoint
+    log = open(os.path.join(model.log_path, "output.log")).read()
+    assert "Starting training for 4 epochs" in log and "Epoch: 4/4" in log and "Training completed" in log
+    state = qb.DVPDESolver.load_state(os.path.join(model.log_path, "model.pth"))
+    assert state["quantum_layer"]["params"].shape == (1, 12)
+
+
+@pytest.mark.parametrize("batch", [0, 1, 31, 32, 33, 127, 129, 1000])
+def test_ragged_and_empty_batches(batch):
+    w, oracle, prog = make_case("cascade", 4, 1, "angle", 1)
+    plan = F.Plan(prog, 0, torch.float64, 50, DEV)
+    dw = device_weights(w, torch.float64, DEV, requires_grad=True)
+    X = points(max(batch, 1), seed=batch)[:batch]
+    u, r = F.solver_residual(plan, X.to(DEV), dw["theta"], mlp_list(dw), (1, 1, 1, -0.01, -0.01))
+    assert u.shape == (batch, 1) and r.shape == (batch, 1)
+    (u.sum() + 2 * r.sum()).backward()
+    if batch == 0:
+        assert float(dw["w1"].grad.abs().max()) == 0.0 and float(dw["theta"].grad.abs().max()) == 0.0
+        return
+    uo, ro = osolver.diffusion_operator(oracle, X[:, 0:1].clone(), X[:, 1:2].clone(), X[:, 2:3].clone())
+    (uo.sum() + 2 * ro.sum()).backward()
+    assert rel_err(r, ro) < 1e-10
+    for k in osolver.WEIGHT_NAMES:
+        assert rel_err(dw[k].grad, oracle.w[k].grad) < 1e-10, k
+
+
+def test_other_hidden_widths_and_pde_coefficients():
+    w, oracle, prog = make_case("layered", 3, 1, "angle", None, hidden=17)
+    plan = F.Plan(prog, 0, torch.float64, 17, DEV)
+    dw = device_weights(w, torch.float64, DEV, requires_grad=True)
+    X = points(21)
+    kw = dict(sigma_t=2.0, sigma_x=0.5, sigma_y=4.0, D=0.3, v_x=-1.5, v_y=0.25)
+    uo, ro = osolver.diffusion_operator(oracle, X[:, 0:1].clone(), X[:, 1:2].clone(), X[:, 2:3].clone(), **kw)
+    from qcpinn_b200.nn.pde import _diffusion_coeffs
+    coeffs = _diffusion_coeffs(kw["sigma_t"], kw["sigma_x"], kw["sigma_y"], kw["D"], kw["v_x"], kw["v_y"])
+    u, r = F.solver_residual(plan, X.to(DEV), dw["theta"], mlp_list(dw), coeffs)
+    assert rel_err(r, ro) < 1e-10 and rel_err(u, uo) < 1e-10
+
+
+def test_full_size_properties_4m_points():
+    """BASELINE config 5 size (4 194 304 points): size-independent properties.
+    (a) the residual kernel is deterministic and finite; (b) gradients are additive over a
+    partition of the batch (what data-parallel sharding relies on); (c) a strided sample agrees
+    with the oracle."""
+    n_pts = 4_194_304
+    w, oracle, prog = make_case("cascade", 4, 1, "angle", None)
+    plan = F.Plan(prog, 0, torch.float64, 50, DEV)
+    dw = device_weights(w, torch.float64, DEV)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    X = torch.rand(n_pts, 3, device=DEV, dtype=torch.float64, generator=g)
+    gr = torch.rand(n_pts, device=DEV, dtype=torch.float64, generator=g) / n_pts
+    coeffs = (1.0, 1.0, 1.0, -0.01, -0.01)
+    theta = dw["theta"].reshape(-1)
+    mlp = mlp_list(dw)
+    plan.prepare(theta)
+    u1, r1, _ = plan.solver_forward(X, mlp, F.MODE_RESIDUAL, coeffs)
+    u2, r2, _ = plan.solver_forward(X, mlp, F.MODE_RESIDUAL, coeffs)
+    assert torch.equal(r1, r2) and torch.equal(u1, u2) and bool(torch.isfinite(r1).all())
+    full, _ = plan.solver_backward(X, mlp, theta, None, gr, F.MODE_RESIDUAL, coeffs)
+    full = [v.clone() for v in full]
+    half = n_pts // 2
+    a, _ = plan.solver_backward(X[:half].contiguous(), mlp, theta, None, gr[:half].contiguous(),
+                                F.MODE_RESIDUAL, coeffs)
+    a = [v.clone() for v in a]
+    b, _ = plan.solver_backward(X[half:].contiguous(), mlp, theta, None, gr[half:].contiguous(),
+                                F.MODE_RESIDUAL, coeffs)
+    for f_, a_, b_ in zip(full, a, b):
+        assert rel_err(a_ + b_, f_) < 1e-10
+    idx = torch.arange(0, n_pts, n_pts // 64, device=DEV)
+    Xs = X[idx].cpu()
+    _, ro = osolver.diffusion_operator(oracle, Xs[:, 0:1].clone(), Xs[:, 1:2].clone(), Xs[:, 2:3].clone())
+    assert rel_err(r1[idx], ro[:, 0]) < 1e-10
+
+
+def test_abi_error_reporting():
+    lib = qb._lib.load()
+    import ctypes
+    handle = ctypes.c_void_p()
+    ops = (ctypes.c_int32 * 4)(0, 9, -1, 0)            # wire 9 on a 4-qubit plan
+    rc = lib.qcp_plan_create(ctypes.byref(handle), 4, 0, 1, 50, ops, 1, None, 0, 1)
+    assert rc != 0 and b"invalid" in lib.qcp_last_error()
+    rc = lib.qcp_plan_create(ctypes.byref(handle), 9, 0, 1, 50, ops, 0, None, 0, 0)
+    assert rc != 0 and b"qubits" in lib.qcp_last_error()
+    prog = qb.program.compile_program("cascade", 4, 1)
+    plan = F.Plan(prog, 0, torch.float64, 50, DEV)
+    with pytest.raises(RuntimeError, match="qcp_prepare"):
+        plan.layer_forward(torch.zeros(3, 4, dtype=torch.float64, device=DEV))
+    with pytest.raises(ValueError):
+        plan.prepare(torch.zeros(5, dtype=torch.float64, device=DEV))
+    with pytest.raises(RuntimeError, match="plan on"):
+        plan._t(torch.zeros(3))

@@ -1,0 +1,66 @@
+"""CPU checks of the host-side circuit compiler and of the Heisenberg-picture derivation the CUDA
+library implements (feature matrix C with <Z_i>(z) = C phi(z)), against the oracle."""
+
+import numpy as np
+import pytest
+import torch
+
+import feature_model as fm
+import qcpinn_b200 as qb
+from oracle import circuits as oc
+
+P = qb.program
+
+
+@pytest.mark.parametrize("ansatz", oc.ANSATZ_NAMES)
+@pytest.mark.parametrize("n", [2, 3, 4])
+def test_program_matches_oracle_for_both_encodings(ansatz, n):
+    if ansatz == "alternate" and n % 2 == 0:
+        pytest.skip("reference over-indexes (separate test)")
+    if ansatz == "sim_circ_15" and n == 3:
+        pytest.skip("CNOT(c, (c+3)%3) acts on one wire: invalid in the reference as well")
+    g = torch.Generator().manual_seed(n)
+    for layers in (1, 2):
+        for seed in (None, 1):
+            prog = P.compile_program(ansatz, n, layers, seed)
+            assert prog.n_theta == layers * oc.params_per_layer(ansatz, n)
+            th = torch.randn(layers, prog.params_per_layer, generator=g, dtype=torch.float64)
+            V = fm.program_unitary(prog, th)
+            assert np.abs(V.conj().T @ V - np.eye(2 ** n)).max() < 1e-12
+            O = fm.observables(V, n)
+            z = torch.randn(5, n, generator=g, dtype=torch.float64)
+            haar = oc.haar_for(seed, n)
+            want = oc.quantum_layer(z, th, ansatz, n, "angle", haar).numpy()
+            got = fm.feature_matrix_angle(O, n) @ fm.features_angle(z.numpy()).T
+            assert np.abs(got - want).max() < 1e-12
+            want = oc.quantum_layer(z, th, ansatz, n, "amplitude", haar).numpy()
+            got = fm.feature_matrix_amplitude(O, n) @ fm.features_amplitude(z.numpy()).T
+            assert np.abs(got - want).max() < 1e-12
+
+
+def test_gate_table_layout():
+    prog = P.compile_program("cascade", 4, 1, 1)
+    ops = prog.ops.tolist()
+    assert ops[0] == [P.RX, 0, -1, 0] and ops[8] == [P.CRX, 3, 0, 8] and ops[11] == [P.CRX, 0, 1, 11]
+    assert ops[-3:] == [[P.U4, 0, 1, 0], [P.U4, 2, 3, 1], [P.HAD, 3, -1, -1]]
+    assert prog.consts.shape == (2, 4, 4) and prog.ops.dtype == np.int32
+    # Haar only with a seed AND n >= 4 (reference nn/DVQuantumLayer.py:88-94)
+    assert P.compile_program("cascade", 3, 1, 1).consts.shape[0] == 0
+    assert P.compile_program("cascade", 4, 1, None).consts.shape[0] == 0
+    # second layer indexes the second row of the (L, P) angle matrix
+    two = P.compile_program("layered", 4, 2, None)
+    assert two.ops[two.ops[:, 3] >= 0][:, 3].tolist() == list(range(32))
+
+
+def test_error_paths_match_reference():
+    with pytest.raises(ValueError, match="Parameters are not initialized"):
+        P.compile_program("nope", 4, 1)
+    with pytest.raises(IndexError):           # alternate, even n
+        P.compile_program("alternate", 4, 1)
+    assert P.compile_program("alternate", 5, 1).n_theta == 16
+
+
+def test_haar_pair_is_scipy_reproducible():
+    u1, u2 = P.haar_pair(1)
+    r1, r2 = oc.haar_unitaries(1)
+    assert np.array_equal(u1, r1) and np.array_equal(u2, r2)
