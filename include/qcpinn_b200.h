@@ -102,16 +102,24 @@ int qcp_layer_backward(qcp_plan_t* plan, const void* theta, const void* z, const
  * X [B,3] -> u [B], r [B] (NULL in value mode), streams [B,6] (optional, may be NULL). */
 int qcp_solver_forward(qcp_plan_t* plan, const qcp_mlp_t* weights, const void* X, long long batch,
                        int mode, const double* coeffs, void* u, void* r, void* streams,
-                       void* stream);
+                       void* save, void* stream);
+
+/* Elements (of the plan dtype) of the optional ``save`` workspace of a (batch, mode) call:
+ * 2 * n_qubits * mode * batch.  When ``save`` is given, the forward stores the Taylor jets of the
+ * pre-MLP outputs z and of the expectation values q in it (component-major, coalesced) and the
+ * backward runs as three lean kernels over them instead of recomputing the forward. */
+long long qcp_solver_workspace_elems(const qcp_plan_t* plan, long long batch, int mode);
 
 /* Reverse mode of the above: given grad_u / grad_r [B] (either may be NULL) write (overwrite, not
  * accumulate) the gradient of every weight tensor, of theta [n_theta], and optionally of X [B,3]
- * (value mode only; NULL otherwise).  Replaces loss.backward() through the nested-autograd graph
- * (reference trainer/diffusion_train.py:81). */
+ * (value mode only; NULL otherwise).  ``save`` is the workspace filled by the matching forward call
+ * (it is consumed: overwritten with cotangents) or NULL to recompute the forward from X inside one
+ * fused kernel.  Replaces loss.backward() through the nested-autograd graph (reference
+ * trainer/diffusion_train.py:81). */
 int qcp_solver_backward(qcp_plan_t* plan, const qcp_mlp_t* weights, const void* theta,
                         const void* X, const void* grad_u, const void* grad_r, long long batch,
-                        int mode, const double* coeffs, const qcp_mlp_t* grads, void* grad_theta,
-                        void* grad_X, void* stream);
+                        int mode, const double* coeffs, void* save, const qcp_mlp_t* grads,
+                        void* grad_theta, void* grad_X, void* stream);
 
 /* FMA-pipe micro-benchmark used as the roofline denominator: runs
  * ``iters`` dependent-chain FMA rounds on every SM and returns achieved FLOP/s. */

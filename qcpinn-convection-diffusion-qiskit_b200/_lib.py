@@ -41,9 +41,10 @@ SIGNATURES = {
     "qcp_layer_backward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_void_p,
                                     _c_void_p, _c_void_p]),
     "qcp_solver_forward": (_c_int, [_c_void_p, ctypes.POINTER(QcpMlp), _c_void_p, _c_ll, _c_int,
-                                    _dptr, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+                                    _dptr, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "qcp_solver_workspace_elems": (_c_ll, [_c_void_p, _c_ll, _c_int]),
     "qcp_solver_backward": (_c_int, [_c_void_p, ctypes.POINTER(QcpMlp), _c_void_p, _c_void_p,
-                                     _c_void_p, _c_void_p, _c_ll, _c_int, _dptr,
+                                     _c_void_p, _c_void_p, _c_ll, _c_int, _dptr, _c_void_p,
                                      ctypes.POINTER(QcpMlp), _c_void_p, _c_void_p, _c_void_p]),
     "qcp_bench_fma": (_c_int, [_c_int, _c_int, _dptr, _c_void_p]),
 }

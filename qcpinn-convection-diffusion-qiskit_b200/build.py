@@ -45,9 +45,12 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+EXTRA_DEFINES: list[str] = []
+
+
 def _compile(src: str, verbose: bool) -> Path:
     obj = BUILD_DIR / (Path(src).stem + ".o")
-    cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+    cmd = [_nvcc(), *NVCC_FLAGS, *EXTRA_DEFINES, "-c", str(CSRC / src), "-o", str(obj)]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -58,8 +61,16 @@ def _compile(src: str, verbose: bool) -> Path:
     return obj
 
 
-def build_library(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA source for sm_100a and link the shared library (idempotent)."""
+def build_library(force: bool = False, verbose: bool = False, out: Path | None = None,
+                  defines: list[str] | None = None) -> Path:
+    """Compile every CUDA source for sm_100a and link the shared library (idempotent).
+    ``out`` / ``defines`` build an experimental variant next to the default library."""
+    global BUILD_DIR, LIB_PATH
+    if out is not None or defines:
+        EXTRA_DEFINES[:] = [f"-D{d}" for d in (defines or [])]
+        LIB_PATH = Path(out) if out is not None else LIB_PATH
+        BUILD_DIR = CSRC / "build" / ("variant_" + LIB_PATH.stem)
+        force = True
     BUILD_DIR.mkdir(parents=True, exist_ok=True)
     stamp = BUILD_DIR / "digest.txt"
     digest = _digest()
@@ -80,6 +91,8 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true", help="keep ptxas -v output in csrc/build/")
+    ap.add_argument("--out", default=None, help="write an experimental variant to this path")
+    ap.add_argument("-D", dest="defines", action="append", default=[], help="extra -D macro")
     ns = ap.parse_args()
-    print(build_library(force=ns.force, verbose=ns.verbose))
+    print(build_library(force=ns.force, verbose=ns.verbose, out=ns.out, defines=ns.defines))
     sys.exit(0)

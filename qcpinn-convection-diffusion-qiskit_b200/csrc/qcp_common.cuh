@@ -15,7 +15,7 @@ constexpr int kCStride = 4;          // feature-matrix row stride (outputs padde
 constexpr int kMaxHidden = 128;      // hidden width of the pre/post MLP held in shared memory
 constexpr int kWarpsPerBlock = 4;
 constexpr int kThreads = kWarpsPerBlock * 32;
-constexpr int kStageRows = 64;       // rows of the per-warp gradient staging tile
+constexpr int kStageRows = 32;       // rows of the per-warp gradient staging tile
 constexpr int kStagePitch = 33;      // +1 padding: column sums are bank-conflict free
 
 // One gate of the batch-shared circuit program (ansatz layers, Haar blocks, final Hadamard).
@@ -49,6 +49,7 @@ struct SolverArgs {
   const void* gr;      // [B]        backward in (may be null => 0)
   void* gX;            // [B,3]      backward out or null
   void* partials;      // [grid, nacc] backward out (plan-owned)
+  void* ws;            // saved-jet workspace [2][n*S][B] or null (forward: save; split backward: use)
   long long B;
   int H;
   PdeCoeffs pde;
@@ -75,6 +76,10 @@ __host__ __device__ constexpr int nacc_solver(int n, int enc, int H) {
   return 1 + H * (n + 2) + num_features(n, enc) * n + n + H * (4 + n);
 }
 
+struct SplitGrids {
+  int post, contract, pre;
+};
+
 void set_error(const char* fmt, ...);
 
 // per-dtype launchers (qcp_point_f32.cu / qcp_point_f64.cu)
@@ -86,6 +91,12 @@ template <typename T>
 int launch_layer_forward(int n, int enc, const LayerArgs& a, int grid, cudaStream_t s);
 template <typename T>
 int launch_layer_backward(int n, int enc, const LayerArgs& a, int grid, cudaStream_t s);
+template <typename T>
+int solver_split_grids(int n, int enc, int mode, int H, int num_sms, SplitGrids* g);
+template <typename T>
+int launch_solver_backward_split(int n, int enc, int mode, const SolverArgs& a, const SplitGrids& g,
+                                 void* part_post, void* part_contract, void* part_pre,
+                                 cudaStream_t s);
 template <typename T>
 size_t solver_backward_smem(int n, int enc, int H);
 template <typename T>

@@ -1,21 +1,33 @@
 // qcpinn_b200 -- truncated Taylor "jets" carried by one collocation point.
 //
 // The convection-diffusion residual (reference nn/pde.py:53-72) needs u, u_t, u_x, u_y, u_xx, u_yy.
-// Instead of five nested autograd sweeps we push a 6-component jet through every operation:
+// Instead of five nested autograd sweeps we push a small jet through every operation.  Every forward
+// rule has a hand-derived pullback, so the backward kernels are the exact adjoint of the forward.
 //
-//   c[0] value | c[1] d/dt | c[2] d/dx | c[3] d/dy | c[4] d2/dx2 | c[5] d2/dy2
-//
-// (no second t-derivative is needed).  S = 1 degenerates to the plain value (IC / BC points,
-// reference trainer/diffusion_train.py:40-41).  Every forward rule has a hand-derived pullback so
-// the backward kernel is the exact adjoint of the six-stream forward.
+// Component layout of a jet with S components:
+//   c[0]                         value
+//   c[1 .. N1]                   first derivatives along directions WITHOUT a second derivative
+//   c[1+N1 .. N1+N2]             first derivatives along directions WITH a second derivative
+//   c[1+N1+N2 .. N1+2*N2]        the matching pure second derivatives
+// S = 6 -> (N1, N2) = (1, 2): (u, u_t | u_x, u_y | u_xx, u_yy)   the full residual jet
+// S = 4 -> (1, 1): (u, u_t | u_x | u_xx)   and   S = 3 -> (0, 1): (u | u_y | u_yy)
+//          sub-jets that let the S = 6 adjoint run as two register-light passes
+// S = 1 -> (0, 0): plain value (IC / BC points, reference trainer/diffusion_train.py:40-41)
 #pragma once
 
 #include <cuda_runtime.h>
 
 namespace qcp {
 
+__host__ __device__ constexpr int jet_n2(int S) { return S == 6 ? 2 : (S >= 3 ? 1 : 0); }
+__host__ __device__ constexpr int jet_n1(int S) { return S - 1 - 2 * jet_n2(S); }
+
 template <typename T, int S>
 struct Jet {
+  static constexpr int N2 = jet_n2(S);
+  static constexpr int N1 = jet_n1(S);
+  static constexpr int P0 = 1 + N1;        // first "paired" first-derivative slot
+  static constexpr int E0 = 1 + N1 + N2;   // first second-derivative slot
   T c[S];
 };
 
@@ -50,16 +62,16 @@ __device__ __forceinline__ T jdot(const Jet<T, S>& a, const Jet<T, S>& b) {
 // product rule:  (ab)_d = a_d b + a b_d ;  (ab)_dd = a_dd b + 2 a_d b_d + a b_dd
 template <typename T, int S>
 __device__ __forceinline__ Jet<T, S> jmul(const Jet<T, S>& a, const Jet<T, S>& b) {
-  Jet<T, S> r;
+  using J = Jet<T, S>;
+  J r;
   r.c[0] = a.c[0] * b.c[0];
-  if constexpr (S == 6) {
 #pragma unroll
-    for (int i = 1; i <= 3; ++i) r.c[i] = fma(a.c[i], b.c[0], a.c[0] * b.c[i]);
+  for (int i = 1; i < J::E0; ++i) r.c[i] = fma(a.c[i], b.c[0], a.c[0] * b.c[i]);
 #pragma unroll
-    for (int e = 4; e <= 5; ++e) {
-      T t = fma(a.c[e], b.c[0], a.c[0] * b.c[e]);
-      r.c[e] = fma(T(2) * a.c[e - 2], b.c[e - 2], t);
-    }
+  for (int k = 0; k < J::N2; ++k) {
+    const int e = J::E0 + k, p = J::P0 + k;
+    const T t = fma(a.c[e], b.c[0], a.c[0] * b.c[e]);
+    r.c[e] = fma(T(2) * a.c[p], b.c[p], t);
   }
   return r;
 }
@@ -67,66 +79,75 @@ __device__ __forceinline__ Jet<T, S> jmul(const Jet<T, S>& a, const Jet<T, S>& b
 // acc += a * b
 template <typename T, int S>
 __device__ __forceinline__ void jmul_acc(Jet<T, S>& acc, const Jet<T, S>& a, const Jet<T, S>& b) {
+  using J = Jet<T, S>;
   acc.c[0] = fma(a.c[0], b.c[0], acc.c[0]);
-  if constexpr (S == 6) {
 #pragma unroll
-    for (int i = 1; i <= 3; ++i) acc.c[i] = fma(a.c[i], b.c[0], fma(a.c[0], b.c[i], acc.c[i]));
+  for (int i = 1; i < J::E0; ++i) acc.c[i] = fma(a.c[i], b.c[0], fma(a.c[0], b.c[i], acc.c[i]));
 #pragma unroll
-    for (int e = 4; e <= 5; ++e) {
-      T t = fma(a.c[e], b.c[0], fma(a.c[0], b.c[e], acc.c[e]));
-      acc.c[e] = fma(T(2) * a.c[e - 2], b.c[e - 2], t);
-    }
+  for (int k = 0; k < J::N2; ++k) {
+    const int e = J::E0 + k, p = J::P0 + k;
+    const T t = fma(a.c[e], b.c[0], fma(a.c[0], b.c[e], acc.c[e]));
+    acc.c[e] = fma(T(2) * a.c[p], b.c[p], t);
   }
 }
 
 // Pullback of c = a*b w.r.t. b:  bbar += (d c / d b)^T cbar, with the other factor a.
+// Linear in cbar, so the partial cotangents of a two-pass adjoint can be pulled independently.
 template <typename T, int S>
 __device__ __forceinline__ void jmul_pull_acc(Jet<T, S>& bbar, const Jet<T, S>& cbar,
                                               const Jet<T, S>& a) {
-  bbar.c[0] = fma(cbar.c[0], a.c[0], bbar.c[0]);
-  if constexpr (S == 6) {
+  using J = Jet<T, S>;
+  T s0 = fma(cbar.c[0], a.c[0], bbar.c[0]);
 #pragma unroll
-    for (int i = 1; i <= 5; ++i) bbar.c[0] = fma(cbar.c[i], a.c[i], bbar.c[0]);
-    bbar.c[1] = fma(cbar.c[1], a.c[0], bbar.c[1]);
+  for (int i = 1; i < S; ++i) s0 = fma(cbar.c[i], a.c[i], s0);
+  bbar.c[0] = s0;
 #pragma unroll
-    for (int i = 2; i <= 3; ++i)
-      bbar.c[i] = fma(cbar.c[i], a.c[0], fma(T(2) * cbar.c[i + 2], a.c[i], bbar.c[i]));
+  for (int i = 1; i < J::P0; ++i) bbar.c[i] = fma(cbar.c[i], a.c[0], bbar.c[i]);
 #pragma unroll
-    for (int e = 4; e <= 5; ++e) bbar.c[e] = fma(cbar.c[e], a.c[0], bbar.c[e]);
+  for (int k = 0; k < J::N2; ++k) {
+    const int e = J::E0 + k, p = J::P0 + k;
+    bbar.c[p] = fma(cbar.c[p], a.c[0], fma(T(2) * cbar.c[e], a.c[p], bbar.c[p]));
+    bbar.c[e] = fma(cbar.c[e], a.c[0], bbar.c[e]);
   }
 }
 
 // c = f(a) with f0 = f(a0), f1 = f'(a0), f2 = f''(a0)
 template <typename T, int S>
 __device__ __forceinline__ Jet<T, S> jfunc(const Jet<T, S>& a, T f0, T f1, T f2) {
-  Jet<T, S> r;
+  using J = Jet<T, S>;
+  J r;
   r.c[0] = f0;
-  if constexpr (S == 6) {
 #pragma unroll
-    for (int i = 1; i <= 3; ++i) r.c[i] = f1 * a.c[i];
+  for (int i = 1; i < J::E0; ++i) r.c[i] = f1 * a.c[i];
 #pragma unroll
-    for (int e = 4; e <= 5; ++e) r.c[e] = fma(f1, a.c[e], f2 * a.c[e - 2] * a.c[e - 2]);
+  for (int k = 0; k < J::N2; ++k) {
+    const int e = J::E0 + k, p = J::P0 + k;
+    r.c[e] = fma(f1, a.c[e], f2 * a.c[p] * a.c[p]);
   }
   return r;
 }
 
-// Pullback of c = f(a):  abar += (d c / d a)^T cbar   (needs f''' for the second-order rows).
+// Pullback of c = f(a):  abar += (d c / d a)^T cbar  (f3 = third derivative, needed by the
+// second-order rows).
 template <typename T, int S>
 __device__ __forceinline__ void jfunc_pull_acc(Jet<T, S>& abar, const Jet<T, S>& cbar,
                                                const Jet<T, S>& a, T f1, T f2, T f3) {
+  using J = Jet<T, S>;
   T s0 = cbar.c[0] * f1;
-  if constexpr (S == 6) {
 #pragma unroll
-    for (int i = 1; i <= 3; ++i) s0 = fma(cbar.c[i] * f2, a.c[i], s0);
+  for (int i = 1; i < J::E0; ++i) s0 = fma(cbar.c[i] * f2, a.c[i], s0);
 #pragma unroll
-    for (int e = 4; e <= 5; ++e)
-      s0 = fma(cbar.c[e], fma(f2, a.c[e], f3 * a.c[e - 2] * a.c[e - 2]), s0);
-    abar.c[1] = fma(cbar.c[1], f1, abar.c[1]);
+  for (int k = 0; k < J::N2; ++k) {
+    const int e = J::E0 + k, p = J::P0 + k;
+    s0 = fma(cbar.c[e], fma(f2, a.c[e], f3 * a.c[p] * a.c[p]), s0);
+  }
 #pragma unroll
-    for (int i = 2; i <= 3; ++i)
-      abar.c[i] = fma(cbar.c[i], f1, fma(T(2) * cbar.c[i + 2] * f2, a.c[i], abar.c[i]));
+  for (int i = 1; i < J::P0; ++i) abar.c[i] = fma(cbar.c[i], f1, abar.c[i]);
 #pragma unroll
-    for (int e = 4; e <= 5; ++e) abar.c[e] = fma(cbar.c[e], f1, abar.c[e]);
+  for (int k = 0; k < J::N2; ++k) {
+    const int e = J::E0 + k, p = J::P0 + k;
+    abar.c[p] = fma(cbar.c[p], f1, fma(T(2) * cbar.c[e] * f2, a.c[p], abar.c[p]));
+    abar.c[e] = fma(cbar.c[e], f1, abar.c[e]);
   }
   abar.c[0] += s0;
 }

@@ -226,18 +226,35 @@ prepare_kernel(int n, int enc, const GateOp* ops, int n_ops, const T* theta, con
 // ---------------------------------------------------------------------------------------------
 // reduce the per-block partial sums and scatter them to the caller's gradient tensors
 // ---------------------------------------------------------------------------------------------
+// The per-point kernels push d C in (a, i, b) order for angle encoding (a / b = feature index of the
+// first ceil(n/2) / remaining qubits) and in (s, i) order for amplitude encoding; Cbar is [s][i].
+__device__ __forceinline__ int cbar_index(int r, int n, int enc) {
+  if (enc != QCP_ENC_ANGLE) return r;
+  const int FB = ipow3(n - (n + 1) / 2);
+  const int b = r % FB, i = (r / FB) % n, a = r / (FB * n);
+  return (a * FB + b) * n + i;
+}
+
 struct ScatterArgs {
   void *w1, *b1, *w2, *b2, *w3, *b3, *w4, *b4;
   double* Cbar;   // [F][n]
-  int n, H, F, grid, nacc;
+  int n, H, F, nacc, enc;
+  // up to three consecutive accumulator segments, each with its own partial buffer and grid
+  const void* seg_ptr[3];
+  int seg_len[3];
+  int seg_grid[3];
 };
 
 template <typename T>
-__global__ void reduce_solver_kernel(const T* __restrict__ partials, const ScatterArgs a) {
+__global__ void reduce_solver_kernel(const ScatterArgs a) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.nacc) return;
+  int seg = 0, local = idx;
+  while (seg < 2 && local >= a.seg_len[seg]) { local -= a.seg_len[seg]; ++seg; }
+  const T* partials = static_cast<const T*>(a.seg_ptr[seg]);
+  const int len = a.seg_len[seg];
   double s = 0.0;
-  for (int g = 0; g < a.grid; ++g) s += (double)partials[(size_t)g * a.nacc + idx];
+  for (int g = 0; g < a.seg_grid[seg]; ++g) s += (double)partials[(size_t)g * len + local];
   const int n = a.n, H = a.H;
   int r = idx;
   if (r == 0) { static_cast<T*>(a.b4)[0] = (T)s; return; }
@@ -250,7 +267,7 @@ __global__ void reduce_solver_kernel(const T* __restrict__ partials, const Scatt
     return;
   }
   r -= H * (n + 2);
-  if (r < a.F * n) { a.Cbar[r] = s; return; }
+  if (r < a.F * n) { a.Cbar[cbar_index(r, n, a.enc)] = s; return; }
   r -= a.F * n;
   if (r < n) { static_cast<T*>(a.b2)[r] = (T)s; return; }
   r -= n;
@@ -263,12 +280,13 @@ __global__ void reduce_solver_kernel(const T* __restrict__ partials, const Scatt
 }
 
 template <typename T>
-__global__ void reduce_layer_kernel(const T* __restrict__ partials, double* Cbar, int grid, int nacc) {
+__global__ void reduce_layer_kernel(const T* __restrict__ partials, double* Cbar, int grid, int nacc,
+                                    int n, int enc) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nacc) return;
   double s = 0.0;
   for (int g = 0; g < grid; ++g) s += (double)partials[(size_t)g * nacc + idx];
-  Cbar[idx] = s;
+  Cbar[cbar_index(idx, n, enc)] = s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -418,6 +436,8 @@ struct qcp_plan {
   void* d_partials;
   size_t partials_elems;
   int grid_cache[2];   // persistent grid of the backward kernel per mode (0: value, 1: residual)
+  SplitGrids split_cache[2];
+  bool split_ready[2];
   bool prepared;
 };
 
@@ -610,9 +630,9 @@ int qcp_layer_backward(qcp_plan_t* p, const void* theta, const void* z, const vo
   if (rc) return rc;
   const int rb = (nacc + 127) / 128;
   if (p->dtype == QCP_F64)
-    reduce_layer_kernel<double><<<rb, 128, 0, s>>>(static_cast<const double*>(p->d_partials), p->d_Cbar, grid, nacc);
+    reduce_layer_kernel<double><<<rb, 128, 0, s>>>(static_cast<const double*>(p->d_partials), p->d_Cbar, grid, nacc, p->n, p->enc);
   else
-    reduce_layer_kernel<float><<<rb, 128, 0, s>>>(static_cast<const float*>(p->d_partials), p->d_Cbar, grid, nacc);
+    reduce_layer_kernel<float><<<rb, 128, 0, s>>>(static_cast<const float*>(p->d_partials), p->d_Cbar, grid, nacc, p->n, p->enc);
   QCP_CUDA(cudaGetLastError());
   return run_theta_grad(p, theta, grad_theta, s);
 }
@@ -631,15 +651,21 @@ static int check_mode(int mode, const double* coeffs, const char* who) {
   return 0;
 }
 
+long long qcp_solver_workspace_elems(const qcp_plan_t* p, long long B, int mode) {
+  if (!p || B < 0 || (mode != QCP_MODE_VALUE && mode != QCP_MODE_RESIDUAL)) return -1;
+  return 2LL * p->n * mode * B;
+}
+
 int qcp_solver_forward(qcp_plan_t* p, const qcp_mlp_t* w, const void* X, long long B, int mode,
-                       const double* coeffs, void* u, void* r, void* streams, void* stream) {
+                       const double* coeffs, void* u, void* r, void* streams, void* save,
+                       void* stream) {
   if (!p || !w || (B > 0 && (!X || !u))) { set_error("qcp_solver_forward: NULL argument"); return 1; }
   if (!p->prepared) { set_error("qcp_solver_forward: qcp_prepare() has not run"); return 1; }
   if (check_mode(mode, coeffs, "qcp_solver_forward")) return 1;
   if (B <= 0) return 0;
   SolverArgs a{};
   fill_solver_args(a, p, w, X, B, coeffs);
-  a.u = u; a.r = r; a.streams = streams;
+  a.u = u; a.r = r; a.streams = streams; a.ws = save;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int grid = forward_grid(p, B);
   return p->dtype == QCP_F64 ? launch_solver_forward<double>(p->n, p->enc, mode, a, grid, s)
@@ -648,42 +674,71 @@ int qcp_solver_forward(qcp_plan_t* p, const qcp_mlp_t* w, const void* X, long lo
 
 int qcp_solver_backward(qcp_plan_t* p, const qcp_mlp_t* w, const void* theta, const void* X,
                         const void* grad_u, const void* grad_r, long long B, int mode,
-                        const double* coeffs, const qcp_mlp_t* g, void* grad_theta, void* grad_X,
-                        void* stream) {
+                        const double* coeffs, void* save, const qcp_mlp_t* g, void* grad_theta,
+                        void* grad_X, void* stream) {
   if (!p || !w || !theta || !g || !grad_theta || (B > 0 && !X)) { set_error("qcp_solver_backward: NULL argument"); return 1; }
   if (!p->prepared) { set_error("qcp_solver_backward: qcp_prepare() has not run"); return 1; }
   if (check_mode(mode, coeffs, "qcp_solver_backward")) return 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int nacc = nacc_solver(p->n, p->enc, p->H);
-  int& cached = p->grid_cache[mode == QCP_MODE_RESIDUAL ? 1 : 0];
-  if (cached == 0)
-    cached = p->dtype == QCP_F64
-                 ? solver_backward_max_grid<double>(p->n, p->enc, mode, p->H, p->num_sms)
-                 : solver_backward_max_grid<float>(p->n, p->enc, mode, p->H, p->num_sms);
-  long long blocks = (B + kThreads - 1) / kThreads;
-  if (blocks > cached) blocks = cached;
-  if (blocks < 1) blocks = 1;
-  const int grid = (int)blocks;
-  if (ensure_partials(p, (size_t)grid * nacc)) return 1;
+  const int mi = mode == QCP_MODE_RESIDUAL ? 1 : 0;
+  const bool f64 = p->dtype == QCP_F64;
   SolverArgs a{};
   fill_solver_args(a, p, w, X, B > 0 ? B : 0, coeffs);
-  a.gu = grad_u; a.gr = grad_r; a.gX = grad_X; a.partials = p->d_partials;
-  if (B > 0) {
-    int rc = p->dtype == QCP_F64 ? launch_solver_backward<double>(p->n, p->enc, mode, a, grid, s)
-                                 : launch_solver_backward<float>(p->n, p->enc, mode, a, grid, s);
-    if (rc) return rc;
-  } else {
-    QCP_CUDA(cudaMemsetAsync(p->d_partials, 0, elem_size(p->dtype) * (size_t)grid * nacc, s));
-  }
+  a.gu = grad_u; a.gr = grad_r; a.gX = grad_X; a.ws = save;
   ScatterArgs sc{};
   sc.w1 = g->w1; sc.b1 = g->b1; sc.w2 = g->w2; sc.b2 = g->b2;
   sc.w3 = g->w3; sc.b3 = g->b3; sc.w4 = g->w4; sc.b4 = g->b4;
-  sc.Cbar = p->d_Cbar; sc.n = p->n; sc.H = p->H; sc.F = p->F; sc.grid = grid; sc.nacc = nacc;
+  sc.Cbar = p->d_Cbar; sc.n = p->n; sc.H = p->H; sc.F = p->F; sc.nacc = nacc; sc.enc = p->enc;
+  const size_t es = elem_size(p->dtype);
+  const long long want_blocks = B > 0 ? (B + kThreads - 1) / kThreads : 1;
+
+  if (save && B > 0) {
+    // split path: three kernels over the jets saved by the forward
+    if (!p->split_ready[mi]) {
+      int rc = f64 ? solver_split_grids<double>(p->n, p->enc, mode, p->H, p->num_sms, &p->split_cache[mi])
+                   : solver_split_grids<float>(p->n, p->enc, mode, p->H, p->num_sms, &p->split_cache[mi]);
+      if (rc) return rc;
+      p->split_ready[mi] = true;
+    }
+    SplitGrids gr = p->split_cache[mi];
+    if (gr.post > want_blocks) gr.post = (int)want_blocks;
+    if (gr.contract > want_blocks) gr.contract = (int)want_blocks;
+    if (gr.pre > want_blocks) gr.pre = (int)want_blocks;
+    const int n0 = 1 + p->H * (p->n + 2), n1 = p->F * p->n, n2 = nacc - n0 - n1;
+    const size_t e0 = (size_t)gr.post * n0, e1 = (size_t)gr.contract * n1, e2 = (size_t)gr.pre * n2;
+    if (ensure_partials(p, e0 + e1 + e2)) return 1;
+    char* base = static_cast<char*>(p->d_partials);
+    void* p0 = base; void* p1 = base + e0 * es; void* p2 = base + (e0 + e1) * es;
+    int rc = f64 ? launch_solver_backward_split<double>(p->n, p->enc, mode, a, gr, p0, p1, p2, s)
+                 : launch_solver_backward_split<float>(p->n, p->enc, mode, a, gr, p0, p1, p2, s);
+    if (rc) return rc;
+    sc.seg_ptr[0] = p0; sc.seg_len[0] = n0; sc.seg_grid[0] = gr.post;
+    sc.seg_ptr[1] = p1; sc.seg_len[1] = n1; sc.seg_grid[1] = gr.contract;
+    sc.seg_ptr[2] = p2; sc.seg_len[2] = n2; sc.seg_grid[2] = gr.pre;
+  } else {
+    // fused path: recompute the forward from X inside one kernel (no workspace needed)
+    int& cached = p->grid_cache[mi];
+    if (cached == 0)
+      cached = f64 ? solver_backward_max_grid<double>(p->n, p->enc, mode, p->H, p->num_sms)
+                   : solver_backward_max_grid<float>(p->n, p->enc, mode, p->H, p->num_sms);
+    const int grid = (int)(want_blocks > cached ? cached : want_blocks);
+    if (ensure_partials(p, (size_t)grid * nacc)) return 1;
+    a.partials = p->d_partials;
+    if (B > 0) {
+      int rc = f64 ? launch_solver_backward<double>(p->n, p->enc, mode, a, grid, s)
+                   : launch_solver_backward<float>(p->n, p->enc, mode, a, grid, s);
+      if (rc) return rc;
+    } else {
+      QCP_CUDA(cudaMemsetAsync(p->d_partials, 0, es * (size_t)grid * nacc, s));
+    }
+    sc.seg_ptr[0] = p->d_partials; sc.seg_len[0] = nacc; sc.seg_grid[0] = grid;
+    sc.seg_ptr[1] = p->d_partials; sc.seg_len[1] = 0; sc.seg_grid[1] = 0;
+    sc.seg_ptr[2] = p->d_partials; sc.seg_len[2] = 0; sc.seg_grid[2] = 0;
+  }
   const int rb = (nacc + 127) / 128;
-  if (p->dtype == QCP_F64)
-    reduce_solver_kernel<double><<<rb, 128, 0, s>>>(static_cast<const double*>(p->d_partials), sc);
-  else
-    reduce_solver_kernel<float><<<rb, 128, 0, s>>>(static_cast<const float*>(p->d_partials), sc);
+  if (f64) reduce_solver_kernel<double><<<rb, 128, 0, s>>>(sc);
+  else reduce_solver_kernel<float><<<rb, 128, 0, s>>>(sc);
   QCP_CUDA(cudaGetLastError());
   return run_theta_grad(p, theta, grad_theta, s);
 }

@@ -14,10 +14,18 @@
 // w_j = cos z_j, hence phi(z) = (x)_j (1, y_j, w_j) (3^n real features); for amplitude encoding
 // phi_ab = f_a f_b / |f|^2 (n(n+1)/2 features).
 //
-// The backward kernel recomputes the forward from X (12 B/point) instead of saving ~1 KB/point of
-// intermediates, runs the hand-derived pullbacks of every jet operation, and sums the per-point
-// parameter-gradient contributions across the warp through a padded shared-memory staging tile.
+// Backward, two ways:
+//   * split (default for training): the forward saves the jets of z (pre-MLP output) and q (<Z_i>)
+//     in a component-major workspace; post_backward / contract_backward / pre_backward then run as
+//     three lean kernels, each with its own register budget, handing cotangent jets through the
+//     same workspace.  The S = 6 contraction adjoint can run as two sub-jet passes (qcp_jet.cuh).
+//   * fused: one kernel recomputes the forward from X (12 B/point), no workspace.
+// Per-point parameter-gradient contributions are summed across the warp through a padded
+// shared-memory staging tile, per block in shared accumulators, and across blocks by
+// reduce_solver_kernel (deterministic: no atomics anywhere).
 #pragma once
+
+#include <type_traits>
 
 #include "qcp_common.cuh"
 #include "qcp_jet.cuh"
@@ -25,7 +33,88 @@
 namespace qcp {
 
 // ------------------------------------------------------------------------------------------
-// shared-memory image of the weights
+// occupancy knobs: min resident blocks per SM handed to __launch_bounds__ (tuned on B200 with
+// tools/kbench.py; the register caps they imply are checked with -Xptxas -v)
+// ------------------------------------------------------------------------------------------
+// Encoded as decimal digits  FWD FUSED POST CONTRACT PRE TWOPASS ROLL  (one macro per kernel family
+// so variants can be built with a single -D).
+#ifndef QCP_TUNE_F64_6
+#define QCP_TUNE_F64_6 1122310
+#endif
+#ifndef QCP_TUNE_F32_6
+#define QCP_TUNE_F32_6 2332401
+#endif
+#ifndef QCP_TUNE_F64_1
+#define QCP_TUNE_F64_1 3243400
+#endif
+#ifndef QCP_TUNE_F32_1
+#define QCP_TUNE_F32_1 4444401
+#endif
+
+template <int V>
+struct TuneValues {
+  static constexpr int kFwd = (V / 1000000) % 10, kFused = (V / 100000) % 10,
+                       kPost = (V / 10000) % 10, kContract = (V / 1000) % 10, kPre = (V / 100) % 10;
+  // S = 6 contraction adjoint as two sub-jet passes (needed when 6-component jets overflow the
+  // 255-register budget, i.e. in float64)
+  static constexpr int kPasses = (V / 10) % 10;     // 0: one pass, 1: (t,x | y), 2: (t | x | y)
+  static constexpr bool kTwoPass = kPasses != 0;
+  // keep the loop over the A-half feature index rolled (9x less code, runtime-selected factors:
+  // wins in float32 where the unrolled body thrashed the instruction cache; loses in float64)
+  static constexpr bool kRollA = (V % 10) != 0;
+};
+template <typename T, int S>
+struct Tune : TuneValues<1111100> {};
+template <>
+struct Tune<double, 6> : TuneValues<QCP_TUNE_F64_6> {};
+template <>
+struct Tune<float, 6> : TuneValues<QCP_TUNE_F32_6> {};
+template <>
+struct Tune<double, 1> : TuneValues<QCP_TUNE_F64_1> {};
+template <>
+struct Tune<float, 1> : TuneValues<QCP_TUNE_F32_1> {};
+
+// ------------------------------------------------------------------------------------------
+// feature-matrix image in shared memory
+//   angle:     Ct[(a*NQ + i)*FBP + b] = C[i, a*FB + b]  (rows over b padded to a multiple of 4, so
+//              one (a, i) row is a couple of LDS.128 broadcasts)
+//   amplitude: C4[s][4]               = C[i, s]         (i padded to 4)
+// ------------------------------------------------------------------------------------------
+template <int NQ>
+struct AngleShape {
+  static constexpr int NA = (NQ + 1) / 2;
+  static constexpr int NB = NQ - NA;
+  static constexpr int FA = ipow3(NA);
+  static constexpr int FB = ipow3(NB);
+  static constexpr int FBP = (FB + 3) & ~3;
+};
+
+__host__ __device__ constexpr int c_elems(int n, int enc) {
+  return enc == QCP_ENC_AMPLITUDE
+             ? 4 * (n * (n + 1) / 2)
+             : ipow3((n + 1) / 2) * n * ((ipow3(n - (n + 1) / 2) + 3) & ~3);
+}
+
+// accumulator segment sizes (also the staging / reduce order, see reduce_solver_kernel)
+__host__ __device__ constexpr int nacc_post(int n, int H) { return 1 + H * (n + 2); }
+__host__ __device__ constexpr int nacc_contract(int n, int enc) { return num_features(n, enc) * n; }
+__host__ __device__ constexpr int nacc_pre(int n, int H) { return n + H * (4 + n); }
+
+template <typename T, int NQ, int ENC>
+__device__ __forceinline__ void load_C(T* sC, const T* Cg) {
+  if constexpr (ENC == QCP_ENC_ANGLE) {
+    using A = AngleShape<NQ>;
+    for (int e = threadIdx.x; e < A::FA * NQ * A::FBP; e += blockDim.x) {
+      const int b = e % A::FBP, i = (e / A::FBP) % NQ, a = e / (A::FBP * NQ);
+      sC[e] = b < A::FB ? Cg[(a * A::FB + b) * kCStride + i] : T(0);
+    }
+  } else {
+    for (int e = threadIdx.x; e < c_elems(NQ, ENC); e += blockDim.x) sC[e] = Cg[e];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// shared-memory image of the MLP weights
 // ------------------------------------------------------------------------------------------
 template <typename T>
 struct SmemWeights {
@@ -35,30 +124,30 @@ struct SmemWeights {
   T* b3w4;        // [H][2] (b3[k], w4[k])
   T* b2;          // [4]
   T* b4;          // [4]  (only [0] used)
-  Vec4<T>* C;     // [F]  C[i,s], i < n (zero padded)
+  T* C;           // feature matrix image (layout above)
 };
 
 template <typename T>
-__host__ __device__ inline size_t smem_weights_bytes(int H, int F) {
-  return sizeof(T) * (size_t)(4 * H * 3 + 2 * H + 4 + 4 + 4 * F);
+__host__ __device__ inline size_t smem_weights_bytes(int H, int celems) {
+  return sizeof(T) * (size_t)(4 * H * 3 + 2 * H + 4 + 4 + celems);
 }
 
 template <typename T>
-__device__ __forceinline__ SmemWeights<T> carve_weights(unsigned char* base, int H, int F) {
+__device__ __forceinline__ SmemWeights<T> carve_weights(unsigned char* base, int H, int celems) {
   SmemWeights<T> s;
   T* p = reinterpret_cast<T*>(base);
   s.w1b = reinterpret_cast<Vec4<T>*>(p); p += 4 * H;
   s.w2t = reinterpret_cast<Vec4<T>*>(p); p += 4 * H;
   s.w3 = reinterpret_cast<Vec4<T>*>(p);  p += 4 * H;
-  s.C = reinterpret_cast<Vec4<T>*>(p);   p += 4 * F;
+  s.C = p;    p += celems;
   s.b3w4 = p; p += 2 * H;
   s.b2 = p;   p += 4;
   s.b4 = p;   p += 4;
   return s;
 }
 
-template <typename T, int NQ>
-__device__ __forceinline__ void load_weights(const SmemWeights<T>& s, const SolverArgs& a, int F) {
+template <typename T, int NQ, int ENC>
+__device__ __forceinline__ void load_weights(const SmemWeights<T>& s, const SolverArgs& a) {
   const int H = a.H;
   const T* w1 = static_cast<const T*>(a.w1);
   const T* b1 = static_cast<const T*>(a.b1);
@@ -68,7 +157,6 @@ __device__ __forceinline__ void load_weights(const SmemWeights<T>& s, const Solv
   const T* b3 = static_cast<const T*>(a.b3);
   const T* w4 = static_cast<const T*>(a.w4);
   const T* b4 = static_cast<const T*>(a.b4);
-  const T* C = static_cast<const T*>(a.C);
   for (int k = threadIdx.x; k < H; k += blockDim.x) {
     Vec4<T> v;
     v.v[0] = w1[k * 3 + 0]; v.v[1] = w1[k * 3 + 1]; v.v[2] = w1[k * 3 + 2]; v.v[3] = b1[k];
@@ -84,8 +172,7 @@ __device__ __forceinline__ void load_weights(const SmemWeights<T>& s, const Solv
     s.b3w4[2 * k] = b3[k];
     s.b3w4[2 * k + 1] = w4[k];
   }
-  T* Cs = reinterpret_cast<T*>(s.C);
-  for (int i = threadIdx.x; i < 4 * F; i += blockDim.x) Cs[i] = C[i];
+  load_C<T, NQ, ENC>(s.C, static_cast<const T*>(a.C));
   if (threadIdx.x < 4) {
     s.b2[threadIdx.x] = threadIdx.x < NQ ? b2[threadIdx.x] : T(0);
     s.b4[threadIdx.x] = b4[0];
@@ -93,8 +180,18 @@ __device__ __forceinline__ void load_weights(const SmemWeights<T>& s, const Solv
 }
 
 // ------------------------------------------------------------------------------------------
-// pre MLP:  z_j = b2_j + sum_k w2[j,k] tanh(b1_k + w1[k,:] . X)
+// pre MLP:  z_j = b2_j + sum_k w2[j,k] tanh(b1_k + w1[k,:] . X)       (S = 1 or 6)
 // ------------------------------------------------------------------------------------------
+template <typename T, int S>
+__device__ __forceinline__ Jet<T, S> pre_activation(const Vec4<T>& w, const T (&X)[3]) {
+  Jet<T, S> a;
+  a.c[0] = fma(w.v[0], X[0], fma(w.v[1], X[1], fma(w.v[2], X[2], w.v[3])));
+  if constexpr (S == 6) {
+    a.c[1] = w.v[0]; a.c[2] = w.v[1]; a.c[3] = w.v[2]; a.c[4] = T(0); a.c[5] = T(0);
+  }
+  return a;
+}
+
 template <typename T, int NQ, int S>
 __device__ __forceinline__ void pre_forward(const SmemWeights<T>& s, int H, const T (&X)[3],
                                             Jet<T, S> (&z)[NQ]) {
@@ -107,11 +204,7 @@ __device__ __forceinline__ void pre_forward(const SmemWeights<T>& s, int H, cons
   for (int k = 0; k < H; ++k) {
     const Vec4<T> w = s.w1b[k];
     const Vec4<T> w2 = s.w2t[k];
-    Jet<T, S> a;
-    a.c[0] = fma(w.v[0], X[0], fma(w.v[1], X[1], fma(w.v[2], X[2], w.v[3])));
-    if constexpr (S == 6) {
-      a.c[1] = w.v[0]; a.c[2] = w.v[1]; a.c[3] = w.v[2]; a.c[4] = T(0); a.c[5] = T(0);
-    }
+    const Jet<T, S> a = pre_activation<T, S>(w, X);
     const T h0 = Math<T>::tanh_(a.c[0]);
     const T f1 = fma(-h0, h0, T(1));
     const T f2 = T(-2) * h0 * f1;
@@ -147,21 +240,19 @@ __device__ __forceinline__ void post_forward(const SmemWeights<T>& s, int H,
 }
 
 // ------------------------------------------------------------------------------------------
-// angle-encoding features: per-qubit Bloch jets and their tensor products
+// angle-encoding features.  Qubits [0, NA) form the "A" half (index a), qubits [NA, NQ) the "B"
+// half (index b); trit 0 = I (factor 1), 1 = Y (y_j), 2 = Z (w_j); a = 3*s_0 + s_1 etc.
+// The B-half products Q[b] are kept; A-half products P_a are formed on the fly.
 // ------------------------------------------------------------------------------------------
 template <typename T, int NQ, int S>
 struct AngleFeat {
-  static constexpr int NA = (NQ + 1) / 2;
-  static constexpr int NB = NQ - NA;
-  static constexpr int FA = ipow3(NA);
-  static constexpr int FB = ipow3(NB);
+  using A = AngleShape<NQ>;
   T sn[NQ], cs[NQ];
   Jet<T, S> y[NQ], w[NQ];   // y = -sin z (Pauli-Y Bloch component), w = cos z (Pauli-Z)
-  Jet<T, S> P[FA];          // products over qubits [0, NA); P[0] unused (== 1)
-  Jet<T, S> Q[FB];          // products over qubits [NA, NQ); Q[0] unused (== 1)
+  Jet<T, S> Q[A::FB];       // Q[0] unused (== 1)
 };
 
-// e[3*s0 + s1] over two qubits (or e[s0] over one); trit 0 = I, 1 = Y, 2 = Z
+// e[3*s0 + s1] over two qubits (or e[s0] over one)
 template <typename T, int S, int K>
 __device__ __forceinline__ void prod_build(Jet<T, S>* e, const Jet<T, S>* y, const Jet<T, S>* w) {
   if constexpr (K == 1) {
@@ -187,50 +278,130 @@ __device__ __forceinline__ void prod_pull(const Jet<T, S>* eb, const Jet<T, S>* 
   }
 }
 
+// runtime-selected Bloch factor of one qubit: trit 0 -> 1, 1 -> y, 2 -> w.  `s` is warp-uniform
+// (it comes from the rolled loop over the A-half feature index), so these selects never diverge.
+template <typename T, int S>
+__device__ __forceinline__ Jet<T, S> bloch_select(int s, const Jet<T, S>& y, const Jet<T, S>& w) {
+  Jet<T, S> r;
+#pragma unroll
+  for (int c = 0; c < S; ++c) r.c[c] = s == 1 ? y.c[c] : (s == 2 ? w.c[c] : (c == 0 ? T(1) : T(0)));
+  return r;
+}
+
+// A-half product P_a, formed on the fly inside the ROLLED loop over a (keeping that loop rolled
+// cuts the kernel's code size ~9x: the unrolled version thrashed the instruction cache)
 template <typename T, int NQ, int S>
-__device__ __forceinline__ void angle_forward(const Jet<T, S> (&z)[NQ], AngleFeat<T, NQ, S>& f) {
-  using F = AngleFeat<T, NQ, S>;
+struct PA {
+  using A = AngleShape<NQ>;
+  Jet<T, S> f0, f1, p;
+  int s0, s1;
+  __device__ __forceinline__ void set(const AngleFeat<T, NQ, S>& f, int a) {
+    if constexpr (A::NA == 1) {
+      s0 = a; s1 = 0;
+      p = bloch_select<T, S>(s0, f.y[0], f.w[0]);
+    } else {
+      s0 = a / 3; s1 = a - 3 * s0;
+      f0 = bloch_select<T, S>(s0, f.y[0], f.w[0]);
+      f1 = bloch_select<T, S>(s1, f.y[1], f.w[1]);
+      p = jmul(f0, f1);
+    }
+  }
+  // pull the cotangent of P_a into the A-half Bloch cotangents
+  __device__ __forceinline__ void pull(const Jet<T, S>& pb, Jet<T, S>* yb, Jet<T, S>* wb) const {
+    if constexpr (A::NA == 1) {
+      if (s0 == 1) jadd(yb[0], pb);
+      else if (s0 == 2) jadd(wb[0], pb);
+    } else {
+      Jet<T, S> b0, b1;
+      jzero(b0); jzero(b1);
+      jmul_pull_acc(b0, pb, f1);
+      jmul_pull_acc(b1, pb, f0);
+      if (s0 == 1) jadd(yb[0], b0);
+      else if (s0 == 2) jadd(wb[0], b0);
+      if (s1 == 1) jadd(yb[1], b1);
+      else if (s1 == 2) jadd(wb[1], b1);
+    }
+  }
+};
+
+template <typename T, int NQ>
+__device__ __forceinline__ void angle_sincos(const T (&z0)[NQ], T (&sn)[NQ], T (&cs)[NQ]) {
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) Math<T>::sincos_(z0[j], &sn[j], &cs[j]);
+}
+
+// Bloch jets and B-half products from z jets and precomputed sin / cos of their values
+template <typename T, int NQ, int S>
+__device__ __forceinline__ void angle_features(const Jet<T, S> (&z)[NQ], const T (&sn)[NQ],
+                                               const T (&cs)[NQ], AngleFeat<T, NQ, S>& f) {
+  using A = AngleShape<NQ>;
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {
-    Math<T>::sincos_(z[j].c[0], &f.sn[j], &f.cs[j]);
-    f.y[j] = jfunc(z[j], -f.sn[j], -f.cs[j], f.sn[j]);
-    f.w[j] = jfunc(z[j], f.cs[j], -f.sn[j], -f.cs[j]);
+    f.sn[j] = sn[j];
+    f.cs[j] = cs[j];
+    f.y[j] = jfunc(z[j], -sn[j], -cs[j], sn[j]);
+    f.w[j] = jfunc(z[j], cs[j], -sn[j], -cs[j]);
   }
-  prod_build<T, S, F::NA>(f.P, f.y, f.w);
-  prod_build<T, S, F::NB>(f.Q, f.y + F::NA, f.w + F::NA);
-}
-
-// t[i] = sum_b C[i, a*FB + b] Q[b]   (Q[0] == 1)
-template <typename T, int NQ, int S, int FB>
-__device__ __forceinline__ void contract_row(const Vec4<T>* sC, int a, const Jet<T, S>* Q,
-                                             Jet<T, S> (&t)[NQ]) {
-  const Vec4<T> c0 = sC[a * FB];
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) {
-    jzero(t[i]);
-    t[i].c[0] = c0.v[i];
-  }
-#pragma unroll
-  for (int b = 1; b < FB; ++b) {
-    const Vec4<T> c = sC[a * FB + b];
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) jaxpy(t[i], c.v[i], Q[b]);
-  }
+  prod_build<T, S, A::NB>(f.Q, f.y + A::NA, f.w + A::NA);
 }
 
 template <typename T, int NQ, int S>
-__device__ __forceinline__ void angle_contract(const Vec4<T>* sC, const AngleFeat<T, NQ, S>& f,
-                                               Jet<T, S> (&q)[NQ]) {
-  using F = AngleFeat<T, NQ, S>;
+__device__ __forceinline__ void angle_forward(const Jet<T, S> (&z)[NQ], AngleFeat<T, NQ, S>& f) {
+  T z0[NQ], sn[NQ], cs[NQ];
 #pragma unroll
-  for (int a = 0; a < F::FA; ++a) {
-    Jet<T, S> t[NQ];
-    contract_row<T, NQ, S, F::FB>(sC, a, f.Q, t);
+  for (int j = 0; j < NQ; ++j) z0[j] = z[j].c[0];
+  angle_sincos<T, NQ>(z0, sn, cs);
+  angle_features<T, NQ, S>(z, sn, cs, f);
+}
+
+// coefficients C[i, a, 0..FB) of one (a, i) row
+template <typename T, int NQ>
+struct CRow {
+  using A = AngleShape<NQ>;
+  Vec4<T> v[A::FBP / 4];
+  __device__ __forceinline__ void load(const T* sC, int a, int i) {
+    const Vec4<T>* p = reinterpret_cast<const Vec4<T>*>(sC + (a * NQ + i) * A::FBP);
+#pragma unroll
+    for (int k = 0; k < A::FBP / 4; ++k) v[k] = p[k];
+  }
+  __device__ __forceinline__ T at(int b) const { return v[b >> 2].v[b & 3]; }
+};
+
+// t = sum_b C[i, a, b] Q[b]   (Q[0] == 1)
+template <typename T, int NQ, int S>
+__device__ __forceinline__ Jet<T, S> contract_row(const CRow<T, NQ>& c, const Jet<T, S>* Q) {
+  using A = AngleShape<NQ>;
+  Jet<T, S> t;
+  jzero(t);
+  t.c[0] = c.at(0);
+#pragma unroll
+  for (int b = 1; b < A::FB; ++b) jaxpy(t, c.at(b), Q[b]);
+  return t;
+}
+
+template <typename T, int NQ, int S>
+__device__ __forceinline__ void angle_contract(const T* sC, const AngleFeat<T, NQ, S>& f,
+                                               Jet<T, S> (&q)[NQ]) {
+  using A = AngleShape<NQ>;
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) jzero(q[i]);
+  auto body = [&](int a) {
+    PA<T, NQ, S> pa;
+    pa.set(f, a);
 #pragma unroll
     for (int i = 0; i < NQ; ++i) {
-      if (a == 0) q[i] = t[i];
-      else jmul_acc(q[i], f.P[a], t[i]);
+      CRow<T, NQ> c;
+      c.load(sC, a, i);
+      const Jet<T, S> t = contract_row<T, NQ, S>(c, f.Q);
+      jmul_acc(q[i], pa.p, t);
     }
+  };
+  if constexpr (Tune<T, (S == 1 ? 1 : 6)>::kRollA) {
+#pragma unroll 1
+    for (int a = 0; a < A::FA; ++a) body(a);
+  } else {
+#pragma unroll
+    for (int a = 0; a < A::FA; ++a) body(a);
   }
 }
 
@@ -246,6 +417,10 @@ struct AmpFeat {
   Jet<T, S> phi[F];
 };
 
+__host__ __device__ constexpr int pair_index(int a, int b, int n) {
+  return a * n - a * (a - 1) / 2 + (b - a);
+}
+
 template <typename T, int NQ, int S>
 __device__ __forceinline__ void amp_forward(const Jet<T, S> (&z)[NQ], AmpFeat<T, NQ, S>& f) {
   jzero(f.nrm);
@@ -259,18 +434,18 @@ __device__ __forceinline__ void amp_forward(const Jet<T, S> (&z)[NQ], AmpFeat<T,
 #pragma unroll
   for (int a = 0; a < NQ; ++a)
 #pragma unroll
-    for (int b = a; b < NQ; ++b)
-      f.phi[a * NQ - a * (a - 1) / 2 + (b - a)] = jmul(jmul(z[a], z[b]), f.inv);
+    for (int b = a; b < NQ; ++b) f.phi[pair_index(a, b, NQ)] = jmul(jmul(z[a], z[b]), f.inv);
 }
 
 template <typename T, int NQ, int S>
-__device__ __forceinline__ void amp_contract(const Vec4<T>* sC, const AmpFeat<T, NQ, S>& f,
+__device__ __forceinline__ void amp_contract(const T* sC, const AmpFeat<T, NQ, S>& f,
                                              Jet<T, S> (&q)[NQ]) {
+  const Vec4<T>* C4 = reinterpret_cast<const Vec4<T>*>(sC);
 #pragma unroll
   for (int i = 0; i < NQ; ++i) jzero(q[i]);
 #pragma unroll
   for (int s = 0; s < AmpFeat<T, NQ, S>::F; ++s) {
-    const Vec4<T> c = sC[s];
+    const Vec4<T> c = C4[s];
 #pragma unroll
     for (int i = 0; i < NQ; ++i) jaxpy(q[i], c.v[i], f.phi[s]);
   }
@@ -296,14 +471,14 @@ struct Stager {
   }
   __device__ __forceinline__ void flush() {
     __syncwarp();
-    for (int r = lane; r < cnt; r += 32) {
-      const T* p = tile + r * kStagePitch;
+    if (lane < cnt) {
+      const T* p = tile + lane * kStagePitch;
       T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         s0 += p[j]; s1 += p[j + 1]; s2 += p[j + 2]; s3 += p[j + 3];
       }
-      acc[base + r] += (s0 + s1) + (s2 + s3);
+      acc[base + lane] += (s0 + s1) + (s2 + s3);
     }
     __syncwarp();
     base += cnt;
@@ -351,62 +526,58 @@ __device__ __forceinline__ void post_backward(const SmemWeights<T>& s, int H,
   }
 }
 
+// Adjoint of features + contraction for one jet layout.  Pushes d C in (a, i, b) order and ADDS
+// the pulled-back cotangent into zb (so sub-jet passes can accumulate).
 template <typename T, int NQ, int S>
-__device__ __forceinline__ void angle_backward(const Vec4<T>* sC, const Jet<T, S> (&z)[NQ],
+__device__ __forceinline__ void angle_backward(const T* sC, const Jet<T, S> (&z)[NQ],
                                                const AngleFeat<T, NQ, S>& f,
                                                const Jet<T, S> (&qb)[NQ], Jet<T, S> (&zb)[NQ],
                                                Stager<T>& st) {
-  using F = AngleFeat<T, NQ, S>;
-  Jet<T, S> Pb[F::FA], Qb[F::FB];
-#pragma unroll
-  for (int a = 0; a < F::FA; ++a) jzero(Pb[a]);
-#pragma unroll
-  for (int b = 0; b < F::FB; ++b) jzero(Qb[b]);
-
-#pragma unroll
-  for (int a = 0; a < F::FA; ++a) {
-    // D_i = pullback of qb_i through multiplication by P[a]; also P[a]'s own cotangent
-    Jet<T, S> D[NQ];
-    if (a == 0) {
-#pragma unroll
-      for (int i = 0; i < NQ; ++i) D[i] = qb[i];
-    } else {
-      Jet<T, S> t[NQ];
-      contract_row<T, NQ, S, F::FB>(sC, a, f.Q, t);
-#pragma unroll
-      for (int i = 0; i < NQ; ++i) {
-        jzero(D[i]);
-        jmul_pull_acc(D[i], qb[i], f.P[a]);
-        jmul_pull_acc(Pb[a], qb[i], t[i]);
-      }
-    }
-    st.reserve(F::FB * NQ);
-    {
-#pragma unroll
-      for (int i = 0; i < NQ; ++i) st.put(D[i].c[0]);      // d C[i, a, 0]  (Q[0] == 1)
-    }
-#pragma unroll
-    for (int b = 1; b < F::FB; ++b) {
-      const Vec4<T> c = sC[a * F::FB + b];
-#pragma unroll
-      for (int i = 0; i < NQ; ++i) {
-        st.put(jdot(D[i], f.Q[b]));                        // d C[i, a, b]
-        jaxpy(Qb[b], c.v[i], D[i]);
-      }
-    }
-  }
-
-  Jet<T, S> yb[NQ], wb[NQ];
+  using A = AngleShape<NQ>;
+  Jet<T, S> yb[NQ], wb[NQ], Qb[A::FB];
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {
     jzero(yb[j]);
     jzero(wb[j]);
   }
-  prod_pull<T, S, F::NA>(Pb, f.y, f.w, yb, wb);
-  prod_pull<T, S, F::NB>(Qb, f.y + F::NA, f.w + F::NA, yb + F::NA, wb + F::NA);
+#pragma unroll
+  for (int b = 0; b < A::FB; ++b) jzero(Qb[b]);
+
+  auto body = [&](int a) {
+    PA<T, NQ, S> pa;
+    pa.set(f, a);
+    Jet<T, S> pab;
+    jzero(pab);
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      CRow<T, NQ> c;
+      c.load(sC, a, i);
+      // D = pullback of qb_i through the multiplication by P_a
+      Jet<T, S> D;
+      jzero(D);
+      jmul_pull_acc(D, qb[i], pa.p);
+      const Jet<T, S> t = contract_row<T, NQ, S>(c, f.Q);
+      jmul_pull_acc(pab, qb[i], t);
+      st.reserve(A::FB);
+      st.put(D.c[0]);                                      // d C[i, a, 0]  (Q[0] == 1)
+#pragma unroll
+      for (int b = 1; b < A::FB; ++b) {
+        st.put(jdot(D, f.Q[b]));                           // d C[i, a, b]
+        jaxpy(Qb[b], c.at(b), D);
+      }
+    }
+    pa.pull(pab, yb, wb);
+  };
+  if constexpr (Tune<T, (S == 1 ? 1 : 6)>::kRollA) {
+#pragma unroll 1
+    for (int a = 0; a < A::FA; ++a) body(a);
+  } else {
+#pragma unroll
+    for (int a = 0; a < A::FA; ++a) body(a);
+  }
+  prod_pull<T, S, A::NB>(Qb, f.y + A::NA, f.w + A::NA, yb + A::NA, wb + A::NA);
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {
-    jzero(zb[j]);
     // y = -sin z : f' = -cos, f'' = sin, f''' = cos ;  w = cos z : f' = -sin, f'' = -cos, f''' = sin
     jfunc_pull_acc(zb[j], yb[j], z[j], -f.cs[j], f.sn[j], f.cs[j]);
     jfunc_pull_acc(zb[j], wb[j], z[j], -f.sn[j], -f.cs[j], f.sn[j]);
@@ -414,20 +585,19 @@ __device__ __forceinline__ void angle_backward(const Vec4<T>* sC, const Jet<T, S
 }
 
 template <typename T, int NQ, int S>
-__device__ __forceinline__ void amp_backward(const Vec4<T>* sC, const Jet<T, S> (&z)[NQ],
+__device__ __forceinline__ void amp_backward(const T* sC, const Jet<T, S> (&z)[NQ],
                                              const AmpFeat<T, NQ, S>& f,
                                              const Jet<T, S> (&qb)[NQ], Jet<T, S> (&zb)[NQ],
                                              Stager<T>& st) {
+  const Vec4<T>* C4 = reinterpret_cast<const Vec4<T>*>(sC);
   Jet<T, S> invb;
   jzero(invb);
-#pragma unroll
-  for (int j = 0; j < NQ; ++j) jzero(zb[j]);
 #pragma unroll
   for (int a = 0; a < NQ; ++a) {
 #pragma unroll
     for (int b = a; b < NQ; ++b) {
-      const int s = a * NQ - a * (a - 1) / 2 + (b - a);
-      const Vec4<T> c = sC[s];
+      const int s = pair_index(a, b, NQ);
+      const Vec4<T> c = C4[s];
       Jet<T, S> phib;
       jzero(phib);
       st.reserve(NQ);
@@ -455,6 +625,85 @@ __device__ __forceinline__ void amp_backward(const Vec4<T>* sC, const Jet<T, S> 
   }
 }
 
+// features + contraction adjoint of one point; zb is overwritten
+template <typename T, int NQ, int ENC, int S>
+__device__ __forceinline__ void feature_backward(const T* sC, const Jet<T, S> (&z)[NQ],
+                                                 const Jet<T, S> (&qb)[NQ], Jet<T, S> (&zb)[NQ],
+                                                 Stager<T>& st) {
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) jzero(zb[j]);
+  if constexpr (ENC == QCP_ENC_AMPLITUDE) {
+    AmpFeat<T, NQ, S> f;
+    amp_forward<T, NQ, S>(z, f);
+    amp_backward<T, NQ, S>(sC, z, f, qb, zb, st);
+  } else if constexpr (S == 6 && Tune<T, S>::kTwoPass) {
+    // register-light passes over sub-jets, e.g. X = (u, u_t | u_x | u_xx), Y = (u | u_y | u_yy).
+    // Every pullback is linear in the cotangent, so the value-component cotangent may be carried
+    // by the first pass alone; the partial parameter-gradient pushes of all passes add up in acc.
+    T z0[NQ], sn[NQ], cs[NQ];
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) z0[j] = z[j].c[0];
+    angle_sincos<T, NQ>(z0, sn, cs);
+    st.flush();                  // all passes must start at the same accumulator index
+    const int base0 = st.base;
+    // one pass over the full-jet components idx[0..SS) (idx[0] == 0 is the value)
+    auto pass = [&](auto tag, const int (&idx)[decltype(tag)::value], bool carry_value) {
+      constexpr int SS = decltype(tag)::value;
+      Jet<T, SS> zs[NQ], qs[NQ], zbs[NQ];
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) {
+#pragma unroll
+        for (int c = 0; c < SS; ++c) {
+          zs[j].c[c] = z[j].c[idx[c]];
+          qs[j].c[c] = qb[j].c[idx[c]];
+        }
+        if (!carry_value) qs[j].c[0] = T(0);
+        jzero(zbs[j]);
+      }
+      AngleFeat<T, NQ, SS> f;
+      angle_features<T, NQ, SS>(zs, sn, cs, f);
+      angle_backward<T, NQ, SS>(sC, zs, f, qs, zbs, st);
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) {
+        zb[j].c[0] += zbs[j].c[0];
+#pragma unroll
+        for (int c = 1; c < SS; ++c) zb[j].c[idx[c]] = zbs[j].c[c];
+      }
+      st.flush();
+      st.base = base0;           // the next pass adds onto the same accumulator segment
+    };
+    if constexpr (Tune<T, S>::kPasses == 1) {
+      const int ix[4] = {0, 1, 2, 4}, iy[3] = {0, 3, 5};
+      pass(std::integral_constant<int, 4>{}, ix, true);
+      pass(std::integral_constant<int, 3>{}, iy, false);
+    } else {
+      const int it[2] = {0, 1}, ix[3] = {0, 2, 4}, iy[3] = {0, 3, 5};
+      pass(std::integral_constant<int, 3>{}, ix, true);
+      pass(std::integral_constant<int, 3>{}, iy, false);
+      pass(std::integral_constant<int, 2>{}, it, false);
+    }
+    st.base = base0 + nacc_contract(NQ, ENC);
+  } else {
+    AngleFeat<T, NQ, S> f;
+    angle_forward<T, NQ, S>(z, f);
+    angle_backward<T, NQ, S>(sC, z, f, qb, zb, st);
+  }
+}
+
+template <typename T, int NQ, int ENC, int S>
+__device__ __forceinline__ void feature_forward(const T* sC, const Jet<T, S> (&z)[NQ],
+                                                Jet<T, S> (&q)[NQ]) {
+  if constexpr (ENC == QCP_ENC_ANGLE) {
+    AngleFeat<T, NQ, S> f;
+    angle_forward<T, NQ, S>(z, f);
+    angle_contract<T, NQ, S>(sC, f, q);
+  } else {
+    AmpFeat<T, NQ, S> f;
+    amp_forward<T, NQ, S>(z, f);
+    amp_contract<T, NQ, S>(sC, f, q);
+  }
+}
+
 template <typename T, int NQ, int S>
 __device__ __forceinline__ void pre_backward(const SmemWeights<T>& s, int H, const T (&X)[3],
                                              const Jet<T, S> (&zb)[NQ], T (&Xb)[3],
@@ -466,11 +715,7 @@ __device__ __forceinline__ void pre_backward(const SmemWeights<T>& s, int H, con
   for (int k = 0; k < H; ++k) {
     const Vec4<T> w = s.w1b[k];
     const Vec4<T> w2 = s.w2t[k];
-    Jet<T, S> a;
-    a.c[0] = fma(w.v[0], X[0], fma(w.v[1], X[1], fma(w.v[2], X[2], w.v[3])));
-    if constexpr (S == 6) {
-      a.c[1] = w.v[0]; a.c[2] = w.v[1]; a.c[3] = w.v[2]; a.c[4] = T(0); a.c[5] = T(0);
-    }
+    const Jet<T, S> a = pre_activation<T, S>(w, X);
     T h0, f1, f2, f3;
     tanh_derivs(a.c[0], h0, f1, f2, f3);
     const Jet<T, S> h = jfunc(a, h0, f1, f2);
@@ -496,36 +741,97 @@ __device__ __forceinline__ void pre_backward(const SmemWeights<T>& s, int H, con
 }
 
 // ------------------------------------------------------------------------------------------
+// saved-jet workspace: ws[slot][j*S + c][B] (component-major => coalesced across the warp).
+// slot 0: z jets (pre-MLP output), overwritten by their cotangents zb;
+// slot 1: q jets (<Z_i> streams),  overwritten by their cotangents qb.
+// ------------------------------------------------------------------------------------------
+template <typename T, int NQ, int S>
+__device__ __forceinline__ void ws_store(T* ws, long long B, int slot, long long p,
+                                         const Jet<T, S> (&v)[NQ]) {
+  T* base = ws + (size_t)slot * NQ * S * B + p;
+#pragma unroll
+  for (int j = 0; j < NQ; ++j)
+#pragma unroll
+    for (int c = 0; c < S; ++c) base[(size_t)(j * S + c) * B] = v[j].c[c];
+}
+
+template <typename T, int NQ, int S>
+__device__ __forceinline__ void ws_load(const T* ws, long long B, int slot, long long p,
+                                        Jet<T, S> (&v)[NQ]) {
+  const T* base = ws + (size_t)slot * NQ * S * B + p;
+#pragma unroll
+  for (int j = 0; j < NQ; ++j)
+#pragma unroll
+    for (int c = 0; c < S; ++c) v[j].c[c] = base[(size_t)(j * S + c) * B];
+}
+
+// cotangent seed of the outputs: (grad_u, grad_r) -> jet cotangent of u
+template <typename T, int S>
+__device__ __forceinline__ Jet<T, S> seed_cotangent(const SolverArgs& a, long long p, bool valid) {
+  Jet<T, S> ub;
+  jzero(ub);
+  if (valid) {
+    const T* gug = static_cast<const T*>(a.gu);
+    const T* grg = static_cast<const T*>(a.gr);
+    if (gug) ub.c[0] = gug[p];
+    if constexpr (S == 6) {
+      if (grg) {
+        const T g = grg[p];
+        ub.c[1] = T(a.pde.ct) * g; ub.c[2] = T(a.pde.cx) * g; ub.c[3] = T(a.pde.cy) * g;
+        ub.c[4] = T(a.pde.cxx) * g; ub.c[5] = T(a.pde.cyy) * g;
+      }
+    }
+  }
+  return ub;
+}
+
+template <typename T>
+__device__ __forceinline__ Stager<T> make_stager(T* acc_all, T* tile_all, int nacc) {
+  Stager<T> st;
+  const int warp = threadIdx.x >> 5;
+  st.lane = threadIdx.x & 31;
+  st.acc = acc_all + (size_t)warp * nacc;
+  st.tile = tile_all + (size_t)warp * kStageRows * kStagePitch;
+  return st;
+}
+
+template <typename T>
+__device__ __forceinline__ void write_partials(const T* acc_all, int nacc, T* partials) {
+  __syncthreads();
+  T* out = partials + (size_t)blockIdx.x * nacc;
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
+    T s = T(0);
+#pragma unroll
+    for (int w = 0; w < kWarpsPerBlock; ++w) s += acc_all[(size_t)w * nacc + i];
+    out[i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
 template <typename T, int NQ, int ENC, int S>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, Tune<T, S>::kFwd)
 solver_forward_kernel(const SolverArgs a) {
   extern __shared__ __align__(32) unsigned char smem_raw[];
-  constexpr int F = num_features(NQ, ENC);
   const int H = a.H;
-  const SmemWeights<T> sw = carve_weights<T>(smem_raw, H, F);
-  load_weights<T, NQ>(sw, a, F);
+  const SmemWeights<T> sw = carve_weights<T>(smem_raw, H, c_elems(NQ, ENC));
+  load_weights<T, NQ, ENC>(sw, a);
   __syncthreads();
 
   const T* Xg = static_cast<const T*>(a.X);
   T* ug = static_cast<T*>(a.u);
   T* rg = static_cast<T*>(a.r);
   T* sg = static_cast<T*>(a.streams);
+  T* wsg = static_cast<T*>(a.ws);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < a.B; p += stride) {
     T X[3] = {Xg[3 * p], Xg[3 * p + 1], Xg[3 * p + 2]};
     Jet<T, S> z[NQ], q[NQ], u;
     pre_forward<T, NQ, S>(sw, H, X, z);
-    if constexpr (ENC == QCP_ENC_ANGLE) {
-      AngleFeat<T, NQ, S> f;
-      angle_forward<T, NQ, S>(z, f);
-      angle_contract<T, NQ, S>(sw.C, f, q);
-    } else {
-      AmpFeat<T, NQ, S> f;
-      amp_forward<T, NQ, S>(z, f);
-      amp_contract<T, NQ, S>(sw.C, f, q);
-    }
+    if (wsg) ws_store<T, NQ, S>(wsg, a.B, 0, p, z);
+    feature_forward<T, NQ, ENC, S>(sw.C, z, q);
+    if (wsg) ws_store<T, NQ, S>(wsg, a.B, 1, p, q);
     post_forward<T, NQ, S>(sw, H, q, u);
     ug[p] = u.c[0];
     if constexpr (S == 6) {
@@ -541,29 +847,23 @@ solver_forward_kernel(const SolverArgs a) {
   }
 }
 
+// fused backward: recompute the forward from X, then the whole reverse sweep
 template <typename T, int NQ, int ENC, int S>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, Tune<T, S>::kFused)
 solver_backward_kernel(const SolverArgs a) {
   extern __shared__ __align__(32) unsigned char smem_raw[];
-  constexpr int F = num_features(NQ, ENC);
+  constexpr int CE = c_elems(NQ, ENC);
   const int H = a.H;
   const int nacc = nacc_solver(NQ, ENC, H);
-  const SmemWeights<T> sw = carve_weights<T>(smem_raw, H, F);
-  T* acc_all = reinterpret_cast<T*>(smem_raw + ((smem_weights_bytes<T>(H, F) + 31) & ~size_t(31)));
+  const SmemWeights<T> sw = carve_weights<T>(smem_raw, H, CE);
+  T* acc_all = reinterpret_cast<T*>(smem_raw + ((smem_weights_bytes<T>(H, CE) + 31) & ~size_t(31)));
   T* tile_all = acc_all + (size_t)kWarpsPerBlock * nacc;
-  load_weights<T, NQ>(sw, a, F);
+  load_weights<T, NQ, ENC>(sw, a);
   for (int i = threadIdx.x; i < kWarpsPerBlock * nacc; i += blockDim.x) acc_all[i] = T(0);
   __syncthreads();
-
-  const int warp = threadIdx.x >> 5;
-  Stager<T> st;
-  st.lane = threadIdx.x & 31;
-  st.acc = acc_all + (size_t)warp * nacc;
-  st.tile = tile_all + (size_t)warp * kStageRows * kStagePitch;
+  Stager<T> st = make_stager<T>(acc_all, tile_all, nacc);
 
   const T* Xg = static_cast<const T*>(a.X);
-  const T* gug = static_cast<const T*>(a.gu);
-  const T* grg = static_cast<const T*>(a.gr);
   T* gXg = static_cast<T*>(a.gX);
   const long long stride = (long long)gridDim.x * blockDim.x;
   // whole warps iterate together (staging needs every lane); out-of-range lanes carry zero seeds
@@ -572,52 +872,139 @@ solver_backward_kernel(const SolverArgs a) {
     const bool valid = p0 < a.B;
     const long long p = valid ? p0 : a.B - 1;
     T X[3] = {Xg[3 * p], Xg[3 * p + 1], Xg[3 * p + 2]};
-    Jet<T, S> ub;
-    jzero(ub);
-    if (valid) {
-      if (gug) ub.c[0] = gug[p];
-      if constexpr (S == 6) {
-        if (grg) {
-          const T g = grg[p];
-          ub.c[1] = T(a.pde.ct) * g; ub.c[2] = T(a.pde.cx) * g; ub.c[3] = T(a.pde.cy) * g;
-          ub.c[4] = T(a.pde.cxx) * g; ub.c[5] = T(a.pde.cyy) * g;
-        }
-      }
-    }
+    const Jet<T, S> ub = seed_cotangent<T, S>(a, p, valid);
     st.begin();
     st.put(ub.c[0]);                                       // d b4
-
-    // ---- recompute forward ----
     Jet<T, S> z[NQ], q[NQ], qb[NQ], zb[NQ];
     pre_forward<T, NQ, S>(sw, H, X, z);
+    feature_forward<T, NQ, ENC, S>(sw.C, z, q);
+    post_backward<T, NQ, S>(sw, H, q, ub, qb, st);
+    st.flush();                  // segment boundary: d C starts at a known accumulator index
+    feature_backward<T, NQ, ENC, S>(sw.C, z, qb, zb, st);
+    st.flush();
+    st.base = nacc_post(NQ, H) + nacc_contract(NQ, ENC);
     T Xb[3];
-    if constexpr (ENC == QCP_ENC_ANGLE) {
-      AngleFeat<T, NQ, S> f;
-      angle_forward<T, NQ, S>(z, f);
-      angle_contract<T, NQ, S>(sw.C, f, q);
-      post_backward<T, NQ, S>(sw, H, q, ub, qb, st);
-      angle_backward<T, NQ, S>(sw.C, z, f, qb, zb, st);
-    } else {
-      AmpFeat<T, NQ, S> f;
-      amp_forward<T, NQ, S>(z, f);
-      amp_contract<T, NQ, S>(sw.C, f, q);
-      post_backward<T, NQ, S>(sw, H, q, ub, qb, st);
-      amp_backward<T, NQ, S>(sw.C, z, f, qb, zb, st);
-    }
     pre_backward<T, NQ, S>(sw, H, X, zb, Xb, st);
     st.flush();
     if (gXg && valid) {
       gXg[3 * p] = Xb[0]; gXg[3 * p + 1] = Xb[1]; gXg[3 * p + 2] = Xb[2];
     }
   }
+  write_partials<T>(acc_all, nacc, static_cast<T*>(a.partials));
+}
+
+// ---- split backward (the forward saved its jets) --------------------------------------------
+//   post_backward_kernel     q (slot 1), grad_u/grad_r  -> qb (slot 1);  d b4, d w3, d b3, d w4
+//   contract_backward_kernel z (slot 0), qb (slot 1)    -> zb (slot 0);  d C
+//   pre_backward_kernel      X, zb (slot 0)             -> grad_X;       d b2, d w1, d b1, d w2
+// Their accumulators are consecutive segments of the fused kernel's accumulator order.
+template <typename T, int NQ, int ENC, int S>
+__global__ void __launch_bounds__(kThreads, Tune<T, S>::kPost)
+post_backward_kernel(const SolverArgs a) {
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  constexpr int CE = c_elems(NQ, ENC);
+  const int H = a.H;
+  const int nacc = nacc_post(NQ, H);
+  const SmemWeights<T> sw = carve_weights<T>(smem_raw, H, CE);
+  T* acc_all = reinterpret_cast<T*>(smem_raw + ((smem_weights_bytes<T>(H, CE) + 31) & ~size_t(31)));
+  T* tile_all = acc_all + (size_t)kWarpsPerBlock * nacc;
+  load_weights<T, NQ, ENC>(sw, a);
+  for (int i = threadIdx.x; i < kWarpsPerBlock * nacc; i += blockDim.x) acc_all[i] = T(0);
   __syncthreads();
-  T* out = static_cast<T*>(a.partials) + (size_t)blockIdx.x * nacc;
-  for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
-    T s = T(0);
-#pragma unroll
-    for (int w = 0; w < kWarpsPerBlock; ++w) s += acc_all[(size_t)w * nacc + i];
-    out[i] = s;
+  Stager<T> st = make_stager<T>(acc_all, tile_all, nacc);
+
+  T* wsg = static_cast<T*>(a.ws);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long Bpad = (a.B + 31) & ~31LL;
+  for (long long p0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; p0 < Bpad; p0 += stride) {
+    const bool valid = p0 < a.B;
+    const long long p = valid ? p0 : a.B - 1;
+    const Jet<T, S> ub = seed_cotangent<T, S>(a, p, valid);
+    Jet<T, S> q[NQ], qb[NQ];
+    ws_load<T, NQ, S>(wsg, a.B, 1, p, q);
+    st.begin();
+    st.put(ub.c[0]);                                       // d b4
+    post_backward<T, NQ, S>(sw, H, q, ub, qb, st);
+    st.flush();
+    if (valid) ws_store<T, NQ, S>(wsg, a.B, 1, p, qb);
   }
+  write_partials<T>(acc_all, nacc, static_cast<T*>(a.partials));
+}
+
+template <typename T, int NQ, int ENC, int S>
+__global__ void __launch_bounds__(kThreads, Tune<T, S>::kContract)
+contract_backward_kernel(const SolverArgs a) {
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  constexpr int CE = c_elems(NQ, ENC);
+  constexpr int nacc = nacc_contract(NQ, ENC);
+  T* sC = reinterpret_cast<T*>(smem_raw);
+  T* acc_all = sC + ((CE + 3) & ~3);
+  T* tile_all = acc_all + (size_t)kWarpsPerBlock * nacc;
+  load_C<T, NQ, ENC>(sC, static_cast<const T*>(a.C));
+  for (int i = threadIdx.x; i < kWarpsPerBlock * nacc; i += blockDim.x) acc_all[i] = T(0);
+  __syncthreads();
+  Stager<T> st = make_stager<T>(acc_all, tile_all, nacc);
+
+  T* wsg = static_cast<T*>(a.ws);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long Bpad = (a.B + 31) & ~31LL;
+  for (long long p0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; p0 < Bpad; p0 += stride) {
+    const bool valid = p0 < a.B;
+    const long long p = valid ? p0 : a.B - 1;
+    Jet<T, S> z[NQ], qb[NQ], zb[NQ];
+    ws_load<T, NQ, S>(wsg, a.B, 0, p, z);
+    ws_load<T, NQ, S>(wsg, a.B, 1, p, qb);
+    if (!valid) {
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) jzero(qb[i]);
+    }
+    st.begin();
+    feature_backward<T, NQ, ENC, S>(sC, z, qb, zb, st);
+    st.flush();
+    if (valid) ws_store<T, NQ, S>(wsg, a.B, 0, p, zb);
+  }
+  write_partials<T>(acc_all, nacc, static_cast<T*>(a.partials));
+}
+
+template <typename T, int NQ, int ENC, int S>
+__global__ void __launch_bounds__(kThreads, Tune<T, S>::kPre)
+pre_backward_kernel(const SolverArgs a) {
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  constexpr int CE = c_elems(NQ, ENC);
+  const int H = a.H;
+  const int nacc = nacc_pre(NQ, H);
+  const SmemWeights<T> sw = carve_weights<T>(smem_raw, H, CE);
+  T* acc_all = reinterpret_cast<T*>(smem_raw + ((smem_weights_bytes<T>(H, CE) + 31) & ~size_t(31)));
+  T* tile_all = acc_all + (size_t)kWarpsPerBlock * nacc;
+  load_weights<T, NQ, ENC>(sw, a);
+  for (int i = threadIdx.x; i < kWarpsPerBlock * nacc; i += blockDim.x) acc_all[i] = T(0);
+  __syncthreads();
+  Stager<T> st = make_stager<T>(acc_all, tile_all, nacc);
+
+  const T* Xg = static_cast<const T*>(a.X);
+  T* gXg = static_cast<T*>(a.gX);
+  const T* wsg = static_cast<const T*>(a.ws);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long Bpad = (a.B + 31) & ~31LL;
+  for (long long p0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; p0 < Bpad; p0 += stride) {
+    const bool valid = p0 < a.B;
+    const long long p = valid ? p0 : a.B - 1;
+    T X[3] = {Xg[3 * p], Xg[3 * p + 1], Xg[3 * p + 2]};
+    Jet<T, S> zb[NQ];
+    ws_load<T, NQ, S>(wsg, a.B, 0, p, zb);
+    if (!valid) {
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) jzero(zb[j]);
+    }
+    T Xb[3];
+    st.begin();
+    pre_backward<T, NQ, S>(sw, H, X, zb, Xb, st);
+    st.flush();
+    if (gXg && valid) {
+      gXg[3 * p] = Xb[0]; gXg[3 * p + 1] = Xb[1]; gXg[3 * p + 2] = Xb[2];
+    }
+  }
+  write_partials<T>(acc_all, nacc, static_cast<T*>(a.partials));
 }
 
 // ---- stand-alone quantum layer (DVQuantumLayer.forward / its reverse mode) ----------------
@@ -625,13 +1012,8 @@ template <typename T, int NQ, int ENC>
 __global__ void __launch_bounds__(kThreads)
 layer_forward_kernel(const LayerArgs a) {
   extern __shared__ __align__(32) unsigned char smem_raw[];
-  constexpr int F = num_features(NQ, ENC);
-  Vec4<T>* sC = reinterpret_cast<Vec4<T>*>(smem_raw);
-  {
-    T* d = reinterpret_cast<T*>(sC);
-    const T* C = static_cast<const T*>(a.C);
-    for (int i = threadIdx.x; i < 4 * F; i += blockDim.x) d[i] = C[i];
-  }
+  T* sC = reinterpret_cast<T*>(smem_raw);
+  load_C<T, NQ, ENC>(sC, static_cast<const T*>(a.C));
   __syncthreads();
   const T* zg = static_cast<const T*>(a.z);
   T* qg = static_cast<T*>(a.q);
@@ -640,15 +1022,7 @@ layer_forward_kernel(const LayerArgs a) {
     Jet<T, 1> z[NQ], q[NQ];
 #pragma unroll
     for (int j = 0; j < NQ; ++j) z[j].c[0] = zg[p * NQ + j];
-    if constexpr (ENC == QCP_ENC_ANGLE) {
-      AngleFeat<T, NQ, 1> f;
-      angle_forward<T, NQ, 1>(z, f);
-      angle_contract<T, NQ, 1>(sC, f, q);
-    } else {
-      AmpFeat<T, NQ, 1> f;
-      amp_forward<T, NQ, 1>(z, f);
-      amp_contract<T, NQ, 1>(sC, f, q);
-    }
+    feature_forward<T, NQ, ENC, 1>(sC, z, q);
 #pragma unroll
     for (int i = 0; i < NQ; ++i) qg[(long long)i * a.B + p] = q[i].c[0];
   }
@@ -658,23 +1032,15 @@ template <typename T, int NQ, int ENC>
 __global__ void __launch_bounds__(kThreads)
 layer_backward_kernel(const LayerArgs a) {
   extern __shared__ __align__(32) unsigned char smem_raw[];
-  constexpr int F = num_features(NQ, ENC);
-  constexpr int nacc = F * NQ;
-  Vec4<T>* sC = reinterpret_cast<Vec4<T>*>(smem_raw);
-  T* acc_all = reinterpret_cast<T*>(smem_raw) + 4 * F;
+  constexpr int CE = c_elems(NQ, ENC);
+  constexpr int nacc = nacc_contract(NQ, ENC);
+  T* sC = reinterpret_cast<T*>(smem_raw);
+  T* acc_all = sC + ((CE + 3) & ~3);
   T* tile_all = acc_all + kWarpsPerBlock * nacc;
-  {
-    T* d = reinterpret_cast<T*>(sC);
-    const T* C = static_cast<const T*>(a.C);
-    for (int i = threadIdx.x; i < 4 * F; i += blockDim.x) d[i] = C[i];
-    for (int i = threadIdx.x; i < kWarpsPerBlock * nacc; i += blockDim.x) acc_all[i] = T(0);
-  }
+  load_C<T, NQ, ENC>(sC, static_cast<const T*>(a.C));
+  for (int i = threadIdx.x; i < kWarpsPerBlock * nacc; i += blockDim.x) acc_all[i] = T(0);
   __syncthreads();
-  const int warp = threadIdx.x >> 5;
-  Stager<T> st;
-  st.lane = threadIdx.x & 31;
-  st.acc = acc_all + warp * nacc;
-  st.tile = tile_all + (size_t)warp * kStageRows * kStagePitch;
+  Stager<T> st = make_stager<T>(acc_all, tile_all, nacc);
 
   const T* zg = static_cast<const T*>(a.z);
   const T* gq = static_cast<const T*>(a.gq);
@@ -691,51 +1057,55 @@ layer_backward_kernel(const LayerArgs a) {
       qb[j].c[0] = valid ? gq[(long long)j * a.B + p] : T(0);
     }
     st.begin();
-    if constexpr (ENC == QCP_ENC_ANGLE) {
-      AngleFeat<T, NQ, 1> f;
-      angle_forward<T, NQ, 1>(z, f);
-      angle_backward<T, NQ, 1>(sC, z, f, qb, zb, st);
-    } else {
-      AmpFeat<T, NQ, 1> f;
-      amp_forward<T, NQ, 1>(z, f);
-      amp_backward<T, NQ, 1>(sC, z, f, qb, zb, st);
-    }
+    feature_backward<T, NQ, ENC, 1>(sC, z, qb, zb, st);
     st.flush();
     if (gz && valid) {
 #pragma unroll
       for (int j = 0; j < NQ; ++j) gz[p * NQ + j] = zb[j].c[0];
     }
   }
-  __syncthreads();
-  T* out = static_cast<T*>(a.partials) + (size_t)blockIdx.x * nacc;
-  for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
-    T s = T(0);
-#pragma unroll
-    for (int w = 0; w < kWarpsPerBlock; ++w) s += acc_all[w * nacc + i];
-    out[i] = s;
-  }
+  write_partials<T>(acc_all, nacc, static_cast<T*>(a.partials));
 }
 
 // ------------------------------------------------------------------------------------------
 // host-side dispatch (instantiated per dtype in qcp_point_f32.cu / qcp_point_f64.cu)
 // ------------------------------------------------------------------------------------------
 template <typename T>
+size_t tiles_bytes() {
+  return sizeof(T) * (size_t)kWarpsPerBlock * kStageRows * kStagePitch;
+}
+
+template <typename T>
+size_t weights_bytes_padded(int n, int enc, int H) {
+  return (smem_weights_bytes<T>(H, c_elems(n, enc)) + 31) & ~size_t(31);
+}
+
+template <typename T>
 size_t solver_forward_smem(int n, int enc, int H) {
-  return smem_weights_bytes<T>(H, num_features(n, enc));
+  return smem_weights_bytes<T>(H, c_elems(n, enc));
 }
 
 template <typename T>
 size_t solver_backward_smem_impl(int n, int enc, int H) {
-  size_t w = (smem_weights_bytes<T>(H, num_features(n, enc)) + 31) & ~size_t(31);
-  return w + sizeof(T) * ((size_t)kWarpsPerBlock * nacc_solver(n, enc, H) +
-                          (size_t)kWarpsPerBlock * kStageRows * kStagePitch);
+  return weights_bytes_padded<T>(n, enc, H) +
+         sizeof(T) * (size_t)kWarpsPerBlock * nacc_solver(n, enc, H) + tiles_bytes<T>();
 }
 
 template <typename T>
-size_t layer_backward_smem(int n, int enc) {
-  const int F = num_features(n, enc);
-  return sizeof(T) * ((size_t)4 * F + (size_t)kWarpsPerBlock * F * n +
-                      (size_t)kWarpsPerBlock * kStageRows * kStagePitch);
+size_t c_only_smem(int n, int enc) {
+  return sizeof(T) * ((size_t)((c_elems(n, enc) + 3) & ~3) +
+                      (size_t)kWarpsPerBlock * nacc_contract(n, enc)) + tiles_bytes<T>();
+}
+
+// which: 0 post, 1 contract, 2 pre
+template <typename T>
+size_t split_smem(int which, int n, int enc, int H) {
+  if (which == 0)
+    return weights_bytes_padded<T>(n, enc, H) + sizeof(T) * (size_t)kWarpsPerBlock * nacc_post(n, H) +
+           tiles_bytes<T>();
+  if (which == 1) return c_only_smem<T>(n, enc);
+  return weights_bytes_padded<T>(n, enc, H) + sizeof(T) * (size_t)kWarpsPerBlock * nacc_pre(n, H) +
+         tiles_bytes<T>();
 }
 
 template <typename K, typename A>
@@ -757,14 +1127,25 @@ int launch_checked(K kernel, int grid, size_t smem, cudaStream_t s, const char* 
   return 0;
 }
 
-#define QCP_DISPATCH_NQ_ENC(N, E, ...)                                       \
-  do {                                                                        \
-    if ((N) == 2 && (E) == 0) { constexpr int NQ = 2, ENC = 0; __VA_ARGS__; }         \
-    else if ((N) == 3 && (E) == 0) { constexpr int NQ = 3, ENC = 0; __VA_ARGS__; }    \
-    else if ((N) == 4 && (E) == 0) { constexpr int NQ = 4, ENC = 0; __VA_ARGS__; }    \
-    else if ((N) == 2 && (E) == 1) { constexpr int NQ = 2, ENC = 1; __VA_ARGS__; }    \
-    else if ((N) == 3 && (E) == 1) { constexpr int NQ = 3, ENC = 1; __VA_ARGS__; }    \
-    else if ((N) == 4 && (E) == 1) { constexpr int NQ = 4, ENC = 1; __VA_ARGS__; }    \
+template <typename K>
+int blocks_per_sm(K kernel, size_t smem) {
+  int per_sm = 0;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess ||
+      per_sm < 1)
+    per_sm = 1;
+  return per_sm;
+}
+
+#define QCP_DISPATCH_NQ_ENC(N, E, ...)                                                \
+  do {                                                                                \
+    if ((N) == 2 && (E) == 0) { constexpr int NQ = 2, ENC = 0; __VA_ARGS__; }          \
+    else if ((N) == 3 && (E) == 0) { constexpr int NQ = 3, ENC = 0; __VA_ARGS__; }     \
+    else if ((N) == 4 && (E) == 0) { constexpr int NQ = 4, ENC = 0; __VA_ARGS__; }     \
+    else if ((N) == 2 && (E) == 1) { constexpr int NQ = 2, ENC = 1; __VA_ARGS__; }     \
+    else if ((N) == 3 && (E) == 1) { constexpr int NQ = 3, ENC = 1; __VA_ARGS__; }     \
+    else if ((N) == 4 && (E) == 1) { constexpr int NQ = 4, ENC = 1; __VA_ARGS__; }     \
     else { set_error("fused engine supports 2..4 qubits, got n=%d enc=%d", (N), (E)); return 1; } \
   } while (0)
 
@@ -796,20 +1177,58 @@ int launch_solver_backward(int n, int enc, int mode, const SolverArgs& a, int gr
 
 template <typename T>
 int launch_layer_forward(int n, int enc, const LayerArgs& a, int grid, cudaStream_t s) {
-  const size_t smem = sizeof(T) * 4 * (size_t)num_features(n, enc);
+  const size_t smem = sizeof(T) * (size_t)c_elems(n, enc);
   QCP_DISPATCH_NQ_ENC(n, enc, {
-    return launch_checked(&layer_forward_kernel<T, NQ, ENC>, grid, smem, s, "layer_forward",
-                          a);
+    return launch_checked(&layer_forward_kernel<T, NQ, ENC>, grid, smem, s, "layer_forward", a);
   });
   return 1;
 }
 
 template <typename T>
 int launch_layer_backward(int n, int enc, const LayerArgs& a, int grid, cudaStream_t s) {
-  const size_t smem = layer_backward_smem<T>(n, enc);
+  const size_t smem = c_only_smem<T>(n, enc);
   QCP_DISPATCH_NQ_ENC(n, enc, {
-    return launch_checked(&layer_backward_kernel<T, NQ, ENC>, grid, smem, s, "layer_backward",
-                          a);
+    return launch_checked(&layer_backward_kernel<T, NQ, ENC>, grid, smem, s, "layer_backward", a);
+  });
+  return 1;
+}
+
+template <typename T>
+int solver_split_grids(int n, int enc, int mode, int H, int num_sms, SplitGrids* g) {
+  const size_t m0 = split_smem<T>(0, n, enc, H), m1 = split_smem<T>(1, n, enc, H),
+               m2 = split_smem<T>(2, n, enc, H);
+  QCP_DISPATCH_NQ_ENC(n, enc, {
+    if (mode == QCP_MODE_RESIDUAL) {
+      g->post = num_sms * blocks_per_sm(&post_backward_kernel<T, NQ, ENC, 6>, m0);
+      g->contract = num_sms * blocks_per_sm(&contract_backward_kernel<T, NQ, ENC, 6>, m1);
+      g->pre = num_sms * blocks_per_sm(&pre_backward_kernel<T, NQ, ENC, 6>, m2);
+    } else {
+      g->post = num_sms * blocks_per_sm(&post_backward_kernel<T, NQ, ENC, 1>, m0);
+      g->contract = num_sms * blocks_per_sm(&contract_backward_kernel<T, NQ, ENC, 1>, m1);
+      g->pre = num_sms * blocks_per_sm(&pre_backward_kernel<T, NQ, ENC, 1>, m2);
+    }
+    return 0;
+  });
+  return 1;
+}
+
+template <typename T>
+int launch_solver_backward_split(int n, int enc, int mode, const SolverArgs& a, const SplitGrids& g,
+                                 void* part_post, void* part_contract, void* part_pre,
+                                 cudaStream_t s) {
+  SolverArgs a0 = a, a1 = a, a2 = a;
+  a0.partials = part_post; a1.partials = part_contract; a2.partials = part_pre;
+  const size_t m0 = split_smem<T>(0, n, enc, a.H), m1 = split_smem<T>(1, n, enc, a.H),
+               m2 = split_smem<T>(2, n, enc, a.H);
+  QCP_DISPATCH_NQ_ENC(n, enc, {
+    if (mode == QCP_MODE_RESIDUAL) {
+      if (launch_checked(&post_backward_kernel<T, NQ, ENC, 6>, g.post, m0, s, "post_backward", a0)) return 1;
+      if (launch_checked(&contract_backward_kernel<T, NQ, ENC, 6>, g.contract, m1, s, "contract_backward", a1)) return 1;
+      return launch_checked(&pre_backward_kernel<T, NQ, ENC, 6>, g.pre, m2, s, "pre_backward", a2);
+    }
+    if (launch_checked(&post_backward_kernel<T, NQ, ENC, 1>, g.post, m0, s, "post_backward", a0)) return 1;
+    if (launch_checked(&contract_backward_kernel<T, NQ, ENC, 1>, g.contract, m1, s, "contract_backward", a1)) return 1;
+    return launch_checked(&pre_backward_kernel<T, NQ, ENC, 1>, g.pre, m2, s, "pre_backward", a2);
   });
   return 1;
 }
@@ -821,24 +1240,13 @@ size_t solver_backward_smem(int n, int enc, int H) {
 
 template <typename T>
 int solver_backward_max_grid(int n, int enc, int mode, int H, int num_sms) {
-  int per_sm = 0;
   const size_t smem = solver_backward_smem_impl<T>(n, enc, H);
-  cudaError_t e = cudaErrorInvalidValue;
   QCP_DISPATCH_NQ_ENC(n, enc, {
-    if (mode == QCP_MODE_RESIDUAL) {
-      auto k = &solver_backward_kernel<T, NQ, ENC, 6>;
-      if (smem > 48 * 1024)
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, smem);
-    } else {
-      auto k = &solver_backward_kernel<T, NQ, ENC, 1>;
-      if (smem > 48 * 1024)
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, smem);
-    }
+    if (mode == QCP_MODE_RESIDUAL)
+      return num_sms * blocks_per_sm(&solver_backward_kernel<T, NQ, ENC, 6>, smem);
+    return num_sms * blocks_per_sm(&solver_backward_kernel<T, NQ, ENC, 1>, smem);
   });
-  if (e != cudaSuccess || per_sm < 1) per_sm = 1;
-  return per_sm * num_sms;
+  return num_sms;
 }
 
 }  // namespace qcp

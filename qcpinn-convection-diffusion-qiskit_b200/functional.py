@@ -27,6 +27,9 @@ _DTYPE_CODE = {torch.float32: 0, torch.float64: 1}
 MLP_NAMES = ("w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4")
 
 launch_counter = 0   # CUDA kernels launched by this library (bench.py reports it as gpu_launches)
+# True: the forward saves its Taylor jets (2*n*S values per point) and the backward runs as three
+# lean kernels over them; False: one fused backward kernel recomputes the forward from X.
+SAVE_JETS = True
 
 
 def _count(n: int) -> None:
@@ -144,7 +147,12 @@ class Plan:
         _count(3 if b else 1)
         return gz, gtheta
 
-    def solver_forward(self, X, mlp, mode, coeffs=None, want_streams=False):
+    def workspace(self, batch, mode):
+        """Uninitialised saved-jet workspace for one (batch, mode) forward/backward pair."""
+        n = self.lib.qcp_solver_workspace_elems(self._handle, batch, mode)
+        return torch.empty(max(int(n), 1), dtype=self.dtype, device=self.device)
+
+    def solver_forward(self, X, mlp, mode, coeffs=None, want_streams=False, save=None):
         b = X.shape[0]
         u = torch.empty(b, dtype=self.dtype, device=self.device)
         r = torch.empty(b, dtype=self.dtype, device=self.device) if mode == MODE_RESIDUAL else None
@@ -158,12 +166,14 @@ class Plan:
                 ctypes.c_void_p(u.data_ptr()),
                 ctypes.c_void_p(r.data_ptr() if r is not None else None),
                 ctypes.c_void_p(streams.data_ptr() if streams is not None else None),
+                ctypes.c_void_p(save.data_ptr() if save is not None else None),
                 self._stream())
         _lib.check(rc, "qcp_solver_forward")
         _count(1 if b else 0)
         return u, r, streams
 
-    def solver_backward(self, X, mlp, theta, grad_u, grad_r, mode, coeffs=None, need_gx=False):
+    def solver_backward(self, X, mlp, theta, grad_u, grad_r, mode, coeffs=None, need_gx=False,
+                        save=None):
         b = X.shape[0]
         sizes = [t.numel() for t in mlp] + [self.n_theta]
         flat = torch.empty(sum(sizes), dtype=self.dtype, device=self.device)
@@ -181,10 +191,11 @@ class Plan:
                 ctypes.c_void_p(X.data_ptr()),
                 ctypes.c_void_p(grad_u.data_ptr() if grad_u is not None else None),
                 ctypes.c_void_p(grad_r.data_ptr() if grad_r is not None else None),
-                b, mode, c, ctypes.byref(g), ctypes.c_void_p(views[8].data_ptr()),
+                b, mode, c, ctypes.c_void_p(save.data_ptr() if save is not None else None),
+                ctypes.byref(g), ctypes.c_void_p(views[8].data_ptr()),
                 ctypes.c_void_p(gx.data_ptr() if gx is not None else None), self._stream())
         _lib.check(rc, "qcp_solver_backward")
-        _count(3)
+        _count(5 if (save is not None and b > 0) else 3)
         return views, gx
 
 
@@ -227,7 +238,10 @@ class _SolverFn(torch.autograd.Function):
         tt = plan._t(theta).reshape(-1)
         mt = [plan._t(w) for w in mlp]
         plan.prepare(tt, key)
-        u, r, _ = plan.solver_forward(Xt, mt, mode, coeffs)
+        needs_grad = any(ctx.needs_input_grad[4:])
+        save = plan.workspace(Xt.shape[0], mode) if (needs_grad and SAVE_JETS and Xt.shape[0]) else None
+        u, r, _ = plan.solver_forward(Xt, mt, mode, coeffs, save=save)
+        ctx.save = save
         ctx.plan, ctx.key, ctx.mode, ctx.coeffs = plan, key, mode, coeffs
         ctx.save_for_backward(Xt, tt, *mt)
         ctx.in_dtypes = [X.dtype, theta.dtype] + [w.dtype for w in mlp]
@@ -246,7 +260,9 @@ class _SolverFn(torch.autograd.Function):
         gu = _grad_in(plan, grad_u, (b,))
         gr = _grad_in(plan, grad_r, (b,)) if ctx.mode == MODE_RESIDUAL else None
         need_gx = ctx.needs_input_grad[4] and ctx.mode == MODE_VALUE
-        views, gx = plan.solver_backward(Xt, mt, tt, gu, gr, ctx.mode, ctx.coeffs, need_gx)
+        views, gx = plan.solver_backward(Xt, mt, tt, gu, gr, ctx.mode, ctx.coeffs, need_gx,
+                                         save=ctx.save)
+        ctx.save = None   # consumed (overwritten with cotangents)
         dt = ctx.in_dtypes
         gX = gx.to(dt[0]) if gx is not None else None
         gtheta = views[8].to(dt[1]).view(ctx.theta_shape) if ctx.needs_input_grad[5] else None
