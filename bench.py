@@ -50,6 +50,7 @@ def parse_args():
                     help="residual collocation points per step over ALL ranks")
     ap.add_argument("--no-secondary", action="store_true", help="skip the other dtype's line")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="eager steps (no CUDA-graph replay)")
     ap.add_argument("--cpu-points", type=int, default=65_536)
     ap.add_argument("--cpu-steps", type=int, default=3)
     return ap.parse_args()
@@ -160,6 +161,7 @@ def run_ours(ns):
     from qcpinn_b200.trainer.diffusion_train import TrainStep, _make_averager
     import torch.distributed as dist
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's banner off stdout (one JSON line)
     rank, world, local = init_from_env()
     if world != ns.gpus and world > 1:
         raise SystemExit(f"--gpus {ns.gpus} but WORLD_SIZE={world}")
@@ -175,25 +177,26 @@ def run_ours(ns):
         torch.manual_seed(0)                       # identical weights on every rank
         logger = qb.Logging(os.path.join(tempfile.gettempdir(), f"qcpinn_bench_r{rank}"))
         model = qb.DVPDESolver(model_args(dtype_name), logger, device=device)
-        step = TrainStep(model, pts_rank, _make_averager(model))
+        step = TrainStep(model, pts_rank, _make_averager(model),
+                         use_graph=False if ns.no_graph else None)
         return model, step
 
     def measure(dtype_name, with_e2e):
         model, step = make(dtype_name)
         torch.manual_seed(1234 + rank)             # per-rank sampler stream
         clk = ClockSampler(local)
-        # warm-up outside the clock sampler, then the timed region under it
-        for _ in range(ns.warmup):
+        clk.start()       # nvidia-smi needs ~0.2 s to start: launch it before the warm-up steps;
+        for _ in range(ns.warmup):   # only samples in the upper half of the clock range count
             step()
         launches0 = F.launch_counter
-        clk.start()
         ms, wall_ms = timed_steps(step, ns.steps, 0, torch, dist, world, device)
         clocks = clk.stop()
         launches = F.launch_counter - launches0
         res = {"ms": ms, "wall_ms": wall_ms, "clocks": clocks, "launches": launches,
                "value": pts_total * ns.steps / (ms * 1e-3)}
 
-        # dominant kernel: residual backward, timed alone with CUDA events on the launch stream
+        # dominant kernels: the residual backward (post + contraction + pre adjoint kernels over the
+        # jets saved by the forward), timed alone with CUDA events on the launch stream
         plan = model._plan(device)
         X = torch.rand(pts_rank, 3, device=device).to(plan.dtype)
         gr = torch.rand(pts_rank, device=device).to(plan.dtype)
@@ -201,23 +204,28 @@ def run_ours(ns):
         mlp = [plan._t(w) for w in model._mlp_tensors()]
         plan.prepare(theta)
         coeffs = (1.0, 1.0, 1.0, -0.01, -0.01)
-        for _ in range(2):
-            plan.solver_backward(X, mlp, theta, None, gr, F.MODE_RESIDUAL, coeffs)
+        ws = plan.workspace(pts_rank, F.MODE_RESIDUAL)
         reps = max(3, min(ns.steps, 10))
         k0 = torch.cuda.Event(enable_timing=True)
         k1 = torch.cuda.Event(enable_timing=True)
-        k0.record()
-        for _ in range(reps):
-            plan.solver_backward(X, mlp, theta, None, gr, F.MODE_RESIDUAL, coeffs)
-        k1.record()
-        torch.cuda.synchronize(device)
-        res["bwd_kernel_ms"] = k0.elapsed_time(k1) / reps
-        k0.record()
-        for _ in range(reps):
-            plan.solver_forward(X, mlp, F.MODE_RESIDUAL, coeffs)
-        k1.record()
-        torch.cuda.synchronize(device)
-        res["fwd_kernel_ms"] = k0.elapsed_time(k1) / reps
+
+        def timed(fn):
+            for _ in range(2):
+                fn()
+            k0.record()
+            for _ in range(reps):
+                fn()
+            k1.record()
+            torch.cuda.synchronize(device)
+            return k0.elapsed_time(k1) / reps
+
+        def fwd_bwd():
+            plan.solver_forward(X, mlp, F.MODE_RESIDUAL, coeffs, save=ws)
+            plan.solver_backward(X, mlp, theta, None, gr, F.MODE_RESIDUAL, coeffs, save=ws)
+
+        res["fwd_kernel_ms"] = timed(lambda: plan.solver_forward(X, mlp, F.MODE_RESIDUAL, coeffs, save=ws))
+        res["bwd_kernel_ms"] = timed(fwd_bwd) - res["fwd_kernel_ms"]
+        del ws
 
         if with_e2e:
             # host-resident inputs: pinned batches, H2D + loss D2H inside the timed region
@@ -242,8 +250,7 @@ def run_ours(ns):
             def e2e_step():
                 host = ring[state["i"] % len(ring)]
                 state["i"] += 1
-                batch = tuple(t.to(device, non_blocking=True) for t in host)
-                return step(batch)
+                return step(host)       # TrainStep copies the pinned host batch to the device
 
             ms_e, _ = timed_steps(e2e_step, ns.steps, min(ns.warmup, 3), torch, dist, world, device)
             res["e2e"] = {"value": pts_total * ns.steps / (ms_e * 1e-3), "unit": "points/s",
@@ -273,7 +280,8 @@ def run_ours(ns):
 
     def roof(res, d):
         achieved = bwd_flops_pt * pts_rank / (res["bwd_kernel_ms"] * 1e-3)
-        return {"bound": "fma", "kernel": f"solver_backward_kernel<{d},4,angle,residual>",
+        return {"bound": "fma",
+                "kernel": f"residual backward = post_/contract_/pre_backward_kernel<{d},4,angle,6>",
                 "achieved": achieved / 1e12, "peak": peaks[d] / 1e12, "unit": "TFLOP/s",
                 "frac": achieved / peaks[d], "traffic": None,
                 "peak_source": "qcp_bench_fma measured in this run (FP%s FMA pipe)" % d[1:],

@@ -121,6 +121,13 @@ int qcp_solver_backward(qcp_plan_t* plan, const qcp_mlp_t* weights, const void* 
                         int mode, const double* coeffs, void* save, const qcp_mlp_t* grads,
                         void* grad_theta, void* grad_X, void* stream);
 
+/* Sampler.sample() tail fused in one kernel (reference data/diffusion_dataset.py:12-38): maps
+ * uniform random numbers rnd [n,3] (float32, from torch.rand) into the box lo_hi = HOST float[6]
+ * (lo[3], hi[3]) -> X [n,3], and evaluates the analytic target y [n]: kind 0 = solution u,
+ * kind 1 = forcing r(diffusion, v_x, v_y).  float32 like the reference. */
+int qcp_sample_targets(const float* rnd, long long n, const float* lo_hi, int kind,
+                       double diffusion, double v_x, double v_y, float* X, float* y, void* stream);
+
 /* FMA-pipe micro-benchmark used as the roofline denominator: runs
  * ``iters`` dependent-chain FMA rounds on every SM and returns achieved FLOP/s. */
 int qcp_bench_fma(int dtype, int iters, double* flops_per_s, void* stream);

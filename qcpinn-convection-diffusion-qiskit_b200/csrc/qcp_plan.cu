@@ -96,7 +96,7 @@ __device__ __forceinline__ int insert_zero_bit(int r, int pos) {
 // A[col*M + k].  Wire w <-> bit position n-1-w (wire 0 = most significant bit).
 template <typename TH>
 __device__ void apply_op(double2* A, int ncol, int n, const GateOp op, const TH* theta,
-                         const double2* consts, bool dag) {
+                         const double2* consts, bool dag, const Mat2* table = nullptr) {
   const int M = 1 << n;
   if (op.kind == QCP_GATE_U4) {
     const int pa = n - 1 - op.a, pb = n - 1 - op.b;
@@ -126,8 +126,13 @@ __device__ void apply_op(double2* A, int ncol, int n, const GateOp op, const TH*
     const int wt = ctl ? op.b : op.a;
     const int pt = n - 1 - wt;
     const int pc = ctl ? n - 1 - op.a : -1;
-    const double th = op.p >= 0 ? (double)theta[op.p] : 0.0;
-    Mat2 u = gate_mat2(op.kind, th);
+    Mat2 u;
+    if (table) {
+      u = *table;
+    } else {
+      const double th = op.p >= 0 ? (double)theta[op.p] : 0.0;
+      u = gate_mat2(op.kind, th);
+    }
     if (dag) u = dagger(u);
     const int items = ncol * (M >> 1);
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
@@ -143,14 +148,30 @@ __device__ void apply_op(double2* A, int ncol, int n, const GateOp op, const TH*
   __syncthreads();
 }
 
+constexpr int kMaxTableOps = 96;   // gate matrices precomputed in shared memory (else on the fly)
+
+// one sincos per gate, computed by n_ops threads in parallel instead of by every phase
+template <typename TH>
+__device__ const Mat2* build_gate_table(Mat2* table, const GateOp* ops, int n_ops, const TH* theta) {
+  if (n_ops > kMaxTableOps) return nullptr;
+  for (int g = threadIdx.x; g < n_ops; g += blockDim.x) {
+    const GateOp op = ops[g];
+    if (op.kind != QCP_GATE_U4)
+      table[g] = gate_mat2(op.kind, op.p >= 0 ? (double)theta[op.p] : 0.0);
+  }
+  __syncthreads();
+  return table;
+}
+
 template <typename TH>
 __device__ void simulate_columns(double2* V, int n, const GateOp* ops, int n_ops, const TH* theta,
-                                 const double2* consts) {
+                                 const double2* consts, const Mat2* table) {
   const int M = 1 << n;
   for (int i = threadIdx.x; i < M * M; i += blockDim.x)
     V[i] = make_double2((i / M) == (i % M) ? 1.0 : 0.0, 0.0);
   __syncthreads();
-  for (int g = 0; g < n_ops; ++g) apply_op(V, M, n, ops[g], theta, consts, false);
+  for (int g = 0; g < n_ops; ++g)
+    apply_op(V, M, n, ops[g], theta, consts, false, table ? table + g : nullptr);
 }
 
 __device__ __forceinline__ int trit_of(int s, int j, int n) {
@@ -162,12 +183,22 @@ __device__ __forceinline__ int trit_of(int s, int j, int n) {
 // ---------------------------------------------------------------------------------------------
 // prepare: theta -> V -> O_i -> C
 // ---------------------------------------------------------------------------------------------
+// Scratch (V: M^2, O/R: n M^2, Lambda: M^2 complex128) lives in shared memory when it fits
+// (n <= 5), which removes the global-memory round trip of every one of the ~100 tiny phases.
+extern __shared__ __align__(16) unsigned char setup_smem[];
+
 template <typename T>
 __global__ void __launch_bounds__(kSetupThreads)
 prepare_kernel(int n, int enc, const GateOp* ops, int n_ops, const T* theta, const double2* consts,
-               double2* V, double2* O, double* C64, T* CT) {
+               double2* V, double2* O, double* C64, T* CT, int use_smem) {
   const int M = 1 << n;
-  simulate_columns(V, n, ops, n_ops, theta, consts);
+  __shared__ Mat2 table_mem[kMaxTableOps];
+  if (use_smem) {
+    V = reinterpret_cast<double2*>(setup_smem);
+    O = V + M * M;
+  }
+  const Mat2* table = build_gate_table(table_mem, ops, n_ops, theta);
+  simulate_columns(V, n, ops, n_ops, theta, consts, table);
 
   // O_i[b,a] = sum_k conj(V[k,b]) z_i(k) V[k,a]
   for (int it = threadIdx.x; it < n * M * M; it += blockDim.x) {
@@ -245,16 +276,28 @@ struct ScatterArgs {
   int seg_grid[3];
 };
 
+constexpr int kReduceSlices = 8;   // threads cooperating on one accumulator (over the block index)
+
 template <typename T>
-__global__ void reduce_solver_kernel(const ScatterArgs a) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.nacc) return;
-  int seg = 0, local = idx;
-  while (seg < 2 && local >= a.seg_len[seg]) { local -= a.seg_len[seg]; ++seg; }
-  const T* partials = static_cast<const T*>(a.seg_ptr[seg]);
-  const int len = a.seg_len[seg];
+__global__ void __launch_bounds__(32 * kReduceSlices)
+reduce_solver_kernel(const ScatterArgs a) {
+  __shared__ double part[kReduceSlices][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + lane;
   double s = 0.0;
-  for (int g = 0; g < a.seg_grid[seg]; ++g) s += (double)partials[(size_t)g * len + local];
+  if (idx < a.nacc) {
+    int seg = 0, local = idx;
+    while (seg < 2 && local >= a.seg_len[seg]) { local -= a.seg_len[seg]; ++seg; }
+    const T* partials = static_cast<const T*>(a.seg_ptr[seg]);
+    const int len = a.seg_len[seg];
+    for (int g = slice; g < a.seg_grid[seg]; g += kReduceSlices)
+      s += (double)partials[(size_t)g * len + local];
+  }
+  part[slice][lane] = s;
+  __syncthreads();
+  if (slice != 0 || idx >= a.nacc) return;
+#pragma unroll
+  for (int k = 1; k < kReduceSlices; ++k) s += part[k][lane];
   const int n = a.n, H = a.H;
   int r = idx;
   if (r == 0) { static_cast<T*>(a.b4)[0] = (T)s; return; }
@@ -280,36 +323,53 @@ __global__ void reduce_solver_kernel(const ScatterArgs a) {
 }
 
 template <typename T>
-__global__ void reduce_layer_kernel(const T* __restrict__ partials, double* Cbar, int grid, int nacc,
-                                    int n, int enc) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= nacc) return;
+__global__ void __launch_bounds__(32 * kReduceSlices)
+reduce_layer_kernel(const T* __restrict__ partials, double* Cbar, int grid, int nacc, int n, int enc) {
+  __shared__ double part[kReduceSlices][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + lane;
   double s = 0.0;
-  for (int g = 0; g < grid; ++g) s += (double)partials[(size_t)g * nacc + idx];
+  if (idx < nacc)
+    for (int g = slice; g < grid; g += kReduceSlices) s += (double)partials[(size_t)g * nacc + idx];
+  part[slice][lane] = s;
+  __syncthreads();
+  if (slice != 0 || idx >= nacc) return;
+#pragma unroll
+  for (int k = 1; k < kReduceSlices; ++k) s += part[k][lane];
   Cbar[cbar_index(idx, n, enc)] = s;
 }
 
 // ---------------------------------------------------------------------------------------------
 // theta gradient: C-bar -> R_i -> Lambda -> reverse sweep
 // ---------------------------------------------------------------------------------------------
-__device__ double block_sum(double v, double* scratch) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double s = 0.0;
-  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += scratch[w];
-  return s;
-}
+constexpr int kMaxThetaSmem = 256;   // circuit angles accumulated in shared memory (per warp)
+
+__device__ __forceinline__ void atomicAdd_T(double* p, double v) { atomicAdd(p, v); }
+__device__ __forceinline__ void atomicAdd_T(float* p, double v) { atomicAdd(p, (float)v); }
 
 template <typename T>
 __global__ void __launch_bounds__(kSetupThreads)
 theta_grad_kernel(int n, int enc, const GateOp* ops, int n_ops, const T* theta, int n_theta,
                   const double2* consts, const double* Cbar, double2* V, double2* R, double2* Lam,
-                  T* gtheta) {
-  __shared__ double scratch[kSetupThreads / 32];
+                  T* gtheta, int use_smem) {
+  __shared__ Mat2 table_mem[kMaxTableOps];
+  __shared__ double gacc[kSetupThreads / 32][kMaxThetaSmem];   // one row per warp: no atomics
   const int M = 1 << n;
-  simulate_columns(V, n, ops, n_ops, theta, consts);
+  if (use_smem) {
+    V = reinterpret_cast<double2*>(setup_smem);
+    R = V + M * M;
+    Lam = R + n * M * M;
+  }
+  const bool smem_acc = n_theta <= kMaxThetaSmem;
+  for (int p = threadIdx.x; p < n_theta; p += blockDim.x) {
+    if (smem_acc) {
+      for (int w = 0; w < kSetupThreads / 32; ++w) gacc[w][p] = 0.0;
+    } else {
+      gtheta[p] = (T)0;
+    }
+  }
+  const Mat2* table = build_gate_table(table_mem, ops, n_ops, theta);
+  simulate_columns(V, n, ops, n_ops, theta, consts, table);
 
   // R_i[b,a] = sum_s Cbar[i,s] E_s[b,a]
   for (int it = threadIdx.x; it < n * M * M; it += blockDim.x) {
@@ -362,9 +422,6 @@ theta_grad_kernel(int n, int enc, const GateOp* ops, int n_ops, const T* theta, 
   }
   __syncthreads();
 
-  for (int p = threadIdx.x; p < n_theta; p += blockDim.x) gtheta[p] = (T)0;
-  __syncthreads();
-
   for (int g = n_ops - 1; g >= 0; --g) {
     const GateOp op = ops[g];
     if (op.p >= 0 && op.kind != QCP_GATE_U4) {
@@ -391,11 +448,23 @@ theta_grad_kernel(int n, int enc, const GateOp* ops, int n_ops, const T* theta, 
         const double2 l = Lam[col + k];
         part += l.x * hpsi.y - l.y * hpsi.x;   // Im(conj(l) * hpsi)
       }
-      const double tot = block_sum(part, scratch);
-      if (threadIdx.x == 0) gtheta[op.p] = (T)((double)gtheta[op.p] + tot);
+      // warp-reduce, then one shared-memory atomic per warp: no block barrier per gate
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if ((threadIdx.x & 31) == 0) {
+        if (smem_acc) gacc[threadIdx.x >> 5][op.p] += part;   // this warp's own row
+        else atomicAdd_T(&gtheta[op.p], part);
+      }
     }
-    apply_op(V, M, n, op, theta, consts, true);
-    apply_op(Lam, M, n, op, theta, consts, true);
+    apply_op(V, M, n, op, theta, consts, true, table ? table + g : nullptr);
+    apply_op(Lam, M, n, op, theta, consts, true, table ? table + g : nullptr);
+  }
+  if (smem_acc) {
+    __syncthreads();
+    for (int p = threadIdx.x; p < n_theta; p += blockDim.x) {
+      double s = 0.0;
+      for (int w = 0; w < kSetupThreads / 32; ++w) s += gacc[w][p];   // fixed order: deterministic
+      gtheta[p] = (T)s;
+    }
   }
 }
 
@@ -442,6 +511,23 @@ struct qcp_plan {
 };
 
 static size_t elem_size(int dtype) { return dtype == QCP_F64 ? sizeof(double) : sizeof(float); }
+
+// dynamic shared memory of the two single-CTA setup kernels (0 => scratch stays in global memory)
+static size_t setup_smem_bytes(const qcp_plan* p, bool grad) {
+  const size_t MM = (size_t)p->M * p->M;
+  const size_t bytes = sizeof(double2) * MM * (size_t)(grad ? 2 + p->n : 1 + p->n);
+  return bytes <= 160 * 1024 ? bytes : 0;
+}
+
+template <typename K>
+static int opt_in_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024 &&
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return 1;
+  }
+  return 0;
+}
 
 static int ensure_partials(qcp_plan* p, size_t elems) {
   if (elems <= p->partials_elems) return 0;
@@ -545,14 +631,18 @@ int qcp_plan_num_features(const qcp_plan_t* p) { return p ? p->F : -1; }
 int qcp_prepare(qcp_plan_t* p, const void* theta, void* stream) {
   if (!p || (!theta && p->n_theta > 0)) { set_error("qcp_prepare: NULL argument"); return 1; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (p->dtype == QCP_F64)
-    prepare_kernel<double><<<1, kSetupThreads, 0, s>>>(p->n, p->enc, p->d_ops, p->n_ops,
+  size_t sm = setup_smem_bytes(p, false);
+  if (p->dtype == QCP_F64) {
+    if (opt_in_smem(&prepare_kernel<double>, sm)) sm = 0;
+    prepare_kernel<double><<<1, kSetupThreads, sm, s>>>(p->n, p->enc, p->d_ops, p->n_ops,
         static_cast<const double*>(theta), p->d_consts, p->d_V, p->d_O, p->d_C64,
-        static_cast<double*>(p->d_C));
-  else
-    prepare_kernel<float><<<1, kSetupThreads, 0, s>>>(p->n, p->enc, p->d_ops, p->n_ops,
+        static_cast<double*>(p->d_C), sm != 0);
+  } else {
+    if (opt_in_smem(&prepare_kernel<float>, sm)) sm = 0;
+    prepare_kernel<float><<<1, kSetupThreads, sm, s>>>(p->n, p->enc, p->d_ops, p->n_ops,
         static_cast<const float*>(theta), p->d_consts, p->d_V, p->d_O, p->d_C64,
-        static_cast<float*>(p->d_C));
+        static_cast<float*>(p->d_C), sm != 0);
+  }
   QCP_CUDA(cudaGetLastError());
   p->prepared = true;
   return 0;
@@ -597,14 +687,18 @@ int qcp_layer_forward(qcp_plan_t* p, const void* z, long long B, void* q, void* 
 }
 
 static int run_theta_grad(qcp_plan* p, const void* theta, void* gtheta, cudaStream_t s) {
-  if (p->dtype == QCP_F64)
-    theta_grad_kernel<double><<<1, kSetupThreads, 0, s>>>(p->n, p->enc, p->d_ops, p->n_ops,
+  size_t sm = setup_smem_bytes(p, true);
+  if (p->dtype == QCP_F64) {
+    if (opt_in_smem(&theta_grad_kernel<double>, sm)) sm = 0;
+    theta_grad_kernel<double><<<1, kSetupThreads, sm, s>>>(p->n, p->enc, p->d_ops, p->n_ops,
         static_cast<const double*>(theta), p->n_theta, p->d_consts, p->d_Cbar, p->d_V, p->d_O,
-        p->d_Lam, static_cast<double*>(gtheta));
-  else
-    theta_grad_kernel<float><<<1, kSetupThreads, 0, s>>>(p->n, p->enc, p->d_ops, p->n_ops,
+        p->d_Lam, static_cast<double*>(gtheta), sm != 0);
+  } else {
+    if (opt_in_smem(&theta_grad_kernel<float>, sm)) sm = 0;
+    theta_grad_kernel<float><<<1, kSetupThreads, sm, s>>>(p->n, p->enc, p->d_ops, p->n_ops,
         static_cast<const float*>(theta), p->n_theta, p->d_consts, p->d_Cbar, p->d_V, p->d_O,
-        p->d_Lam, static_cast<float*>(gtheta));
+        p->d_Lam, static_cast<float*>(gtheta), sm != 0);
+  }
   QCP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -628,11 +722,11 @@ int qcp_layer_backward(qcp_plan_t* p, const void* theta, const void* z, const vo
   int rc = p->dtype == QCP_F64 ? launch_layer_backward<double>(p->n, p->enc, a, grid, s)
                                : launch_layer_backward<float>(p->n, p->enc, a, grid, s);
   if (rc) return rc;
-  const int rb = (nacc + 127) / 128;
+  const int rb = (nacc + 31) / 32;
   if (p->dtype == QCP_F64)
-    reduce_layer_kernel<double><<<rb, 128, 0, s>>>(static_cast<const double*>(p->d_partials), p->d_Cbar, grid, nacc, p->n, p->enc);
+    reduce_layer_kernel<double><<<rb, 32 * kReduceSlices, 0, s>>>(static_cast<const double*>(p->d_partials), p->d_Cbar, grid, nacc, p->n, p->enc);
   else
-    reduce_layer_kernel<float><<<rb, 128, 0, s>>>(static_cast<const float*>(p->d_partials), p->d_Cbar, grid, nacc, p->n, p->enc);
+    reduce_layer_kernel<float><<<rb, 32 * kReduceSlices, 0, s>>>(static_cast<const float*>(p->d_partials), p->d_Cbar, grid, nacc, p->n, p->enc);
   QCP_CUDA(cudaGetLastError());
   return run_theta_grad(p, theta, grad_theta, s);
 }
@@ -736,9 +830,9 @@ int qcp_solver_backward(qcp_plan_t* p, const qcp_mlp_t* w, const void* theta, co
     sc.seg_ptr[1] = p->d_partials; sc.seg_len[1] = 0; sc.seg_grid[1] = 0;
     sc.seg_ptr[2] = p->d_partials; sc.seg_len[2] = 0; sc.seg_grid[2] = 0;
   }
-  const int rb = (nacc + 127) / 128;
-  if (f64) reduce_solver_kernel<double><<<rb, 128, 0, s>>>(sc);
-  else reduce_solver_kernel<float><<<rb, 128, 0, s>>>(sc);
+  const int rb = (nacc + 31) / 32;
+  if (f64) reduce_solver_kernel<double><<<rb, 32 * kReduceSlices, 0, s>>>(sc);
+  else reduce_solver_kernel<float><<<rb, 32 * kReduceSlices, 0, s>>>(sc);
   QCP_CUDA(cudaGetLastError());
   return run_theta_grad(p, theta, grad_theta, s);
 }

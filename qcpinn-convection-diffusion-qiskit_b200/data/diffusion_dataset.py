@@ -23,10 +23,38 @@ class Sampler:
         self.device = device
 
     def sample(self, N):
-        lo, hi = self.coords[0:1, :], self.coords[1:2, :]
         pts = torch.rand(N, self.dim, device=self.device)
+        fused = self._fused(pts)
+        if fused is not None:
+            return fused
+        lo, hi = self.coords[0:1, :], self.coords[1:2, :]
         pts = lo + (hi - lo) * pts
         return pts, self.func(pts.to(self.device))
+
+    def _fused(self, rnd):
+        """CUDA fast path for the two analytic targets of this module: one kernel maps the random
+        numbers into the box and evaluates ``u`` / ``r`` (instead of ~15 / ~30 torch launches)."""
+        kind = _FUSED_KIND.get(self.func)
+        if kind is None or not rnd.is_cuda or self.dim != 3 or rnd.dtype != torch.float32:
+            return None
+        import ctypes
+
+        from .. import _lib
+
+        if getattr(self, "_lo_hi", None) is None:
+            box = self.coords.detach().to("cpu", torch.float32).reshape(-1).tolist()
+            self._lo_hi = (ctypes.c_float * 6)(*box)
+        lib = _lib.require_cuda()
+        X = torch.empty_like(rnd)
+        y = torch.empty((rnd.shape[0], 1), dtype=torch.float32, device=rnd.device)
+        with torch.cuda.device(rnd.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(rnd.device).cuda_stream)
+            rc = lib.qcp_sample_targets(
+                ctypes.c_void_p(rnd.data_ptr()), rnd.shape[0], self._lo_hi, kind,
+                default_D, default_v_x, default_v_y,
+                ctypes.c_void_p(X.data_ptr()), ctypes.c_void_p(y.data_ptr()), stream)
+        _lib.check(rc, "qcp_sample_targets")
+        return X, y
 
 
 def _pulse(txy):
@@ -67,6 +95,9 @@ def r(txy, Diffusion=default_D, v_x=default_v_x, v_y=default_v_y):
     dx, dy, val = _pulse(txy)
     lap = (40000 * dx ** 2 - 400) * val + (40000 * dy ** 2 - 400) * val
     return -val + v_x * (-200 * dx * val) + v_y * (-200 * dy * val) - Diffusion * lap
+
+
+_FUSED_KIND = {u: 0, r: 1}
 
 
 def _box(lo, hi, device):

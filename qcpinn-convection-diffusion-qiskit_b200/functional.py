@@ -64,6 +64,8 @@ class Plan:
         self.n_theta = program.n_theta
         self._handle = ctypes.c_void_p()
         self._key = None
+        self._wkey = None
+        self._wcache = None
         ops = np.ascontiguousarray(program.ops, dtype=np.int32)
         consts = np.ascontiguousarray(program.consts, dtype=np.complex128).view(np.float64)
         with torch.cuda.device(self.device):
@@ -95,6 +97,28 @@ class Plan:
 
     def invalidate(self):
         self._key = None
+        self._wkey = None
+
+    def typed_weights(self, theta, mlp):
+        """(theta, 8 MLP tensors) in the plan dtype, contiguous.  When a cast is needed (float32
+        parameters, float64 plan) all nine tensors are packed and converted with two kernels and
+        the result is cached until any of them changes (3 model calls per step share it)."""
+        tensors = [theta] + list(mlp)
+        if all(t.dtype == self.dtype and t.is_contiguous() for t in tensors):
+            return theta.detach().reshape(-1), [t.detach() for t in mlp]
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        if getattr(self, "_wkey", None) != key:
+            for t in tensors:
+                if t.device != self.device:
+                    raise RuntimeError(f"tensor on {t.device}, plan on {self.device}")
+            flat = torch.cat([t.detach().reshape(-1) for t in tensors]).to(self.dtype)
+            views, off = [], 0
+            for t in tensors:
+                views.append(flat[off:off + t.numel()].view(t.shape))
+                off += t.numel()
+            self._wcache = (views[0].reshape(-1), views[1:])
+            self._wkey = key
+        return self._wcache
 
     def prepare(self, theta: torch.Tensor, key=None) -> None:
         """theta (dtype T, n_theta) -> feature matrix C.  ``key`` lets callers skip repeats."""
@@ -235,8 +259,7 @@ class _SolverFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan: Plan, key, mode, coeffs, X, theta, *mlp):
         Xt = plan._t(X)
-        tt = plan._t(theta).reshape(-1)
-        mt = [plan._t(w) for w in mlp]
+        tt, mt = plan.typed_weights(theta, mlp)
         plan.prepare(tt, key)
         needs_grad = any(ctx.needs_input_grad[4:])
         save = plan.workspace(Xt.shape[0], mode) if (needs_grad and SAVE_JETS and Xt.shape[0]) else None
@@ -265,6 +288,14 @@ class _SolverFn(torch.autograd.Function):
         ctx.save = None   # consumed (overwritten with cotangents)
         dt = ctx.in_dtypes
         gX = gx.to(dt[0]) if gx is not None else None
+        if len(set(dt[1:])) == 1 and dt[1] != plan.dtype:
+            # one cast kernel for the flat gradient buffer instead of nine
+            flat = views[0]._base.to(dt[1])
+            off, cast = 0, []
+            for v in views:
+                cast.append(flat[off:off + v.numel()].view(v.shape))
+                off += v.numel()
+            views = cast
         gtheta = views[8].to(dt[1]).view(ctx.theta_shape) if ctx.needs_input_grad[5] else None
         gm = [v.to(d) if need else None
               for v, d, need in zip(views[:8], dt[2:], ctx.needs_input_grad[6:])]

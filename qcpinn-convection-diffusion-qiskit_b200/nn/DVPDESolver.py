@@ -78,8 +78,16 @@ class DVPDESolver(nn.Module):
         # kernels need every parameter on the model's device.
         self.quantum_layer = DVQuantumLayer(self.args).to(self.device)
 
-        self.optimizer = torch.optim.Adam(
-            [p for p in self.parameters() if p.requires_grad], lr=self.args["lr"])
+        # On a CUDA device Adam is built capturable with a device-resident learning rate, so a
+        # whole train step can be replayed as one CUDA graph (trainer.diffusion_train.TrainStep)
+        # and ReduceLROnPlateau's updates still reach the captured kernels.
+        on_cuda = torch.device(self.device).type == "cuda" if self.device is not None else False
+        trainable = [p for p in self.parameters() if p.requires_grad]
+        if on_cuda:
+            lr0 = torch.tensor(float(self.args["lr"]), dtype=torch.float32, device=self.device)
+            self.optimizer = torch.optim.Adam(trainable, lr=lr0, capturable=True)
+        else:
+            self.optimizer = torch.optim.Adam(trainable, lr=self.args["lr"])
         self.scheduler = _RankConsistentPlateau(
             self.optimizer, mode="min", factor=0.9, patience=1000)
         self.loss_fn = torch.nn.MSELoss()

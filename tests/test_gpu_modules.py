@@ -242,3 +242,23 @@ def test_abi_error_reporting():
         plan.prepare(torch.zeros(5, dtype=torch.float64, device=DEV))
     with pytest.raises(RuntimeError, match="plan on"):
         plan._t(torch.zeros(3))
+
+
+def test_fused_sampler_matches_torch_expressions():
+    """Sampler.sample's CUDA fast path (one kernel) vs the module's torch expressions for u / r."""
+    from qcpinn_b200.data.diffusion_dataset import Sampler, r, training_boxes, u
+
+    boxes = training_boxes(DEV)
+    for func, box in ((u, "ics"), (u, "bc1"), (r, "dom")):
+        torch.manual_seed(3)
+        X, y = Sampler(3, boxes[box], func, device=DEV).sample(4097)
+        torch.manual_seed(3)
+        rnd = torch.rand(4097, 3, device=DEV)
+        lo, hi = boxes[box][0:1], boxes[box][1:2]
+        Xt = lo + (hi - lo) * rnd
+        assert torch.equal(X, Xt)
+        assert y.shape == (4097, 1)
+        assert rel_err(y, func(Xt.double())) < 1e-5     # float32 evaluation of exp(-100 d^2)
+    # generic callables still take the torch path
+    X, y = Sampler(3, boxes["dom"], lambda p: p.sum(1, keepdim=True), device=DEV).sample(5)
+    assert torch.allclose(y, X.sum(1, keepdim=True))
