@@ -19,7 +19,8 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 BUILD_DIR = PKG_DIR / "csrc" / "build"
 LIB_PATH = PKG_DIR / "libqcpinn_b200.so"
-SOURCES = ["qcp_plan.cu", "qcp_point_f32.cu", "qcp_point_f64.cu", "qcp_data.cu", "qcp_state.cu"]
+SOURCES = ["qcp_plan.cu", "qcp_point_f32.cu", "qcp_point_f64.cu", "qcp_data.cu", "qcp_state.cu",
+           "qcp_mlp.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH_FLAGS + [
     "-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr",

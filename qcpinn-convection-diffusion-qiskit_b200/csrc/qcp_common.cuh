@@ -71,6 +71,11 @@ __host__ __device__ constexpr int num_features(int n, int enc) {
   return enc == QCP_ENC_AMPLITUDE ? n * (n + 1) / 2 : ipow3(n);
 }
 
+// accumulator segment sizes (also the staging / reduce order, see reduce_solver_kernel)
+__host__ __device__ constexpr int nacc_post(int n, int H) { return 1 + H * (n + 2); }
+__host__ __device__ constexpr int nacc_contract(int n, int enc) { return num_features(n, enc) * n; }
+__host__ __device__ constexpr int nacc_pre(int n, int H) { return n + H * (4 + n); }
+
 // Accumulator ("kernel order") layout of the backward kernel, see qcp_point.cuh.
 __host__ __device__ constexpr int nacc_solver(int n, int enc, int H) {
   return 1 + H * (n + 2) + num_features(n, enc) * n + n + H * (4 + n);

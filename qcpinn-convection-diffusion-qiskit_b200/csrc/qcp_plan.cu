@@ -14,6 +14,7 @@
 #include <new>
 
 #include "qcp_common.cuh"
+#include "qcp_state.cuh"
 
 namespace qcp {
 
@@ -468,6 +469,20 @@ theta_grad_kernel(int n, int enc, const GateOp* ops, int n_ops, const T* theta, 
   }
 }
 
+// [B][n] <-> component-major [n][B] (stand-alone DVQuantumLayer on engine L)
+template <typename T>
+__global__ void transpose_bn_kernel(const T* __restrict__ in, T* __restrict__ out, long long B, int n,
+                                    int to_component_major) {
+  const long long total = B * n;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long p = e / n;
+    const int j = (int)(e % n);
+    if (to_component_major) out[(size_t)j * B + p] = in[e];
+    else out[e] = in[(size_t)j * B + p];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // FMA-pipe micro-benchmark (roofline denominator)
 // ---------------------------------------------------------------------------------------------
@@ -507,6 +522,15 @@ struct qcp_plan {
   int grid_cache[2];   // persistent grid of the backward kernel per mode (0: value, 1: residual)
   SplitGrids split_cache[2];
   bool split_ready[2];
+  // engine L (n > kMaxQubitsFused): per-sample statevector path
+  bool engine_l;
+  void* d_theta;            // copy of the angles taken by qcp_prepare()
+  void* d_ws;               // internal saved-jet workspace (when the caller gives none)
+  size_t ws_elems;
+  void* d_slab;             // per-CTA statevector storage in global memory
+  size_t slab_bytes;
+  double* d_theta_partials;
+  size_t theta_partials_elems;
   bool prepared;
 };
 
@@ -559,8 +583,8 @@ int qcp_plan_create(qcp_plan_t** out, int n_qubits, int encoding, int dtype, int
                     int n_theta) {
   if (!out) { set_error("qcp_plan_create: out is NULL"); return 1; }
   *out = nullptr;
-  if (n_qubits < 2 || n_qubits > kMaxQubitsFused) {
-    set_error("qcp_plan_create: fused engine supports 2..%d qubits, got %d", kMaxQubitsFused, n_qubits);
+  if (n_qubits < 2 || n_qubits > kMaxQubitsSv) {
+    set_error("qcp_plan_create: 2..%d qubits are supported, got %d", kMaxQubitsSv, n_qubits);
     return 1;
   }
   if (encoding != QCP_ENC_ANGLE && encoding != QCP_ENC_AMPLITUDE) {
@@ -592,7 +616,8 @@ int qcp_plan_create(qcp_plan_t** out, int n_qubits, int encoding, int dtype, int
   memset(p, 0, sizeof(*p));
   p->n = n_qubits; p->enc = encoding; p->dtype = dtype; p->H = hidden;
   p->n_ops = n_ops; p->n_consts = n_consts; p->n_theta = n_theta;
-  p->F = num_features(n_qubits, encoding);
+  p->engine_l = n_qubits > kMaxQubitsFused;
+  p->F = p->engine_l ? 0 : num_features(n_qubits, encoding);
   p->M = 1 << n_qubits;
   cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
   const size_t MM = (size_t)p->M * p->M;
@@ -600,12 +625,16 @@ int qcp_plan_create(qcp_plan_t** out, int n_qubits, int encoding, int dtype, int
   auto alloc = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes ? bytes : 16); };
   alloc((void**)&p->d_ops, sizeof(GateOp) * n_ops);
   alloc((void**)&p->d_consts, sizeof(double2) * 16 * n_consts);
-  alloc((void**)&p->d_V, sizeof(double2) * MM);
-  alloc((void**)&p->d_O, sizeof(double2) * MM * n_qubits);
-  alloc((void**)&p->d_Lam, sizeof(double2) * MM);
-  alloc((void**)&p->d_C64, sizeof(double) * p->F * kCStride);
-  alloc((void**)&p->d_C, elem_size(dtype) * p->F * kCStride);
-  alloc((void**)&p->d_Cbar, sizeof(double) * p->F * n_qubits);
+  if (p->engine_l) {
+    alloc((void**)&p->d_theta, elem_size(dtype) * n_theta);
+  } else {
+    alloc((void**)&p->d_V, sizeof(double2) * MM);
+    alloc((void**)&p->d_O, sizeof(double2) * MM * n_qubits);
+    alloc((void**)&p->d_Lam, sizeof(double2) * MM);
+    alloc((void**)&p->d_C64, sizeof(double) * p->F * kCStride);
+    alloc((void**)&p->d_C, elem_size(dtype) * p->F * kCStride);
+    alloc((void**)&p->d_Cbar, sizeof(double) * p->F * n_qubits);
+  }
   if (e == cudaSuccess && n_ops) e = cudaMemcpy(p->d_ops, ops, sizeof(GateOp) * n_ops, cudaMemcpyHostToDevice);
   if (e == cudaSuccess && n_consts)
     e = cudaMemcpy(p->d_consts, consts, sizeof(double2) * 16 * n_consts, cudaMemcpyHostToDevice);
@@ -622,6 +651,7 @@ int qcp_plan_destroy(qcp_plan_t* p) {
   if (!p) return 0;
   cudaFree(p->d_ops); cudaFree(p->d_consts); cudaFree(p->d_V); cudaFree(p->d_O); cudaFree(p->d_Lam);
   cudaFree(p->d_C64); cudaFree(p->d_C); cudaFree(p->d_Cbar); cudaFree(p->d_partials);
+  cudaFree(p->d_theta); cudaFree(p->d_ws); cudaFree(p->d_slab); cudaFree(p->d_theta_partials);
   delete p;
   return 0;
 }
@@ -631,6 +661,14 @@ int qcp_plan_num_features(const qcp_plan_t* p) { return p ? p->F : -1; }
 int qcp_prepare(qcp_plan_t* p, const void* theta, void* stream) {
   if (!p || (!theta && p->n_theta > 0)) { set_error("qcp_prepare: NULL argument"); return 1; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p->engine_l) {
+    // engine L applies the gates per sample: just keep a stream-ordered copy of the angles
+    if (p->n_theta > 0)
+      QCP_CUDA(cudaMemcpyAsync(p->d_theta, theta, elem_size(p->dtype) * p->n_theta,
+                               cudaMemcpyDeviceToDevice, s));
+    p->prepared = true;
+    return 0;
+  }
   size_t sm = setup_smem_bytes(p, false);
   if (p->dtype == QCP_F64) {
     if (opt_in_smem(&prepare_kernel<double>, sm)) sm = 0;
@@ -651,6 +689,7 @@ int qcp_prepare(qcp_plan_t* p, const void* theta, void* stream) {
 int qcp_feature_matrix(qcp_plan_t* p, double* out_host, void* stream) {
   if (!p || !out_host) { set_error("qcp_feature_matrix: NULL argument"); return 1; }
   if (!p->prepared) { set_error("qcp_feature_matrix: qcp_prepare() has not run"); return 1; }
+  if (p->engine_l) { set_error("qcp_feature_matrix: no feature matrix for n > %d (statevector engine)", kMaxQubitsFused); return 1; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t cnt = (size_t)p->F * kCStride;
   double* tmp = new double[cnt];
@@ -667,6 +706,79 @@ int qcp_feature_matrix(qcp_plan_t* p, double* out_host, void* stream) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// engine L plumbing
+// ---------------------------------------------------------------------------------------------
+static int ensure_buffer(void** ptr, size_t* have, size_t want_bytes) {
+  if (want_bytes <= *have) return 0;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr;
+  *have = 0;
+  QCP_CUDA(cudaMalloc(ptr, want_bytes));
+  *have = want_bytes;
+  return 0;
+}
+
+// grid + state placement of the statevector kernels for S streams
+static int sv_configure(qcp_plan* p, int S, long long B, SvLaunch& L) {
+  const size_t fixed = sv_fixed_smem_rt(p->dtype, p->n, S, p->n_ops, p->n_theta);
+  const size_t state = sv_state_bytes_rt(p->dtype, p->n, S);
+  const size_t smem_cap = 200 * 1024;
+  int grid;
+  if (fixed + state <= smem_cap) {
+    int per_sm = (int)((220 * 1024) / (fixed + state));
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    grid = p->num_sms * per_sm;
+    L.slab = nullptr;
+  } else {
+    grid = p->num_sms * 2;
+    if ((long long)grid > B) grid = (int)B;
+    size_t have = p->slab_bytes;
+    if (ensure_buffer(&p->d_slab, &have, state * (size_t)grid)) return 1;
+    p->slab_bytes = have;
+    L.slab = p->d_slab;
+  }
+  if ((long long)grid > B) grid = (int)B;
+  if (grid < 1) grid = 1;
+  L.grid = grid;
+  size_t have = p->theta_partials_elems * sizeof(double);
+  if (ensure_buffer((void**)&p->d_theta_partials, &have, sizeof(double) * (size_t)grid * (p->n_theta > 0 ? p->n_theta : 1)))
+    return 1;
+  p->theta_partials_elems = have / sizeof(double);
+  L.n = p->n; L.enc = p->enc; L.n_ops = p->n_ops; L.n_theta = p->n_theta;
+  L.ops = p->d_ops; L.consts = p->d_consts; L.theta = p->d_theta; L.B = B;
+  L.theta_partials = p->d_theta_partials;
+  return 0;
+}
+
+static void* internal_ws(qcp_plan* p, long long B, int S) {
+  const size_t want = elem_size(p->dtype) * 2 * (size_t)p->n * S * (size_t)B;
+  size_t have = p->ws_elems;
+  if (ensure_buffer(&p->d_ws, &have, want)) return nullptr;
+  p->ws_elems = have;
+  return p->d_ws;
+}
+
+static int mlp_grid(const qcp_plan* p, long long B, bool backward) {
+  long long blocks = (B + kThreads - 1) / kThreads;
+  const long long cap = (long long)p->num_sms * (backward ? 2 : 8);
+  if (blocks > cap) blocks = cap;
+  return blocks < 1 ? 1 : (int)blocks;
+}
+
+static void launch_transpose(int dtype, const void* in, void* out, long long B, int n, int to_cm,
+                             cudaStream_t s) {
+  long long blocks = (B * n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (dtype == QCP_F64)
+    transpose_bn_kernel<double><<<(int)blocks, 256, 0, s>>>(static_cast<const double*>(in),
+                                                            static_cast<double*>(out), B, n, to_cm);
+  else
+    transpose_bn_kernel<float><<<(int)blocks, 256, 0, s>>>(static_cast<const float*>(in),
+                                                           static_cast<float*>(out), B, n, to_cm);
+}
+
 static int forward_grid(const qcp_plan* p, long long B) {
   long long blocks = (B + kThreads - 1) / kThreads;
   const long long cap = (long long)p->num_sms * 8;
@@ -679,9 +791,24 @@ int qcp_layer_forward(qcp_plan_t* p, const void* z, long long B, void* q, void* 
   if (!p || (B > 0 && (!z || !q))) { set_error("qcp_layer_forward: NULL argument"); return 1; }
   if (!p->prepared) { set_error("qcp_layer_forward: qcp_prepare() has not run"); return 1; }
   if (B <= 0) return 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p->engine_l) {
+    void* ws = internal_ws(p, B, 1);
+    if (!ws) return 1;
+    const size_t es = elem_size(p->dtype);
+    launch_transpose(p->dtype, z, ws, B, p->n, 1, s);
+    QCP_CUDA(cudaGetLastError());
+    SvLaunch L{};
+    if (sv_configure(p, 1, B, L)) return 1;
+    L.ws = ws;
+    if (sv_run(p->dtype, 1, false, L, s)) return 1;
+    // slot 1 is q in [n][B] order == the (n, B) output orientation
+    QCP_CUDA(cudaMemcpyAsync(q, static_cast<char*>(ws) + es * (size_t)p->n * B, es * (size_t)p->n * B,
+                             cudaMemcpyDeviceToDevice, s));
+    return 0;
+  }
   LayerArgs a{};
   a.z = z; a.C = p->d_C; a.q = q; a.B = B;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   return p->dtype == QCP_F64 ? launch_layer_forward<double>(p->n, p->enc, a, forward_grid(p, B), s)
                              : launch_layer_forward<float>(p->n, p->enc, a, forward_grid(p, B), s);
 }
@@ -711,6 +838,24 @@ int qcp_layer_backward(qcp_plan_t* p, const void* theta, const void* z, const vo
   const int nacc = p->F * p->n;
   if (B <= 0) {
     QCP_CUDA(cudaMemsetAsync(grad_theta, 0, elem_size(p->dtype) * p->n_theta, s));
+    return 0;
+  }
+  if (p->engine_l) {
+    void* ws = internal_ws(p, B, 1);
+    if (!ws) return 1;
+    const size_t es = elem_size(p->dtype);
+    launch_transpose(p->dtype, z, ws, B, p->n, 1, s);
+    QCP_CUDA(cudaGetLastError());
+    QCP_CUDA(cudaMemcpyAsync(static_cast<char*>(ws) + es * (size_t)p->n * B, grad_q, es * (size_t)p->n * B,
+                             cudaMemcpyDeviceToDevice, s));
+    SvLaunch L{};
+    if (sv_configure(p, 1, B, L)) return 1;
+    L.ws = ws; L.grad_theta = grad_theta;
+    if (sv_run(p->dtype, 1, true, L, s)) return 1;
+    if (grad_z) {
+      launch_transpose(p->dtype, ws, grad_z, B, p->n, 0, s);
+      QCP_CUDA(cudaGetLastError());
+    }
     return 0;
   }
   long long blocks = (B + kThreads - 1) / kThreads;
@@ -761,6 +906,19 @@ int qcp_solver_forward(qcp_plan_t* p, const qcp_mlp_t* w, const void* X, long lo
   fill_solver_args(a, p, w, X, B, coeffs);
   a.u = u; a.r = r; a.streams = streams; a.ws = save;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p->engine_l) {
+    // pre MLP -> per-sample statevector sweep -> post MLP, exchanging jets through the workspace
+    if (!a.ws) a.ws = internal_ws(p, B, mode);
+    if (!a.ws) return 1;
+    MlpLaunch M{};
+    M.n = p->n; M.H = p->H; M.grid = mlp_grid(p, B, false); M.args = a;
+    if (mlp_pre_forward(p->dtype, mode, M, s)) return 1;
+    SvLaunch L{};
+    if (sv_configure(p, mode, B, L)) return 1;
+    L.ws = a.ws;
+    if (sv_run(p->dtype, mode, false, L, s)) return 1;
+    return mlp_post_forward(p->dtype, mode, M, s);
+  }
   const int grid = forward_grid(p, B);
   return p->dtype == QCP_F64 ? launch_solver_forward<double>(p->n, p->enc, mode, a, grid, s)
                              : launch_solver_forward<float>(p->n, p->enc, mode, a, grid, s);
@@ -774,7 +932,7 @@ int qcp_solver_backward(qcp_plan_t* p, const qcp_mlp_t* w, const void* theta, co
   if (!p->prepared) { set_error("qcp_solver_backward: qcp_prepare() has not run"); return 1; }
   if (check_mode(mode, coeffs, "qcp_solver_backward")) return 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int nacc = nacc_solver(p->n, p->enc, p->H);
+  const int nacc = p->engine_l ? 0 : nacc_solver(p->n, p->enc, p->H);
   const int mi = mode == QCP_MODE_RESIDUAL ? 1 : 0;
   const bool f64 = p->dtype == QCP_F64;
   SolverArgs a{};
@@ -786,6 +944,48 @@ int qcp_solver_backward(qcp_plan_t* p, const qcp_mlp_t* w, const void* theta, co
   sc.Cbar = p->d_Cbar; sc.n = p->n; sc.H = p->H; sc.F = p->F; sc.nacc = nacc; sc.enc = p->enc;
   const size_t es = elem_size(p->dtype);
   const long long want_blocks = B > 0 ? (B + kThreads - 1) / kThreads : 1;
+
+  if (p->engine_l) {
+    const int n0 = nacc_post(p->n, p->H), n2 = nacc_pre(p->n, p->H);
+    const int gb = mlp_grid(p, B > 0 ? B : 1, true);
+    if (ensure_partials(p, (size_t)gb * (n0 + n2))) return 1;
+    char* base = static_cast<char*>(p->d_partials);
+    void* p0 = base; void* p2 = base + es * (size_t)gb * n0;
+    if (B > 0) {
+      MlpLaunch M{};
+      M.n = p->n; M.H = p->H; M.args = a;
+      SvLaunch L{};
+      if (sv_configure(p, mode, B, L)) return 1;
+      if (!M.args.ws) {
+        // no saved jets: rebuild them (pre MLP + statevector forward) in the internal workspace
+        M.args.ws = internal_ws(p, B, mode);
+        if (!M.args.ws) return 1;
+        M.grid = mlp_grid(p, B, false);
+        if (mlp_pre_forward(p->dtype, mode, M, s)) return 1;
+        L.ws = M.args.ws;
+        if (sv_run(p->dtype, mode, false, L, s)) return 1;
+      }
+      L.ws = M.args.ws; L.grad_theta = grad_theta;
+      M.grid = gb;
+      M.args.partials = p0;
+      if (mlp_post_backward(p->dtype, mode, M, s)) return 1;
+      if (sv_run(p->dtype, mode, true, L, s)) return 1;
+      M.args.partials = p2;
+      if (mlp_pre_backward(p->dtype, mode, M, s)) return 1;
+    } else {
+      QCP_CUDA(cudaMemsetAsync(p->d_partials, 0, es * (size_t)gb * (n0 + n2), s));
+      QCP_CUDA(cudaMemsetAsync(grad_theta, 0, es * p->n_theta, s));
+    }
+    sc.nacc = n0 + n2; sc.F = 0;
+    sc.seg_ptr[0] = p0; sc.seg_len[0] = n0; sc.seg_grid[0] = gb;
+    sc.seg_ptr[1] = p0; sc.seg_len[1] = 0; sc.seg_grid[1] = 0;
+    sc.seg_ptr[2] = p2; sc.seg_len[2] = n2; sc.seg_grid[2] = gb;
+    const int rbl = (sc.nacc + 31) / 32;
+    if (f64) reduce_solver_kernel<double><<<rbl, 32 * kReduceSlices, 0, s>>>(sc);
+    else reduce_solver_kernel<float><<<rbl, 32 * kReduceSlices, 0, s>>>(sc);
+    QCP_CUDA(cudaGetLastError());
+    return 0;
+  }
 
   if (save && B > 0) {
     // split path: three kernels over the jets saved by the forward

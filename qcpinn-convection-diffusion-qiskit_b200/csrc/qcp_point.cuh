@@ -95,11 +95,6 @@ __host__ __device__ constexpr int c_elems(int n, int enc) {
              : ipow3((n + 1) / 2) * n * ((ipow3(n - (n + 1) / 2) + 3) & ~3);
 }
 
-// accumulator segment sizes (also the staging / reduce order, see reduce_solver_kernel)
-__host__ __device__ constexpr int nacc_post(int n, int H) { return 1 + H * (n + 2); }
-__host__ __device__ constexpr int nacc_contract(int n, int enc) { return num_features(n, enc) * n; }
-__host__ __device__ constexpr int nacc_pre(int n, int H) { return n + H * (4 + n); }
-
 template <typename T, int NQ, int ENC>
 __device__ __forceinline__ void load_C(T* sC, const T* Cg) {
   if constexpr (ENC == QCP_ENC_ANGLE) {

@@ -1,0 +1,38 @@
+// qcpinn_b200 -- host-side interface of engine L (qcp_state.cu, qcp_mlp.cu); internal header.
+#pragma once
+
+#include "qcp_common.cuh"
+
+namespace qcp {
+
+constexpr int kMaxQubitsSv = 16;      // largest statevector engine L handles (2^16 amplitudes)
+
+struct SvLaunch {
+  int n, enc, n_ops, n_theta, grid;
+  const GateOp* ops;
+  const double2* consts;
+  const void* theta;
+  void* ws;                 // saved-jet workspace [2][n*S][B]
+  long long B;
+  void* slab;               // per-CTA state storage in global memory, or null => shared memory
+  double* theta_partials;   // [grid][n_theta]   (backward)
+  void* grad_theta;         // [n_theta]          (backward)
+};
+
+size_t sv_state_bytes_rt(int dtype, int n, int S);
+size_t sv_fixed_smem_rt(int dtype, int n, int S, int n_ops, int n_theta);
+int sv_run(int dtype, int S, bool backward, const SvLaunch& L, cudaStream_t s);
+
+// generic-n MLP stages (one thread per point, jets through the workspace)
+struct MlpLaunch {
+  int n, H, grid;
+  SolverArgs args;          // X, weights, u/r/streams, gu/gr, gX, ws, B, pde; partials per stage
+};
+size_t mlp_smem_bytes(int dtype, int n, int H, int nacc);
+int mlp_pre_forward(int dtype, int S, const MlpLaunch& L, cudaStream_t s);
+int mlp_post_forward(int dtype, int S, const MlpLaunch& L, cudaStream_t s);
+int mlp_post_backward(int dtype, int S, const MlpLaunch& L, cudaStream_t s);
+int mlp_pre_backward(int dtype, int S, const MlpLaunch& L, cudaStream_t s);
+int mlp_backward_grid(int dtype, int S, int n, int H, int num_sms);
+
+}  // namespace qcp

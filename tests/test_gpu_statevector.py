@@ -1,0 +1,156 @@
+"""GPU parity of the per-sample statevector engine (n >= 5 qubits: BASELINE configs 3 and 4 shapes)
+against the CPU oracle: stand-alone layer, solver value mode, Taylor streams, residual and every
+gradient.  Bars as in test_gpu_parity.py (1e-10 float64, 1e-5 float32)."""
+
+import pytest
+import torch
+
+import qcpinn_b200 as qb
+from helpers import F, TOL, device_weights, make_case, mlp_list, points, rel_err
+from oracle import solver as osolver
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+
+CASES = [
+    # ansatz, n, layers, encoding, haar_seed
+    ("cascade", 5, 1, "angle", 1),
+    ("layered", 5, 2, "angle", None),
+    ("alternate", 5, 1, "angle", 1),
+    ("farhi", 6, 1, "angle", None),
+    ("sim_circ_15", 6, 2, "angle", 1),
+    ("cross_mesh", 5, 1, "angle", None),
+    ("cascade", 6, 1, "amplitude", 1),
+    ("cross_mesh", 5, 2, "amplitude", None),
+]
+DTYPES = [torch.float64, torch.float32]
+
+
+def _ids(c):
+    return "-".join(map(str, c))
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f64", "f32"])
+@pytest.mark.parametrize("case", CASES, ids=_ids)
+def test_layer_forward_backward(case, dtype):
+    ansatz, n, layers, enc, seed = case
+    w, oracle, prog = make_case(ansatz, n, layers, enc, seed)
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn(9, n, generator=g, dtype=torch.float64) + (0.8 if enc == "amplitude" else 0.0)
+    cot = torch.randn(n, 9, generator=g, dtype=torch.float64)
+    zo = z.clone().requires_grad_(True)
+    qo = oracle.quantum(zo)
+    (qo * cot).sum().backward()
+
+    plan = F.Plan(prog, F.encoding_code(enc), dtype, 50, DEV)
+    zd = z.to(DEV, dtype).requires_grad_(True)
+    th = w["theta"].to(DEV, dtype).requires_grad_(True)
+    qd = F.layer_apply(plan, zd, th)
+    (qd * cot.to(DEV, dtype)).sum().backward()
+    tol = TOL[dtype]
+    assert rel_err(qd, qo) < tol
+    assert rel_err(zd.grad, zo.grad) < tol
+    assert rel_err(th.grad, oracle.w["theta"].grad) < tol
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f64", "f32"])
+@pytest.mark.parametrize("case", CASES, ids=_ids)
+def test_residual_streams_and_gradients(case, dtype):
+    ansatz, n, layers, enc, seed = case
+    w, oracle, prog = make_case(ansatz, n, layers, enc, seed)
+    X = points(7, seed=11)
+    g = torch.Generator().manual_seed(13)
+    cu = torch.randn(7, 1, generator=g, dtype=torch.float64)
+    cr = torch.randn(7, 1, generator=g, dtype=torch.float64)
+    coeffs = (1.0, 1.0, 1.0, -0.01, -0.01)
+    streams_o = osolver.diffusion_streams(oracle, X).detach()
+    for v in oracle.w.values():
+        v.grad = None
+    uo, ro = osolver.diffusion_operator(
+        oracle, X[:, 0:1].clone(), X[:, 1:2].clone(), X[:, 2:3].clone())
+    ((uo * cu).sum() + (ro * cr).sum()).backward()
+
+    plan = F.Plan(prog, F.encoding_code(enc), dtype, 50, DEV)
+    dw = device_weights(w, dtype, requires_grad=True)
+    Xd = X.to(DEV, dtype)
+    _, _, streams_d = F.solver_streams(plan, Xd, dw["theta"], mlp_list(dw), coeffs)
+    ud, rd = F.solver_residual(plan, Xd, dw["theta"], mlp_list(dw), coeffs)
+    ((ud * cu.to(DEV, dtype)).sum() + (rd * cr.to(DEV, dtype)).sum()).backward()
+    tol = TOL[dtype]
+    for c, name in enumerate(["u", "u_t", "u_x", "u_y", "u_xx", "u_yy"]):
+        assert rel_err(streams_d[:, c], streams_o[:, c]) < tol, name
+    assert rel_err(rd, ro) < tol
+    for k in osolver.WEIGHT_NAMES:
+        assert rel_err(dw[k].grad, oracle.w[k].grad) < tol, k
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f64", "f32"])
+def test_value_mode_and_input_gradient(dtype):
+    w, oracle, prog = make_case("cascade", 5, 1, "angle", 1)
+    X = points(11)
+    Xo = X.clone().requires_grad_(True)
+    uo = oracle.forward(Xo)
+    uo.sum().backward()
+    plan = F.Plan(prog, 0, dtype, 50, DEV)
+    dw = device_weights(w, dtype, requires_grad=True)
+    Xd = X.to(DEV, dtype).requires_grad_(True)
+    ud = F.solver_value(plan, Xd, dw["theta"], mlp_list(dw))
+    ud.sum().backward()
+    tol = TOL[dtype]
+    assert rel_err(ud, uo) < tol and rel_err(Xd.grad, Xo.grad) < tol
+    for k in osolver.WEIGHT_NAMES:
+        assert rel_err(dw[k].grad, oracle.w[k].grad) < tol, k
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f64", "f32"])
+def test_config3_shape_cross_mesh_10q(dtype):
+    """BASELINE config 3 shape: cross_mesh, 10 qubits, 2 layers (small batch for the CPU oracle)."""
+    w, oracle, prog = make_case("cross_mesh", 10, 2, "angle", None)
+    X = points(4, seed=2)
+    coeffs = (1.0, 1.0, 1.0, -0.01, -0.01)
+    for v in oracle.w.values():
+        v.grad = None
+    uo, ro = osolver.diffusion_operator(
+        oracle, X[:, 0:1].clone(), X[:, 1:2].clone(), X[:, 2:3].clone())
+    (uo.sum() + ro.sum()).backward()
+    plan = F.Plan(prog, 0, dtype, 50, DEV)
+    dw = device_weights(w, dtype, requires_grad=True)
+    ud, rd = F.solver_residual(plan, X.to(DEV, dtype), dw["theta"], mlp_list(dw), coeffs)
+    (ud.sum() + rd.sum()).backward()
+    tol = TOL[dtype]
+    assert rel_err(ud, uo) < tol and rel_err(rd, ro) < tol
+    for k in osolver.WEIGHT_NAMES:
+        assert rel_err(dw[k].grad, oracle.w[k].grad) < tol, k
+
+
+def test_config4_shape_sim_circ_15_16q():
+    """BASELINE config 4 shape: sim_circ_15, 16 qubits, 2 layers; state in the global workspace."""
+    w, oracle, prog = make_case("sim_circ_15", 16, 2, "angle", None)
+    X = points(2, seed=4)
+    coeffs = (1.0, 1.0, 1.0, -0.01, -0.01)
+    for v in oracle.w.values():
+        v.grad = None
+    uo, ro = osolver.diffusion_operator(
+        oracle, X[:, 0:1].clone(), X[:, 1:2].clone(), X[:, 2:3].clone())
+    (uo.sum() + ro.sum()).backward()
+    plan = F.Plan(prog, 0, torch.float64, 50, DEV)
+    dw = device_weights(w, torch.float64, requires_grad=True)
+    ud, rd = F.solver_residual(plan, X.to(DEV), dw["theta"], mlp_list(dw), coeffs)
+    (ud.sum() + rd.sum()).backward()
+    assert rel_err(ud, uo) < 1e-10 and rel_err(rd, ro) < 1e-10
+    for k in osolver.WEIGHT_NAMES:
+        assert rel_err(dw[k].grad, oracle.w[k].grad) < 1e-10, k
+
+
+def test_solver_module_runs_a_train_step_at_6_qubits(tmp_path):
+    from qcpinn_b200.trainer.diffusion_train import TrainStep
+
+    torch.manual_seed(0)
+    args = {"batch_size": 16, "epochs": 2, "lr": 0.005, "seed": 1, "print_every": 10,
+            "num_qubits": 6, "num_quantum_layers": 1, "classic_network": [3, 50, 1],
+            "q_ansatz": "layered", "problem": "diffusion", "solver": "DV", "cuda_graph": False}
+    model = qb.DVPDESolver(args, qb.Logging(str(tmp_path)), device=DEV)
+    step = TrainStep(model, 24)
+    l0 = step()
+    l1 = step()
+    assert l0 == l0 and l1 == l1 and len(model.loss_history) == 2
