@@ -121,6 +121,17 @@ int qcp_solver_backward(qcp_plan_t* plan, const qcp_mlp_t* weights, const void* 
                         int mode, const double* coeffs, void* save, const qcp_mlp_t* grads,
                         void* grad_theta, void* grad_X, void* stream);
 
+/* The same reverse mode with a DEFERRED reduction (n <= 4): the three model calls of one train step
+ * (reference trainer/diffusion_train.py:40-43) launch their adjoint kernels with _add() and share ONE
+ * partial-sum reduction + ONE theta-gradient kernel in _finish(), which writes the summed gradients.
+ * qcp_solver_backward() == _begin(); _add(); _finish(). */
+int qcp_solver_backward_begin(qcp_plan_t* plan);
+int qcp_solver_backward_add(qcp_plan_t* plan, const qcp_mlp_t* weights, const void* X,
+                            const void* grad_u, const void* grad_r, long long batch, int mode,
+                            const double* coeffs, void* save, void* grad_X, void* stream);
+int qcp_solver_backward_finish(qcp_plan_t* plan, const void* theta, const qcp_mlp_t* grads,
+                               void* grad_theta, void* stream);
+
 /* Sampler.sample() tail fused in one kernel (reference data/diffusion_dataset.py:12-38): maps
  * uniform random numbers rnd [n,3] (float32, from torch.rand) into the box lo_hi = HOST float[6]
  * (lo[3], hi[3]) -> X [n,3], and evaluates the analytic target y [n]: kind 0 = solution u,

@@ -25,6 +25,7 @@ _ALIASES = {
     "data": "data", "data.diffusion_dataset": "data.diffusion_dataset",
     "utils": "utils", "utils.logger": "utils.logger",
     "trainer": "trainer", "trainer.diffusion_train": "trainer.diffusion_train",
+    "trainer.diffusion_eval": "trainer.diffusion_eval",
 }
 
 

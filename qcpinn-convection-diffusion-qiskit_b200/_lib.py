@@ -46,6 +46,12 @@ SIGNATURES = {
     "qcp_solver_backward": (_c_int, [_c_void_p, ctypes.POINTER(QcpMlp), _c_void_p, _c_void_p,
                                      _c_void_p, _c_void_p, _c_ll, _c_int, _dptr, _c_void_p,
                                      ctypes.POINTER(QcpMlp), _c_void_p, _c_void_p, _c_void_p]),
+    "qcp_solver_backward_begin": (_c_int, [_c_void_p]),
+    "qcp_solver_backward_add": (_c_int, [_c_void_p, ctypes.POINTER(QcpMlp), _c_void_p, _c_void_p,
+                                         _c_void_p, _c_ll, _c_int, _dptr, _c_void_p, _c_void_p,
+                                         _c_void_p]),
+    "qcp_solver_backward_finish": (_c_int, [_c_void_p, _c_void_p, ctypes.POINTER(QcpMlp),
+                                            _c_void_p, _c_void_p]),
     "qcp_sample_targets": (_c_int, [_c_void_p, _c_ll, ctypes.POINTER(ctypes.c_float), _c_int,
                                     ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                     _c_void_p, _c_void_p, _c_void_p]),

@@ -267,14 +267,19 @@ __device__ __forceinline__ int cbar_index(int r, int n, int enc) {
   return (a * FB + b) * n + i;
 }
 
+constexpr int kMaxPending = 4;   // backward calls whose partials one reduce launch can sum
+
 struct ScatterArgs {
   void *w1, *b1, *w2, *b2, *w3, *b3, *w4, *b4;
   double* Cbar;   // [F][n]
   int n, H, F, nacc, enc;
-  // up to three consecutive accumulator segments, each with its own partial buffer and grid
-  const void* seg_ptr[3];
+  // three consecutive accumulator segments (post | contraction | pre); every pending backward
+  // call contributes its own partial buffer and grid per segment
+  int calls;
+  const void* seg_ptr[kMaxPending][3];
+  int seg_grid[kMaxPending][3];
+  int fused[kMaxPending];   // 1: the call's partials are one [grid][nacc] array (fused kernel)
   int seg_len[3];
-  int seg_grid[3];
 };
 
 constexpr int kReduceSlices = 8;   // threads cooperating on one accumulator (over the block index)
@@ -289,10 +294,18 @@ reduce_solver_kernel(const ScatterArgs a) {
   if (idx < a.nacc) {
     int seg = 0, local = idx;
     while (seg < 2 && local >= a.seg_len[seg]) { local -= a.seg_len[seg]; ++seg; }
-    const T* partials = static_cast<const T*>(a.seg_ptr[seg]);
     const int len = a.seg_len[seg];
-    for (int g = slice; g < a.seg_grid[seg]; g += kReduceSlices)
-      s += (double)partials[(size_t)g * len + local];
+    for (int c = 0; c < a.calls; ++c) {
+      if (a.fused[c]) {
+        const T* partials = static_cast<const T*>(a.seg_ptr[c][0]);
+        for (int g = slice; g < a.seg_grid[c][0]; g += kReduceSlices)
+          s += (double)partials[(size_t)g * a.nacc + idx];
+      } else {
+        const T* partials = static_cast<const T*>(a.seg_ptr[c][seg]);
+        for (int g = slice; g < a.seg_grid[c][seg]; g += kReduceSlices)
+          s += (double)partials[(size_t)g * len + local];
+      }
+    }
   }
   part[slice][lane] = s;
   __syncthreads();
@@ -523,6 +536,12 @@ struct qcp_plan {
   SplitGrids split_cache[2];
   bool split_ready[2];
   // engine L (n > kMaxQubitsFused): per-sample statevector path
+  // deferred reduction: kernels of up to kMaxPending backward calls, one reduce + theta_grad
+  int pending;
+  size_t pending_used;      // elements of d_partials handed out so far
+  const void* pend_ptr[kMaxPending][3];
+  int pend_grid[kMaxPending][3];
+  int pend_fused[kMaxPending];
   bool engine_l;
   void* d_theta;            // copy of the angles taken by qcp_prepare()
   void* d_ws;               // internal saved-jet workspace (when the caller gives none)
@@ -924,70 +943,41 @@ int qcp_solver_forward(qcp_plan_t* p, const qcp_mlp_t* w, const void* X, long lo
                              : launch_solver_forward<float>(p->n, p->enc, mode, a, grid, s);
 }
 
-int qcp_solver_backward(qcp_plan_t* p, const qcp_mlp_t* w, const void* theta, const void* X,
-                        const void* grad_u, const void* grad_r, long long B, int mode,
-                        const double* coeffs, void* save, const qcp_mlp_t* g, void* grad_theta,
-                        void* grad_X, void* stream) {
-  if (!p || !w || !theta || !g || !grad_theta || (B > 0 && !X)) { set_error("qcp_solver_backward: NULL argument"); return 1; }
-  if (!p->prepared) { set_error("qcp_solver_backward: qcp_prepare() has not run"); return 1; }
-  if (check_mode(mode, coeffs, "qcp_solver_backward")) return 1;
+static size_t partial_slot_elems(const qcp_plan* p) {
+  return (size_t)p->num_sms * 8 * (size_t)nacc_solver(p->n, p->enc, p->H);
+}
+
+int qcp_solver_backward_begin(qcp_plan_t* p) {
+  if (!p) { set_error("qcp_solver_backward_begin: NULL plan"); return 1; }
+  p->pending = 0;
+  p->pending_used = 0;
+  return 0;
+}
+
+// launch the adjoint kernels of one call; partial sums stay in the plan until _finish()
+int qcp_solver_backward_add(qcp_plan_t* p, const qcp_mlp_t* w, const void* X, const void* grad_u,
+                            const void* grad_r, long long B, int mode, const double* coeffs,
+                            void* save, void* grad_X, void* stream) {
+  if (!p || !w || (B > 0 && !X)) { set_error("qcp_solver_backward_add: NULL argument"); return 1; }
+  if (!p->prepared) { set_error("qcp_solver_backward_add: qcp_prepare() has not run"); return 1; }
+  if (p->engine_l) { set_error("qcp_solver_backward_add: deferred reduction is an n <= %d feature", kMaxQubitsFused); return 1; }
+  if (check_mode(mode, coeffs, "qcp_solver_backward_add")) return 1;
+  if (B <= 0) return 0;
+  if (p->pending >= kMaxPending) { set_error("qcp_solver_backward_add: more than %d pending calls", kMaxPending); return 1; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int nacc = p->engine_l ? 0 : nacc_solver(p->n, p->enc, p->H);
+  const int nacc = nacc_solver(p->n, p->enc, p->H);
   const int mi = mode == QCP_MODE_RESIDUAL ? 1 : 0;
   const bool f64 = p->dtype == QCP_F64;
-  SolverArgs a{};
-  fill_solver_args(a, p, w, X, B > 0 ? B : 0, coeffs);
-  a.gu = grad_u; a.gr = grad_r; a.gX = grad_X; a.ws = save;
-  ScatterArgs sc{};
-  sc.w1 = g->w1; sc.b1 = g->b1; sc.w2 = g->w2; sc.b2 = g->b2;
-  sc.w3 = g->w3; sc.b3 = g->b3; sc.w4 = g->w4; sc.b4 = g->b4;
-  sc.Cbar = p->d_Cbar; sc.n = p->n; sc.H = p->H; sc.F = p->F; sc.nacc = nacc; sc.enc = p->enc;
   const size_t es = elem_size(p->dtype);
-  const long long want_blocks = B > 0 ? (B + kThreads - 1) / kThreads : 1;
-
-  if (p->engine_l) {
-    const int n0 = nacc_post(p->n, p->H), n2 = nacc_pre(p->n, p->H);
-    const int gb = mlp_grid(p, B > 0 ? B : 1, true);
-    if (ensure_partials(p, (size_t)gb * (n0 + n2))) return 1;
-    char* base = static_cast<char*>(p->d_partials);
-    void* p0 = base; void* p2 = base + es * (size_t)gb * n0;
-    if (B > 0) {
-      MlpLaunch M{};
-      M.n = p->n; M.H = p->H; M.args = a;
-      SvLaunch L{};
-      if (sv_configure(p, mode, B, L)) return 1;
-      if (!M.args.ws) {
-        // no saved jets: rebuild them (pre MLP + statevector forward) in the internal workspace
-        M.args.ws = internal_ws(p, B, mode);
-        if (!M.args.ws) return 1;
-        M.grid = mlp_grid(p, B, false);
-        if (mlp_pre_forward(p->dtype, mode, M, s)) return 1;
-        L.ws = M.args.ws;
-        if (sv_run(p->dtype, mode, false, L, s)) return 1;
-      }
-      L.ws = M.args.ws; L.grad_theta = grad_theta;
-      M.grid = gb;
-      M.args.partials = p0;
-      if (mlp_post_backward(p->dtype, mode, M, s)) return 1;
-      if (sv_run(p->dtype, mode, true, L, s)) return 1;
-      M.args.partials = p2;
-      if (mlp_pre_backward(p->dtype, mode, M, s)) return 1;
-    } else {
-      QCP_CUDA(cudaMemsetAsync(p->d_partials, 0, es * (size_t)gb * (n0 + n2), s));
-      QCP_CUDA(cudaMemsetAsync(grad_theta, 0, es * p->n_theta, s));
-    }
-    sc.nacc = n0 + n2; sc.F = 0;
-    sc.seg_ptr[0] = p0; sc.seg_len[0] = n0; sc.seg_grid[0] = gb;
-    sc.seg_ptr[1] = p0; sc.seg_len[1] = 0; sc.seg_grid[1] = 0;
-    sc.seg_ptr[2] = p2; sc.seg_len[2] = n2; sc.seg_grid[2] = gb;
-    const int rbl = (sc.nacc + 31) / 32;
-    if (f64) reduce_solver_kernel<double><<<rbl, 32 * kReduceSlices, 0, s>>>(sc);
-    else reduce_solver_kernel<float><<<rbl, 32 * kReduceSlices, 0, s>>>(sc);
-    QCP_CUDA(cudaGetLastError());
-    return 0;
-  }
-
-  if (save && B > 0) {
+  if (ensure_partials(p, kMaxPending * partial_slot_elems(p))) return 1;
+  SolverArgs a{};
+  fill_solver_args(a, p, w, X, B, coeffs);
+  a.gu = grad_u; a.gr = grad_r; a.gX = grad_X; a.ws = save;
+  const long long want_blocks = (B + kThreads - 1) / kThreads;
+  char* base = static_cast<char*>(p->d_partials) + es * p->pending_used;
+  const int k = p->pending;
+  const int n0 = nacc_post(p->n, p->H), n1 = p->F * p->n, n2 = nacc - n0 - n1;
+  if (save) {
     // split path: three kernels over the jets saved by the forward
     if (!p->split_ready[mi]) {
       int rc = f64 ? solver_split_grids<double>(p->n, p->enc, mode, p->H, p->num_sms, &p->split_cache[mi])
@@ -999,17 +989,16 @@ int qcp_solver_backward(qcp_plan_t* p, const qcp_mlp_t* w, const void* theta, co
     if (gr.post > want_blocks) gr.post = (int)want_blocks;
     if (gr.contract > want_blocks) gr.contract = (int)want_blocks;
     if (gr.pre > want_blocks) gr.pre = (int)want_blocks;
-    const int n0 = 1 + p->H * (p->n + 2), n1 = p->F * p->n, n2 = nacc - n0 - n1;
     const size_t e0 = (size_t)gr.post * n0, e1 = (size_t)gr.contract * n1, e2 = (size_t)gr.pre * n2;
-    if (ensure_partials(p, e0 + e1 + e2)) return 1;
-    char* base = static_cast<char*>(p->d_partials);
     void* p0 = base; void* p1 = base + e0 * es; void* p2 = base + (e0 + e1) * es;
     int rc = f64 ? launch_solver_backward_split<double>(p->n, p->enc, mode, a, gr, p0, p1, p2, s)
                  : launch_solver_backward_split<float>(p->n, p->enc, mode, a, gr, p0, p1, p2, s);
     if (rc) return rc;
-    sc.seg_ptr[0] = p0; sc.seg_len[0] = n0; sc.seg_grid[0] = gr.post;
-    sc.seg_ptr[1] = p1; sc.seg_len[1] = n1; sc.seg_grid[1] = gr.contract;
-    sc.seg_ptr[2] = p2; sc.seg_len[2] = n2; sc.seg_grid[2] = gr.pre;
+    p->pend_ptr[k][0] = p0; p->pend_grid[k][0] = gr.post;
+    p->pend_ptr[k][1] = p1; p->pend_grid[k][1] = gr.contract;
+    p->pend_ptr[k][2] = p2; p->pend_grid[k][2] = gr.pre;
+    p->pend_fused[k] = 0;
+    p->pending_used += e0 + e1 + e2;
   } else {
     // fused path: recompute the forward from X inside one kernel (no workspace needed)
     int& cached = p->grid_cache[mi];
@@ -1017,24 +1006,120 @@ int qcp_solver_backward(qcp_plan_t* p, const qcp_mlp_t* w, const void* theta, co
       cached = f64 ? solver_backward_max_grid<double>(p->n, p->enc, mode, p->H, p->num_sms)
                    : solver_backward_max_grid<float>(p->n, p->enc, mode, p->H, p->num_sms);
     const int grid = (int)(want_blocks > cached ? cached : want_blocks);
-    if (ensure_partials(p, (size_t)grid * nacc)) return 1;
-    a.partials = p->d_partials;
-    if (B > 0) {
-      int rc = f64 ? launch_solver_backward<double>(p->n, p->enc, mode, a, grid, s)
-                   : launch_solver_backward<float>(p->n, p->enc, mode, a, grid, s);
-      if (rc) return rc;
-    } else {
-      QCP_CUDA(cudaMemsetAsync(p->d_partials, 0, es * (size_t)grid * nacc, s));
+    a.partials = base;
+    int rc = f64 ? launch_solver_backward<double>(p->n, p->enc, mode, a, grid, s)
+                 : launch_solver_backward<float>(p->n, p->enc, mode, a, grid, s);
+    if (rc) return rc;
+    // a fused array [grid][nacc] is not segment-major: flagged so the reduce reads pitch nacc
+    for (int q = 0; q < 3; ++q) { p->pend_ptr[k][q] = base; p->pend_grid[k][q] = grid; }
+    p->pend_fused[k] = 1;
+    p->pending_used += (size_t)grid * nacc;
+  }
+  p->pending = k + 1;
+  return 0;
+}
+
+int qcp_solver_backward_finish(qcp_plan_t* p, const void* theta, const qcp_mlp_t* g,
+                               void* grad_theta, void* stream) {
+  if (!p || !theta || !g || !grad_theta) { set_error("qcp_solver_backward_finish: NULL argument"); return 1; }
+  if (p->engine_l) { set_error("qcp_solver_backward_finish: deferred reduction is an n <= %d feature", kMaxQubitsFused); return 1; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int nacc = nacc_solver(p->n, p->enc, p->H);
+  const bool f64 = p->dtype == QCP_F64;
+  const size_t es = elem_size(p->dtype);
+  ScatterArgs sc{};
+  sc.w1 = g->w1; sc.b1 = g->b1; sc.w2 = g->w2; sc.b2 = g->b2;
+  sc.w3 = g->w3; sc.b3 = g->b3; sc.w4 = g->w4; sc.b4 = g->b4;
+  sc.Cbar = p->d_Cbar; sc.n = p->n; sc.H = p->H; sc.F = p->F; sc.nacc = nacc; sc.enc = p->enc;
+  sc.seg_len[0] = nacc_post(p->n, p->H); sc.seg_len[1] = p->F * p->n;
+  sc.seg_len[2] = nacc - sc.seg_len[0] - sc.seg_len[1];
+  if (p->pending == 0) {
+    // nothing was added (all batches empty): gradients are zero
+    if (ensure_partials(p, kMaxPending * partial_slot_elems(p))) return 1;
+    QCP_CUDA(cudaMemsetAsync(p->d_partials, 0, es * (size_t)nacc, s));
+    sc.calls = 1;
+    sc.fused[0] = 1;
+    for (int k = 0; k < 3; ++k) { sc.seg_ptr[0][k] = p->d_partials; sc.seg_grid[0][k] = 1; }
+  } else {
+    sc.calls = p->pending;
+    for (int c = 0; c < p->pending; ++c) {
+      sc.fused[c] = p->pend_fused[c];
+      for (int k = 0; k < 3; ++k) { sc.seg_ptr[c][k] = p->pend_ptr[c][k]; sc.seg_grid[c][k] = p->pend_grid[c][k]; }
     }
-    sc.seg_ptr[0] = p->d_partials; sc.seg_len[0] = nacc; sc.seg_grid[0] = grid;
-    sc.seg_ptr[1] = p->d_partials; sc.seg_len[1] = 0; sc.seg_grid[1] = 0;
-    sc.seg_ptr[2] = p->d_partials; sc.seg_len[2] = 0; sc.seg_grid[2] = 0;
   }
   const int rb = (nacc + 31) / 32;
   if (f64) reduce_solver_kernel<double><<<rb, 32 * kReduceSlices, 0, s>>>(sc);
   else reduce_solver_kernel<float><<<rb, 32 * kReduceSlices, 0, s>>>(sc);
   QCP_CUDA(cudaGetLastError());
+  p->pending = 0;
+  p->pending_used = 0;
   return run_theta_grad(p, theta, grad_theta, s);
+}
+
+int qcp_solver_backward(qcp_plan_t* p, const qcp_mlp_t* w, const void* theta, const void* X,
+                        const void* grad_u, const void* grad_r, long long B, int mode,
+                        const double* coeffs, void* save, const qcp_mlp_t* g, void* grad_theta,
+                        void* grad_X, void* stream) {
+  if (!p || !w || !theta || !g || !grad_theta || (B > 0 && !X)) { set_error("qcp_solver_backward: NULL argument"); return 1; }
+  if (!p->prepared) { set_error("qcp_solver_backward: qcp_prepare() has not run"); return 1; }
+  if (check_mode(mode, coeffs, "qcp_solver_backward")) return 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!p->engine_l) {
+    if (qcp_solver_backward_begin(p)) return 1;
+    if (qcp_solver_backward_add(p, w, X, grad_u, grad_r, B, mode, coeffs, save, grad_X, stream)) return 1;
+    return qcp_solver_backward_finish(p, theta, g, grad_theta, stream);
+  }
+  // ---- engine L: pre MLP / statevector / post MLP adjoints -------------------------------------
+  const bool f64 = p->dtype == QCP_F64;
+  const size_t es = elem_size(p->dtype);
+  SolverArgs a{};
+  fill_solver_args(a, p, w, X, B > 0 ? B : 0, coeffs);
+  a.gu = grad_u; a.gr = grad_r; a.gX = grad_X; a.ws = save;
+  ScatterArgs sc{};
+  sc.w1 = g->w1; sc.b1 = g->b1; sc.w2 = g->w2; sc.b2 = g->b2;
+  sc.w3 = g->w3; sc.b3 = g->b3; sc.w4 = g->w4; sc.b4 = g->b4;
+  sc.Cbar = p->d_Cbar; sc.n = p->n; sc.H = p->H; sc.F = 0; sc.enc = p->enc;
+  const int n0 = nacc_post(p->n, p->H), n2 = nacc_pre(p->n, p->H);
+  const int gb = mlp_grid(p, B > 0 ? B : 1, true);
+  if (ensure_partials(p, (size_t)gb * (n0 + n2))) return 1;
+  char* base = static_cast<char*>(p->d_partials);
+  void* p0 = base; void* p2 = base + es * (size_t)gb * n0;
+  if (B > 0) {
+    MlpLaunch M{};
+    M.n = p->n; M.H = p->H; M.args = a;
+    SvLaunch L{};
+    if (sv_configure(p, mode, B, L)) return 1;
+    if (!M.args.ws) {
+      // no saved jets: rebuild them (pre MLP + statevector forward) in the internal workspace
+      M.args.ws = internal_ws(p, B, mode);
+      if (!M.args.ws) return 1;
+      M.grid = mlp_grid(p, B, false);
+      if (mlp_pre_forward(p->dtype, mode, M, s)) return 1;
+      L.ws = M.args.ws;
+      if (sv_run(p->dtype, mode, false, L, s)) return 1;
+    }
+    L.ws = M.args.ws; L.grad_theta = grad_theta;
+    M.grid = gb;
+    M.args.partials = p0;
+    if (mlp_post_backward(p->dtype, mode, M, s)) return 1;
+    if (sv_run(p->dtype, mode, true, L, s)) return 1;
+    M.args.partials = p2;
+    if (mlp_pre_backward(p->dtype, mode, M, s)) return 1;
+  } else {
+    QCP_CUDA(cudaMemsetAsync(p->d_partials, 0, es * (size_t)gb * (n0 + n2), s));
+    QCP_CUDA(cudaMemsetAsync(grad_theta, 0, es * p->n_theta, s));
+  }
+  sc.nacc = n0 + n2;
+  sc.calls = 1;
+  sc.seg_len[0] = n0; sc.seg_len[1] = 0; sc.seg_len[2] = n2;
+  sc.seg_ptr[0][0] = p0; sc.seg_grid[0][0] = gb;
+  sc.seg_ptr[0][1] = p0; sc.seg_grid[0][1] = 0;
+  sc.seg_ptr[0][2] = p2; sc.seg_grid[0][2] = gb;
+  const int rbl = (sc.nacc + 31) / 32;
+  if (f64) reduce_solver_kernel<double><<<rbl, 32 * kReduceSlices, 0, s>>>(sc);
+  else reduce_solver_kernel<float><<<rbl, 32 * kReduceSlices, 0, s>>>(sc);
+  QCP_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int qcp_bench_fma(int dtype, int iters, double* flops_per_s, void* stream) {

@@ -76,6 +76,7 @@ class Plan:
                 self.n_theta)
         _lib.check(rc, "qcp_plan_create")
         self.num_features = self.lib.qcp_plan_num_features(self._handle)
+        self.fused_engine = self.n <= 4      # n > 4 runs on the per-sample statevector engine
 
     def __del__(self):
         h = getattr(self, "_handle", None)
@@ -99,14 +100,18 @@ class Plan:
         self._key = None
         self._wkey = None
 
-    def typed_weights(self, theta, mlp):
+    def typed_weights(self, theta, mlp, epoch=None):
         """(theta, 8 MLP tensors) in the plan dtype, contiguous.  When a cast is needed (float32
         parameters, float64 plan) all nine tensors are packed and converted with two kernels and
         the result is cached until any of them changes (3 model calls per step share it)."""
         tensors = [theta] + list(mlp)
         if all(t.dtype == self.dtype and t.is_contiguous() for t in tensors):
             return theta.detach().reshape(-1), [t.detach() for t in mlp]
-        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        # `epoch` (bumped by the solver after every optimizer step) guards against in-place
+        # updates that do not touch the tensors' version counters (fused optimizers)
+        key = (epoch,) + tuple((t.data_ptr(), t._version) for t in tensors)
+        if epoch is None:
+            self._wkey = None        # no epoch information: never trust the cache
         if getattr(self, "_wkey", None) != key:
             for t in tensors:
                 if t.device != self.device:
@@ -223,6 +228,48 @@ class Plan:
         return views, gx
 
 
+def _flat_grad_views(plan: Plan, mlp, theta):
+    sizes = [t.numel() for t in mlp] + [plan.n_theta]
+    flat = torch.empty(sum(sizes), dtype=plan.dtype, device=plan.device)
+    views, off = [], 0
+    for t, sz in zip(list(mlp) + [theta], sizes):
+        views.append(flat[off:off + sz].view(t.shape))
+        off += sz
+    return flat, views
+
+
+def solver_backward_many(plan: Plan, items, mlp, theta):
+    """Adjoint kernels of several model calls, ONE partial reduction and ONE theta-gradient kernel.
+    ``items`` = [(X, grad_u, grad_r, mode, coeffs, save, need_gx), ...].  Returns (views, [gx])."""
+    lib = plan.lib
+    flat, views = _flat_grad_views(plan, mlp, theta)
+    m = plan._mlp(mlp)
+    g = plan._mlp(views[:8])
+    gxs = []
+    with torch.cuda.device(plan.device):
+        stream = plan._stream()
+        _lib.check(lib.qcp_solver_backward_begin(plan._handle), "qcp_solver_backward_begin")
+        for X, gu, gr, mode, coeffs, save, need_gx in items:
+            gx = torch.empty_like(X) if need_gx else None
+            gxs.append(gx)
+            c = (ctypes.c_double * 5)(*coeffs) if coeffs is not None else None
+            rc = lib.qcp_solver_backward_add(
+                plan._handle, ctypes.byref(m), ctypes.c_void_p(X.data_ptr()),
+                ctypes.c_void_p(gu.data_ptr() if gu is not None else None),
+                ctypes.c_void_p(gr.data_ptr() if gr is not None else None),
+                X.shape[0], mode, c, ctypes.c_void_p(save.data_ptr() if save is not None else None),
+                ctypes.c_void_p(gx.data_ptr() if gx is not None else None), stream)
+            _lib.check(rc, "qcp_solver_backward_add")
+            if X.shape[0]:
+                _count(3 if save is not None else 1)
+        rc = lib.qcp_solver_backward_finish(
+            plan._handle, ctypes.c_void_p(theta.data_ptr()), ctypes.byref(g),
+            ctypes.c_void_p(views[8].data_ptr()), stream)
+        _lib.check(rc, "qcp_solver_backward_finish")
+        _count(2)
+    return views, gxs
+
+
 def _grad_in(plan: Plan, g, like):
     if g is None:
         return None
@@ -259,7 +306,7 @@ class _SolverFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan: Plan, key, mode, coeffs, X, theta, *mlp):
         Xt = plan._t(X)
-        tt, mt = plan.typed_weights(theta, mlp)
+        tt, mt = plan.typed_weights(theta, mlp, key)
         plan.prepare(tt, key)
         needs_grad = any(ctx.needs_input_grad[4:])
         save = plan.workspace(Xt.shape[0], mode) if (needs_grad and SAVE_JETS and Xt.shape[0]) else None
@@ -300,6 +347,83 @@ class _SolverFn(torch.autograd.Function):
         gm = [v.to(d) if need else None
               for v, d, need in zip(views[:8], dt[2:], ctx.needs_input_grad[6:])]
         return (None, None, None, None, gX, gtheta, *gm)
+
+
+def _cast_grads(plan, views, dt_theta, dt_mlp, theta_shape, needs_theta, needs_mlp):
+    dts = [dt_theta] + list(dt_mlp)
+    if len(set(dts)) == 1 and dts[0] != plan.dtype:
+        flat = views[0]._base.to(dts[0])      # one cast kernel for the flat buffer instead of nine
+        off, cast = 0, []
+        for v in views:
+            cast.append(flat[off:off + v.numel()].view(v.shape))
+            off += v.numel()
+        views = cast
+    gtheta = views[8].to(dt_theta).view(theta_shape) if needs_theta else None
+    gm = [v.to(d) if need else None for v, d, need in zip(views[:8], dt_mlp, needs_mlp)]
+    return gtheta, gm
+
+
+class _SolverManyFn(torch.autograd.Function):
+    """Several model calls of one train step behind ONE autograd node (n <= 4): the forward
+    kernels run back to back, the backward launches every call's adjoint kernels and shares one
+    partial-sum reduction and one theta-gradient kernel, and autograd sees a single gradient per
+    parameter (no 3-way AccumulateGrad adds).  ``specs`` = ((mode, coeffs), ...) per input X."""
+
+    @staticmethod
+    def forward(ctx, plan: Plan, key, specs, theta, *rest):
+        mlp, Xs = rest[:8], rest[8:]
+        tt, mt = plan.typed_weights(theta, mlp, key)
+        plan.prepare(tt, key)
+        needs_grad = any(ctx.needs_input_grad[3:])
+        outs, saved = [], []
+        for (mode, coeffs), X in zip(specs, Xs):
+            Xt = plan._t(X)
+            save = plan.workspace(Xt.shape[0], mode) if (needs_grad and SAVE_JETS and Xt.shape[0]) else None
+            u, r, _ = plan.solver_forward(Xt, mt, mode, coeffs, save=save)
+            saved.append((Xt, save))
+            outs.append(u.view(-1, 1))
+            if mode == MODE_RESIDUAL:
+                outs.append(r.view(-1, 1))
+        ctx.plan, ctx.key, ctx.specs = plan, key, specs
+        ctx.saved = saved
+        ctx.save_for_backward(tt, *mt)
+        ctx.in_dtypes = [theta.dtype] + [w.dtype for w in mlp]
+        ctx.x_dtypes = [X.dtype for X in Xs]
+        ctx.theta_shape = theta.shape
+        return tuple(outs)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *grads):
+        plan = ctx.plan
+        tt, *mt = ctx.saved_tensors
+        plan.prepare(tt, ctx.key)
+        items, gi = [], 0
+        n_x = len(ctx.specs)
+        for i, ((mode, coeffs), (Xt, save)) in enumerate(zip(ctx.specs, ctx.saved)):
+            b = Xt.shape[0]
+            gu = _grad_in(plan, grads[gi], (b,))
+            gi += 1
+            gr = None
+            if mode == MODE_RESIDUAL:
+                gr = _grad_in(plan, grads[gi], (b,))
+                gi += 1
+            need_gx = ctx.needs_input_grad[3 + 1 + 8 + i] and mode == MODE_VALUE
+            items.append((Xt, gu, gr, mode, coeffs, save, need_gx))
+        views, gxs = solver_backward_many(plan, items, mt, tt)
+        ctx.saved = None
+        gtheta, gm = _cast_grads(plan, views, ctx.in_dtypes[0], ctx.in_dtypes[1:], ctx.theta_shape,
+                                 ctx.needs_input_grad[3], ctx.needs_input_grad[4:12])
+        gX = [g.to(d) if g is not None else None for g, d in zip(gxs, ctx.x_dtypes)]
+        return (None, None, None, gtheta, *gm, *gX)
+
+
+def solver_many(plan: Plan, batches, theta, mlp, key=None):
+    """``batches`` = [(X, coeffs or None), ...]; returns a flat tuple: u for value entries,
+    (u, r) for residual entries, in order."""
+    specs = tuple((MODE_RESIDUAL, tuple(float(c) for c in co)) if co is not None else (MODE_VALUE, None)
+                  for _, co in batches)
+    return _SolverManyFn.apply(plan, key, specs, theta, *mlp, *[X for X, _ in batches])
 
 
 def layer_apply(plan: Plan, z, theta, key=None):

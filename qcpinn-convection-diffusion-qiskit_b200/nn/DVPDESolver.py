@@ -85,9 +85,11 @@ class DVPDESolver(nn.Module):
         trainable = [p for p in self.parameters() if p.requires_grad]
         if on_cuda:
             lr0 = torch.tensor(float(self.args["lr"]), dtype=torch.float32, device=self.device)
-            self.optimizer = torch.optim.Adam(trainable, lr=lr0, capturable=True)
+            self.optimizer = torch.optim.Adam(trainable, lr=lr0, capturable=True, fused=True)
         else:
             self.optimizer = torch.optim.Adam(trainable, lr=self.args["lr"])
+        # fused / capturable optimizers update parameters without touching their version counters
+        self.optimizer.register_step_post_hook(lambda *_: self.quantum_layer.mark_updated())
         self.scheduler = _RankConsistentPlateau(
             self.optimizer, mode="min", factor=0.9, patience=1000)
         self.loss_fn = torch.nn.MSELoss()
@@ -155,6 +157,37 @@ class DVPDESolver(nn.Module):
             self.logger.print(f"Forward pass failed: {str(e)}")
             raise
 
+    def forward_many(self, batches):
+        """All model calls of one train step behind one autograd node (n <= 4; falls back to
+        separate calls otherwise).  ``batches`` = [(X, coeffs or None), ...]: ``None`` means
+        ``forward(X)`` -> u, a 5-tuple of PDE coefficients means ``taylor_residual`` -> (u, r).
+        Returns a list with one entry per batch (u, or the pair (u, r)), float32 like forward()."""
+        try:
+            for X, _ in batches:
+                if X.dim() != 2:
+                    raise ValueError(f"Expected 2D input tensor, got shape {X.shape}")
+            if self.draw_quantum_circuit_flag:
+                self.draw_quantum_circuit(batches[0][0])
+                self.draw_quantum_circuit_flag = False
+            plan = self._plan(self._device_of(batches[0][0]))
+            if not plan.fused_engine:
+                return [self.forward(X) if co is None else self.taylor_residual(X, co)
+                        for X, co in batches]
+            flat = F.solver_many(plan, batches, self.quantum_layer.params, self._mlp_tensors(),
+                                 self.quantum_layer.theta_key())
+            out, i = [], 0
+            for _, co in batches:
+                if co is None:
+                    out.append(flat[i].to(torch.float32))
+                    i += 1
+                else:
+                    out.append((flat[i].to(torch.float32), flat[i + 1].to(torch.float32)))
+                    i += 2
+            return out
+        except Exception as e:
+            self.logger.print(f"Forward pass failed: {str(e)}")
+            raise
+
     def taylor_streams(self, X: torch.Tensor):
         """No-grad evaluation helper: (B,6) = u, u_t, u_x, u_y, u_xx, u_yy."""
         plan = self._plan(self._device_of(X))
@@ -202,6 +235,7 @@ class DVPDESolver(nn.Module):
         """Load a ``save_state`` dict (ours or the reference's) back into this model."""
         self.preprocessor.load_state_dict(state["preprocessor"])
         self.quantum_layer.load_state_dict(state["quantum_layer"])
+        self.quantum_layer.mark_updated()
         self.postprocessor.load_state_dict(state["postprocessor"])
         if "optimizer" in state:
             self.optimizer.load_state_dict(state["optimizer"])

@@ -61,6 +61,7 @@ class DVQuantumLayer(nn.Module):
         self.use_batch_processing = True
         self._program = None
         self._plans = {}
+        self._epoch = 0     # bumped by DVPDESolver after every optimizer step (cache keys)
 
     def _initialize_weights(self):
         torch.nn.init.xavier_normal_(self.params)
@@ -83,7 +84,11 @@ class DVQuantumLayer(nn.Module):
         return plan
 
     def theta_key(self):
-        return (self.params.data_ptr(), self.params._version, self.params.device.index)
+        return (self._epoch, self.params.data_ptr(), self.params._version, self.params.device.index)
+
+    def mark_updated(self):
+        """Call after parameters changed in a way that may not bump ``_version`` counters."""
+        self._epoch += 1
 
     def describe(self) -> str:
         names = ["RX", "RY", "RZ", "CRX", "CRZ", "CNOT", "H", "U4"]

@@ -22,6 +22,10 @@ from ..data.diffusion_dataset import Sampler, r, training_boxes, u
 from ..nn.pde import diffusion_operator
 
 
+# diffusion_operator's defaults (sigma = 1, D = 0.01, v = (1, 1)) as residual coefficients
+DIFFUSION_COEFFS = (1.0, 1.0, 1.0, -0.01, -0.01)
+
+
 def fetch_minibatch(sampler, N):
     return sampler.sample(N)
 
@@ -55,6 +59,7 @@ class TrainStep:
         if use_graph is None:
             use_graph = bool(model.args.get("cuda_graph", True))
         self.use_graph = bool(use_graph) and on_cuda
+        self.fuse_calls = bool(model.args.get("fuse_model_calls", True))
         self._eager_calls = 0
         self._graphs = {}          # "device" / "host" -> (graph, static outputs, static batch)
         self.last_terms = None     # (loss, loss_r, loss_bc, loss_ic) tensors of the last step
@@ -74,10 +79,16 @@ class TrainStep:
             model.optimizer.zero_grad()
         X_ics, u_ics, X_bcs, u_bcs, X_res, r_res = self.sample() if batch is None else batch
         X_ics.requires_grad_(True)
-        u_bc1_pred = model.forward(X_bcs)
-        u_ics_pred = model.forward(X_ics)
-        t_r, x_r, y_r = X_res[:, 0:1], X_res[:, 1:2], X_res[:, 2:3]
-        _, r_pred = diffusion_operator(model, t_r, x_r, y_r)
+        many = getattr(model, "forward_many", None) if self.fuse_calls else None
+        if many is not None:
+            # same three model calls, issued behind one autograd node (shared gradient reduction)
+            u_bc1_pred, u_ics_pred, (_, r_pred) = many(
+                [(X_bcs, None), (X_ics, None), (X_res, DIFFUSION_COEFFS)])
+        else:
+            u_bc1_pred = model.forward(X_bcs)
+            u_ics_pred = model.forward(X_ics)
+            t_r, x_r, y_r = X_res[:, 0:1], X_res[:, 1:2], X_res[:, 2:3]
+            _, r_pred = diffusion_operator(model, t_r, x_r, y_r)
         loss_r = model.loss_fn(r_pred, r_res)
         loss_bc1 = model.loss_fn(u_bc1_pred, u_bcs)
         loss_ics = model.loss_fn(u_ics_pred, u_ics)

@@ -232,7 +232,9 @@ def test_abi_error_reporting():
     ops = (ctypes.c_int32 * 4)(0, 9, -1, 0)            # wire 9 on a 4-qubit plan
     rc = lib.qcp_plan_create(ctypes.byref(handle), 4, 0, 1, 50, ops, 1, None, 0, 1)
     assert rc != 0 and b"invalid" in lib.qcp_last_error()
-    rc = lib.qcp_plan_create(ctypes.byref(handle), 9, 0, 1, 50, ops, 0, None, 0, 0)
+    rc = lib.qcp_plan_create(ctypes.byref(handle), 17, 0, 1, 50, ops, 0, None, 0, 0)
+    assert rc != 0 and b"qubits" in lib.qcp_last_error()
+    rc = lib.qcp_plan_create(ctypes.byref(handle), 1, 0, 1, 50, ops, 0, None, 0, 0)
     assert rc != 0 and b"qubits" in lib.qcp_last_error()
     prog = qb.program.compile_program("cascade", 4, 1)
     plan = F.Plan(prog, 0, torch.float64, 50, DEV)
@@ -262,3 +264,43 @@ def test_fused_sampler_matches_torch_expressions():
     # generic callables still take the torch path
     X, y = Sampler(3, boxes["dom"], lambda p: p.sum(1, keepdim=True), device=DEV).sample(5)
     assert torch.allclose(y, X.sum(1, keepdim=True))
+
+
+def test_evaluation_grid_matches_oracle(tmp_path):
+    """Reference evaluation block (20^3 grid, no backward, rel-L2 in percent)."""
+    from qcpinn_b200.trainer.diffusion_eval import evaluate, evaluation_grid
+
+    model = _model(tmp_path)
+    out = evaluate(model, num_points=8)
+    X = evaluation_grid(8)
+    assert out["X_star"].shape == (512, 3) and torch.equal(out["X_star"].cpu(), X)
+    assert torch.equal(X[1], torch.tensor([0.0, 0.0, 1.0 / 7.0]))        # y fastest, t slowest
+    oracle = _oracle_of(model)
+    Xd = X.double()
+    uo, ro = osolver.diffusion_operator(oracle, Xd[:, 0:1].clone(), Xd[:, 1:2].clone(), Xd[:, 2:3].clone())
+    from oracle import dataset as od
+    eu = float(torch.linalg.norm(od.u_exact(Xd) - uo) / torch.linalg.norm(od.u_exact(Xd))) * 100
+    ef = float(torch.linalg.norm(od.forcing(Xd) - ro) / torch.linalg.norm(od.forcing(Xd) + 1e-9)) * 100
+    assert abs(out["error_u"] - eu) < 1e-3 * eu and abs(out["error_f"] - ef) < 1e-3 * ef
+    log = open(os.path.join(model.log_path, "output.log")).read()
+    assert "Relative L2 error_u:" in log and "Relative L2 error_f:" in log
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_forward_many_equals_separate_calls(tmp_path, dtype):
+    """One autograd node for the three model calls (shared reduction) == three separate nodes."""
+    from qcpinn_b200.trainer.diffusion_train import TrainStep
+
+    batches = osolver.make_batches(200, seed=21)
+    batch = [batches[k].to(DEV) for k in ("X_ic", "u_ic", "X_bc", "u_bc", "X_res", "r_res")]
+    grads = {}
+    for fuse in (True, False):
+        model = _model(tmp_path, dtype=dtype, fuse_model_calls=fuse, cuda_graph=False)
+        step = TrainStep(model, 200)
+        loss, *_ = step.objective(tuple(t.clone() for t in batch))
+        loss.backward()
+        grads[fuse] = (loss.item(), [p.grad.clone() for p in model.parameters()])
+    assert abs(grads[True][0] - grads[False][0]) < 1e-6 * abs(grads[False][0])
+    tol = 1e-9 if dtype == "float64" else 2e-5
+    for a, b in zip(grads[True][1], grads[False][1]):
+        assert rel_err(a, b) < max(tol, 2e-6)       # grads are float32 tensors
