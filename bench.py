@@ -198,8 +198,8 @@ def run_ours(ns):
         # dominant kernels: the residual backward (post + contraction + pre adjoint kernels over the
         # jets saved by the forward), timed alone with CUDA events on the launch stream
         plan = model._plan(device)
-        X = torch.rand(pts_rank, 3, device=device).to(plan.dtype)
-        gr = torch.rand(pts_rank, device=device).to(plan.dtype)
+        X = torch.rand(pts_rank, 3, device=device).to(plan.io_dtype)
+        gr = torch.rand(pts_rank, device=device).to(plan.io_dtype)
         theta = model.quantum_layer.params.detach().to(plan.dtype).reshape(-1).contiguous()
         mlp = [plan._t(w) for w in model._mlp_tensors()]
         plan.prepare(theta)

@@ -81,6 +81,13 @@ int qcp_plan_create(qcp_plan_t** out, int n_qubits, int encoding, int dtype, int
 int qcp_plan_destroy(qcp_plan_t* plan);
 int qcp_plan_num_features(const qcp_plan_t* plan);
 
+/* Element type of the caller-facing arrays of the solver entry points (X, u, r, streams, grad_u,
+ * grad_r, grad_X).  Default = the plan dtype.  A QCP_F64 plan (n <= 4) may be switched to QCP_F32
+ * I/O: arithmetic, weights, gradients and the saved jets stay float64, but the float32 tensors of
+ * DVPDESolver (reference nn/DVPDESolver.py:96 casts to float32 anyway) are read and written
+ * directly, with no cast kernels around the calls. */
+int qcp_plan_set_io_dtype(qcp_plan_t* plan, int io_dtype);
+
 /* Evaluate the batch-shared part of the circuit for the current angles ``theta`` [n_theta]:
  * V(theta) = H_last . Haar . ansatz layers, O_i = V^dag Z_i V, and the real feature matrix C with
  * <Z_i>(z) = sum_s C[i,s] phi_s(z).  Must precede forward calls whenever theta changed. */

@@ -52,6 +52,7 @@ struct SolverArgs {
   void* ws;            // saved-jet workspace [2][n*S][B] or null (forward: save; split backward: use)
   long long B;
   int H;
+  int io_f32;          // 1: X, u, r, streams, gu, gr, gX are float32 whatever the plan dtype
   PdeCoeffs pde;
 };
 

@@ -282,7 +282,7 @@ struct ScatterArgs {
   int seg_len[3];
 };
 
-constexpr int kReduceSlices = 8;   // threads cooperating on one accumulator (over the block index)
+constexpr int kReduceSlices = 32;  // threads cooperating on one accumulator (over the block index)
 
 template <typename T>
 __global__ void __launch_bounds__(32 * kReduceSlices)
@@ -356,6 +356,7 @@ reduce_layer_kernel(const T* __restrict__ partials, double* Cbar, int grid, int 
 // ---------------------------------------------------------------------------------------------
 // theta gradient: C-bar -> R_i -> Lambda -> reverse sweep
 // ---------------------------------------------------------------------------------------------
+constexpr int kMaxCbarSmem = 3 * 3 * 3 * 3 * 4;   // 3^4 features x 4 outputs
 constexpr int kMaxThetaSmem = 256;   // circuit angles accumulated in shared memory (per warp)
 
 __device__ __forceinline__ void atomicAdd_T(double* p, double v) { atomicAdd(p, v); }
@@ -384,6 +385,14 @@ theta_grad_kernel(int n, int enc, const GateOp* ops, int n_ops, const T* theta, 
   }
   const Mat2* table = build_gate_table(table_mem, ops, n_ops, theta);
   simulate_columns(V, n, ops, n_ops, theta, consts, table);
+  // stage C-bar in shared memory: the R loop below reads it with data-dependent indices
+  __shared__ double cbar_s[kMaxCbarSmem];
+  const int n_cbar = num_features(n, enc) * n;
+  if (n_cbar <= kMaxCbarSmem) {
+    for (int e = threadIdx.x; e < n_cbar; e += blockDim.x) cbar_s[e] = Cbar[e];
+    __syncthreads();
+    Cbar = cbar_s;
+  }
 
   // R_i[b,a] = sum_s Cbar[i,s] E_s[b,a]
   for (int it = threadIdx.x; it < n * M * M; it += blockDim.x) {
@@ -542,6 +551,7 @@ struct qcp_plan {
   const void* pend_ptr[kMaxPending][3];
   int pend_grid[kMaxPending][3];
   int pend_fused[kMaxPending];
+  int io_f32;               // caller-facing arrays are float32 although the plan is float64
   bool engine_l;
   void* d_theta;            // copy of the angles taken by qcp_prepare()
   void* d_ws;               // internal saved-jet workspace (when the caller gives none)
@@ -564,7 +574,9 @@ static size_t setup_smem_bytes(const qcp_plan* p, bool grad) {
 
 template <typename K>
 static int opt_in_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024 &&
+  // static + dynamic shared memory may exceed the 48 KB default even when the dynamic part alone
+  // does not: always opt in
+  if (bytes > 0 &&
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
     cudaGetLastError();
     return 1;
@@ -676,6 +688,17 @@ int qcp_plan_destroy(qcp_plan_t* p) {
 }
 
 int qcp_plan_num_features(const qcp_plan_t* p) { return p ? p->F : -1; }
+
+int qcp_plan_set_io_dtype(qcp_plan_t* p, int io_dtype) {
+  if (!p || (io_dtype != QCP_F32 && io_dtype != QCP_F64)) { set_error("qcp_plan_set_io_dtype: bad argument"); return 1; }
+  if (io_dtype == p->dtype) { p->io_f32 = 0; return 0; }
+  if (p->dtype != QCP_F64 || p->engine_l) {
+    set_error("qcp_plan_set_io_dtype: float32 I/O is available for float64 plans with n <= %d", kMaxQubitsFused);
+    return 1;
+  }
+  p->io_f32 = 1;
+  return 0;
+}
 
 int qcp_prepare(qcp_plan_t* p, const void* theta, void* stream) {
   if (!p || (!theta && p->n_theta > 0)) { set_error("qcp_prepare: NULL argument"); return 1; }
@@ -899,7 +922,7 @@ static void fill_solver_args(SolverArgs& a, const qcp_plan* p, const qcp_mlp_t* 
                              long long B, const double* c) {
   a.X = X; a.w1 = w->w1; a.b1 = w->b1; a.w2 = w->w2; a.b2 = w->b2;
   a.w3 = w->w3; a.b3 = w->b3; a.w4 = w->w4; a.b4 = w->b4;
-  a.C = p->d_C; a.B = B; a.H = p->H;
+  a.C = p->d_C; a.B = B; a.H = p->H; a.io_f32 = p->io_f32;
   if (c) { a.pde.ct = c[0]; a.pde.cx = c[1]; a.pde.cy = c[2]; a.pde.cxx = c[3]; a.pde.cyy = c[4]; }
 }
 

@@ -761,17 +761,17 @@ __device__ __forceinline__ void ws_load(const T* ws, long long B, int slot, long
 }
 
 // cotangent seed of the outputs: (grad_u, grad_r) -> jet cotangent of u
-template <typename T, int S>
+template <typename T, int S, typename TIO = T>
 __device__ __forceinline__ Jet<T, S> seed_cotangent(const SolverArgs& a, long long p, bool valid) {
   Jet<T, S> ub;
   jzero(ub);
   if (valid) {
-    const T* gug = static_cast<const T*>(a.gu);
-    const T* grg = static_cast<const T*>(a.gr);
-    if (gug) ub.c[0] = gug[p];
+    const TIO* gug = static_cast<const TIO*>(a.gu);
+    const TIO* grg = static_cast<const TIO*>(a.gr);
+    if (gug) ub.c[0] = (T)gug[p];
     if constexpr (S == 6) {
       if (grg) {
-        const T g = grg[p];
+        const T g = (T)grg[p];
         ub.c[1] = T(a.pde.ct) * g; ub.c[2] = T(a.pde.cx) * g; ub.c[3] = T(a.pde.cy) * g;
         ub.c[4] = T(a.pde.cxx) * g; ub.c[5] = T(a.pde.cyy) * g;
       }
@@ -805,7 +805,10 @@ __device__ __forceinline__ void write_partials(const T* acc_all, int nacc, T* pa
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
-template <typename T, int NQ, int ENC, int S>
+// TIO = element type of the caller-facing arrays (X, u, r, streams, grad_u, grad_r, grad_X): the
+// plan dtype T, or float when a float64 plan serves the float32 module interface directly (saves
+// the cast kernels around every call; the arithmetic and the saved jets stay in T).
+template <typename T, int NQ, int ENC, int S, typename TIO>
 __global__ void __launch_bounds__(kThreads, Tune<T, S>::kFwd)
 solver_forward_kernel(const SolverArgs a) {
   extern __shared__ __align__(32) unsigned char smem_raw[];
@@ -814,36 +817,36 @@ solver_forward_kernel(const SolverArgs a) {
   load_weights<T, NQ, ENC>(sw, a);
   __syncthreads();
 
-  const T* Xg = static_cast<const T*>(a.X);
-  T* ug = static_cast<T*>(a.u);
-  T* rg = static_cast<T*>(a.r);
-  T* sg = static_cast<T*>(a.streams);
+  const TIO* Xg = static_cast<const TIO*>(a.X);
+  TIO* ug = static_cast<TIO*>(a.u);
+  TIO* rg = static_cast<TIO*>(a.r);
+  TIO* sg = static_cast<TIO*>(a.streams);
   T* wsg = static_cast<T*>(a.ws);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < a.B; p += stride) {
-    T X[3] = {Xg[3 * p], Xg[3 * p + 1], Xg[3 * p + 2]};
+    T X[3] = {(T)Xg[3 * p], (T)Xg[3 * p + 1], (T)Xg[3 * p + 2]};
     Jet<T, S> z[NQ], q[NQ], u;
     pre_forward<T, NQ, S>(sw, H, X, z);
     if (wsg) ws_store<T, NQ, S>(wsg, a.B, 0, p, z);
     feature_forward<T, NQ, ENC, S>(sw.C, z, q);
     if (wsg) ws_store<T, NQ, S>(wsg, a.B, 1, p, q);
     post_forward<T, NQ, S>(sw, H, q, u);
-    ug[p] = u.c[0];
+    ug[p] = (TIO)u.c[0];
     if constexpr (S == 6) {
       if (rg) {
-        rg[p] = T(a.pde.ct) * u.c[1] + T(a.pde.cx) * u.c[2] + T(a.pde.cy) * u.c[3] +
-                T(a.pde.cxx) * u.c[4] + T(a.pde.cyy) * u.c[5];
+        rg[p] = (TIO)(T(a.pde.ct) * u.c[1] + T(a.pde.cx) * u.c[2] + T(a.pde.cy) * u.c[3] +
+                      T(a.pde.cxx) * u.c[4] + T(a.pde.cyy) * u.c[5]);
       }
       if (sg) {
 #pragma unroll
-        for (int c = 0; c < 6; ++c) sg[6 * p + c] = u.c[c];
+        for (int c = 0; c < 6; ++c) sg[6 * p + c] = (TIO)u.c[c];
       }
     }
   }
 }
 
 // fused backward: recompute the forward from X, then the whole reverse sweep
-template <typename T, int NQ, int ENC, int S>
+template <typename T, int NQ, int ENC, int S, typename TIO>
 __global__ void __launch_bounds__(kThreads, Tune<T, S>::kFused)
 solver_backward_kernel(const SolverArgs a) {
   extern __shared__ __align__(32) unsigned char smem_raw[];
@@ -858,16 +861,16 @@ solver_backward_kernel(const SolverArgs a) {
   __syncthreads();
   Stager<T> st = make_stager<T>(acc_all, tile_all, nacc);
 
-  const T* Xg = static_cast<const T*>(a.X);
-  T* gXg = static_cast<T*>(a.gX);
+  const TIO* Xg = static_cast<const TIO*>(a.X);
+  TIO* gXg = static_cast<TIO*>(a.gX);
   const long long stride = (long long)gridDim.x * blockDim.x;
   // whole warps iterate together (staging needs every lane); out-of-range lanes carry zero seeds
   const long long Bpad = (a.B + 31) & ~31LL;
   for (long long p0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; p0 < Bpad; p0 += stride) {
     const bool valid = p0 < a.B;
     const long long p = valid ? p0 : a.B - 1;
-    T X[3] = {Xg[3 * p], Xg[3 * p + 1], Xg[3 * p + 2]};
-    const Jet<T, S> ub = seed_cotangent<T, S>(a, p, valid);
+    T X[3] = {(T)Xg[3 * p], (T)Xg[3 * p + 1], (T)Xg[3 * p + 2]};
+    const Jet<T, S> ub = seed_cotangent<T, S, TIO>(a, p, valid);
     st.begin();
     st.put(ub.c[0]);                                       // d b4
     Jet<T, S> z[NQ], q[NQ], qb[NQ], zb[NQ];
@@ -882,7 +885,7 @@ solver_backward_kernel(const SolverArgs a) {
     pre_backward<T, NQ, S>(sw, H, X, zb, Xb, st);
     st.flush();
     if (gXg && valid) {
-      gXg[3 * p] = Xb[0]; gXg[3 * p + 1] = Xb[1]; gXg[3 * p + 2] = Xb[2];
+      gXg[3 * p] = (TIO)Xb[0]; gXg[3 * p + 1] = (TIO)Xb[1]; gXg[3 * p + 2] = (TIO)Xb[2];
     }
   }
   write_partials<T>(acc_all, nacc, static_cast<T*>(a.partials));
@@ -893,7 +896,7 @@ solver_backward_kernel(const SolverArgs a) {
 //   contract_backward_kernel z (slot 0), qb (slot 1)    -> zb (slot 0);  d C
 //   pre_backward_kernel      X, zb (slot 0)             -> grad_X;       d b2, d w1, d b1, d w2
 // Their accumulators are consecutive segments of the fused kernel's accumulator order.
-template <typename T, int NQ, int ENC, int S>
+template <typename T, int NQ, int ENC, int S, typename TIO>
 __global__ void __launch_bounds__(kThreads, Tune<T, S>::kPost)
 post_backward_kernel(const SolverArgs a) {
   extern __shared__ __align__(32) unsigned char smem_raw[];
@@ -914,7 +917,7 @@ post_backward_kernel(const SolverArgs a) {
   for (long long p0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; p0 < Bpad; p0 += stride) {
     const bool valid = p0 < a.B;
     const long long p = valid ? p0 : a.B - 1;
-    const Jet<T, S> ub = seed_cotangent<T, S>(a, p, valid);
+    const Jet<T, S> ub = seed_cotangent<T, S, TIO>(a, p, valid);
     Jet<T, S> q[NQ], qb[NQ];
     ws_load<T, NQ, S>(wsg, a.B, 1, p, q);
     st.begin();
@@ -961,7 +964,7 @@ contract_backward_kernel(const SolverArgs a) {
   write_partials<T>(acc_all, nacc, static_cast<T*>(a.partials));
 }
 
-template <typename T, int NQ, int ENC, int S>
+template <typename T, int NQ, int ENC, int S, typename TIO>
 __global__ void __launch_bounds__(kThreads, Tune<T, S>::kPre)
 pre_backward_kernel(const SolverArgs a) {
   extern __shared__ __align__(32) unsigned char smem_raw[];
@@ -976,15 +979,15 @@ pre_backward_kernel(const SolverArgs a) {
   __syncthreads();
   Stager<T> st = make_stager<T>(acc_all, tile_all, nacc);
 
-  const T* Xg = static_cast<const T*>(a.X);
-  T* gXg = static_cast<T*>(a.gX);
+  const TIO* Xg = static_cast<const TIO*>(a.X);
+  TIO* gXg = static_cast<TIO*>(a.gX);
   const T* wsg = static_cast<const T*>(a.ws);
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long Bpad = (a.B + 31) & ~31LL;
   for (long long p0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; p0 < Bpad; p0 += stride) {
     const bool valid = p0 < a.B;
     const long long p = valid ? p0 : a.B - 1;
-    T X[3] = {Xg[3 * p], Xg[3 * p + 1], Xg[3 * p + 2]};
+    T X[3] = {(T)Xg[3 * p], (T)Xg[3 * p + 1], (T)Xg[3 * p + 2]};
     Jet<T, S> zb[NQ];
     ws_load<T, NQ, S>(wsg, a.B, 0, p, zb);
     if (!valid) {
@@ -996,7 +999,7 @@ pre_backward_kernel(const SolverArgs a) {
     pre_backward<T, NQ, S>(sw, H, X, zb, Xb, st);
     st.flush();
     if (gXg && valid) {
-      gXg[3 * p] = Xb[0]; gXg[3 * p + 1] = Xb[1]; gXg[3 * p + 2] = Xb[2];
+      gXg[3 * p] = (TIO)Xb[0]; gXg[3 * p + 1] = (TIO)Xb[1]; gXg[3 * p + 2] = (TIO)Xb[2];
     }
   }
   write_partials<T>(acc_all, nacc, static_cast<T*>(a.partials));
@@ -1144,15 +1147,18 @@ int blocks_per_sm(K kernel, size_t smem) {
     else { set_error("fused engine supports 2..4 qubits, got n=%d enc=%d", (N), (E)); return 1; } \
   } while (0)
 
+// QCP_IO(KERNEL, ...): pick the caller-facing element type (a.io_f32 => float, else T)
+#define QCP_IO_LAUNCH(KERNEL, S_, GRID, SMEM, WHAT, ARGS)                                        \
+  ((ARGS).io_f32 ? launch_checked(&KERNEL<T, NQ, ENC, S_, float>, GRID, SMEM, s, WHAT, ARGS)     \
+                 : launch_checked(&KERNEL<T, NQ, ENC, S_, T>, GRID, SMEM, s, WHAT, ARGS))
+
 template <typename T>
 int launch_solver_forward(int n, int enc, int mode, const SolverArgs& a, int grid, cudaStream_t s) {
   const size_t smem = solver_forward_smem<T>(n, enc, a.H);
   QCP_DISPATCH_NQ_ENC(n, enc, {
     if (mode == QCP_MODE_RESIDUAL)
-      return launch_checked(&solver_forward_kernel<T, NQ, ENC, 6>, grid, smem, s,
-                            "solver_forward<residual>", a);
-    return launch_checked(&solver_forward_kernel<T, NQ, ENC, 1>, grid, smem, s,
-                          "solver_forward<value>", a);
+      return QCP_IO_LAUNCH(solver_forward_kernel, 6, grid, smem, "solver_forward<residual>", a);
+    return QCP_IO_LAUNCH(solver_forward_kernel, 1, grid, smem, "solver_forward<value>", a);
   });
   return 1;
 }
@@ -1162,10 +1168,8 @@ int launch_solver_backward(int n, int enc, int mode, const SolverArgs& a, int gr
   const size_t smem = solver_backward_smem_impl<T>(n, enc, a.H);
   QCP_DISPATCH_NQ_ENC(n, enc, {
     if (mode == QCP_MODE_RESIDUAL)
-      return launch_checked(&solver_backward_kernel<T, NQ, ENC, 6>, grid, smem, s,
-                            "solver_backward<residual>", a);
-    return launch_checked(&solver_backward_kernel<T, NQ, ENC, 1>, grid, smem, s,
-                          "solver_backward<value>", a);
+      return QCP_IO_LAUNCH(solver_backward_kernel, 6, grid, smem, "solver_backward<residual>", a);
+    return QCP_IO_LAUNCH(solver_backward_kernel, 1, grid, smem, "solver_backward<value>", a);
   });
   return 1;
 }
@@ -1194,13 +1198,13 @@ int solver_split_grids(int n, int enc, int mode, int H, int num_sms, SplitGrids*
                m2 = split_smem<T>(2, n, enc, H);
   QCP_DISPATCH_NQ_ENC(n, enc, {
     if (mode == QCP_MODE_RESIDUAL) {
-      g->post = num_sms * blocks_per_sm(&post_backward_kernel<T, NQ, ENC, 6>, m0);
+      g->post = num_sms * blocks_per_sm(&post_backward_kernel<T, NQ, ENC, 6, T>, m0);
       g->contract = num_sms * blocks_per_sm(&contract_backward_kernel<T, NQ, ENC, 6>, m1);
-      g->pre = num_sms * blocks_per_sm(&pre_backward_kernel<T, NQ, ENC, 6>, m2);
+      g->pre = num_sms * blocks_per_sm(&pre_backward_kernel<T, NQ, ENC, 6, T>, m2);
     } else {
-      g->post = num_sms * blocks_per_sm(&post_backward_kernel<T, NQ, ENC, 1>, m0);
+      g->post = num_sms * blocks_per_sm(&post_backward_kernel<T, NQ, ENC, 1, T>, m0);
       g->contract = num_sms * blocks_per_sm(&contract_backward_kernel<T, NQ, ENC, 1>, m1);
-      g->pre = num_sms * blocks_per_sm(&pre_backward_kernel<T, NQ, ENC, 1>, m2);
+      g->pre = num_sms * blocks_per_sm(&pre_backward_kernel<T, NQ, ENC, 1, T>, m2);
     }
     return 0;
   });
@@ -1217,13 +1221,13 @@ int launch_solver_backward_split(int n, int enc, int mode, const SolverArgs& a, 
                m2 = split_smem<T>(2, n, enc, a.H);
   QCP_DISPATCH_NQ_ENC(n, enc, {
     if (mode == QCP_MODE_RESIDUAL) {
-      if (launch_checked(&post_backward_kernel<T, NQ, ENC, 6>, g.post, m0, s, "post_backward", a0)) return 1;
+      if (QCP_IO_LAUNCH(post_backward_kernel, 6, g.post, m0, "post_backward", a0)) return 1;
       if (launch_checked(&contract_backward_kernel<T, NQ, ENC, 6>, g.contract, m1, s, "contract_backward", a1)) return 1;
-      return launch_checked(&pre_backward_kernel<T, NQ, ENC, 6>, g.pre, m2, s, "pre_backward", a2);
+      return QCP_IO_LAUNCH(pre_backward_kernel, 6, g.pre, m2, "pre_backward", a2);
     }
-    if (launch_checked(&post_backward_kernel<T, NQ, ENC, 1>, g.post, m0, s, "post_backward", a0)) return 1;
+    if (QCP_IO_LAUNCH(post_backward_kernel, 1, g.post, m0, "post_backward", a0)) return 1;
     if (launch_checked(&contract_backward_kernel<T, NQ, ENC, 1>, g.contract, m1, s, "contract_backward", a1)) return 1;
-    return launch_checked(&pre_backward_kernel<T, NQ, ENC, 1>, g.pre, m2, s, "pre_backward", a2);
+    return QCP_IO_LAUNCH(pre_backward_kernel, 1, g.pre, m2, "pre_backward", a2);
   });
   return 1;
 }
@@ -1238,8 +1242,8 @@ int solver_backward_max_grid(int n, int enc, int mode, int H, int num_sms) {
   const size_t smem = solver_backward_smem_impl<T>(n, enc, H);
   QCP_DISPATCH_NQ_ENC(n, enc, {
     if (mode == QCP_MODE_RESIDUAL)
-      return num_sms * blocks_per_sm(&solver_backward_kernel<T, NQ, ENC, 6>, smem);
-    return num_sms * blocks_per_sm(&solver_backward_kernel<T, NQ, ENC, 1>, smem);
+      return num_sms * blocks_per_sm(&solver_backward_kernel<T, NQ, ENC, 6, T>, smem);
+    return num_sms * blocks_per_sm(&solver_backward_kernel<T, NQ, ENC, 1, T>, smem);
   });
   return num_sms;
 }

@@ -46,7 +46,7 @@ class Plan:
     """One compiled circuit on one device for one dtype."""
 
     def __init__(self, program: CircuitProgram, encoding: int, dtype: torch.dtype, hidden: int,
-                 device: torch.device):
+                 device: torch.device, io_dtype: torch.dtype | None = None):
         if dtype not in _DTYPE_CODE:
             raise ValueError(f"qcpinn_b200 supports float32/float64 plans, got {dtype}")
         self.lib = _lib.require_cuda()
@@ -77,6 +77,12 @@ class Plan:
         _lib.check(rc, "qcp_plan_create")
         self.num_features = self.lib.qcp_plan_num_features(self._handle)
         self.fused_engine = self.n <= 4      # n > 4 runs on the per-sample statevector engine
+        # element type of X / u / r / grad_u / grad_r / grad_X (weights, jets, grads stay `dtype`)
+        self.io_dtype = dtype
+        if io_dtype is not None and io_dtype != dtype and self.fused_engine and dtype == torch.float64:
+            _lib.check(self.lib.qcp_plan_set_io_dtype(self._handle, _DTYPE_CODE[io_dtype]),
+                       "qcp_plan_set_io_dtype")
+            self.io_dtype = io_dtype
 
     def __del__(self):
         h = getattr(self, "_handle", None)
@@ -95,6 +101,12 @@ class Plan:
         if x.device != self.device:
             raise RuntimeError(f"tensor on {x.device}, plan on {self.device}")
         return x.detach().to(self.dtype).contiguous()
+
+    def _io(self, x: torch.Tensor) -> torch.Tensor:
+        """Caller-facing array (X, grad_u, grad_r) in the plan's I/O dtype."""
+        if x.device != self.device:
+            raise RuntimeError(f"tensor on {x.device}, plan on {self.device}")
+        return x.detach().to(self.io_dtype).contiguous()
 
     def invalidate(self):
         self._key = None
@@ -183,9 +195,9 @@ class Plan:
 
     def solver_forward(self, X, mlp, mode, coeffs=None, want_streams=False, save=None):
         b = X.shape[0]
-        u = torch.empty(b, dtype=self.dtype, device=self.device)
-        r = torch.empty(b, dtype=self.dtype, device=self.device) if mode == MODE_RESIDUAL else None
-        streams = (torch.empty((b, 6), dtype=self.dtype, device=self.device)
+        u = torch.empty(b, dtype=self.io_dtype, device=self.device)
+        r = torch.empty(b, dtype=self.io_dtype, device=self.device) if mode == MODE_RESIDUAL else None
+        streams = (torch.empty((b, 6), dtype=self.io_dtype, device=self.device)
                    if (want_streams and mode == MODE_RESIDUAL) else None)
         c = (ctypes.c_double * 5)(*coeffs) if coeffs is not None else None
         m = self._mlp(mlp)
@@ -270,10 +282,10 @@ def solver_backward_many(plan: Plan, items, mlp, theta):
     return views, gxs
 
 
-def _grad_in(plan: Plan, g, like):
+def _grad_in(plan: Plan, g, like, io=False):
     if g is None:
         return None
-    return g.detach().to(plan.dtype).reshape(like).contiguous()
+    return g.detach().to(plan.io_dtype if io else plan.dtype).reshape(like).contiguous()
 
 
 class _LayerFn(torch.autograd.Function):
@@ -305,7 +317,7 @@ class _SolverFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, plan: Plan, key, mode, coeffs, X, theta, *mlp):
-        Xt = plan._t(X)
+        Xt = plan._io(X)
         tt, mt = plan.typed_weights(theta, mlp, key)
         plan.prepare(tt, key)
         needs_grad = any(ctx.needs_input_grad[4:])
@@ -327,8 +339,8 @@ class _SolverFn(torch.autograd.Function):
         Xt, tt, *mt = ctx.saved_tensors
         plan.prepare(tt, ctx.key)
         b = Xt.shape[0]
-        gu = _grad_in(plan, grad_u, (b,))
-        gr = _grad_in(plan, grad_r, (b,)) if ctx.mode == MODE_RESIDUAL else None
+        gu = _grad_in(plan, grad_u, (b,), io=True)
+        gr = _grad_in(plan, grad_r, (b,), io=True) if ctx.mode == MODE_RESIDUAL else None
         need_gx = ctx.needs_input_grad[4] and ctx.mode == MODE_VALUE
         views, gx = plan.solver_backward(Xt, mt, tt, gu, gr, ctx.mode, ctx.coeffs, need_gx,
                                          save=ctx.save)
@@ -377,7 +389,7 @@ class _SolverManyFn(torch.autograd.Function):
         needs_grad = any(ctx.needs_input_grad[3:])
         outs, saved = [], []
         for (mode, coeffs), X in zip(specs, Xs):
-            Xt = plan._t(X)
+            Xt = plan._io(X)
             save = plan.workspace(Xt.shape[0], mode) if (needs_grad and SAVE_JETS and Xt.shape[0]) else None
             u, r, _ = plan.solver_forward(Xt, mt, mode, coeffs, save=save)
             saved.append((Xt, save))
@@ -402,11 +414,11 @@ class _SolverManyFn(torch.autograd.Function):
         n_x = len(ctx.specs)
         for i, ((mode, coeffs), (Xt, save)) in enumerate(zip(ctx.specs, ctx.saved)):
             b = Xt.shape[0]
-            gu = _grad_in(plan, grads[gi], (b,))
+            gu = _grad_in(plan, grads[gi], (b,), io=True)
             gi += 1
             gr = None
             if mode == MODE_RESIDUAL:
-                gr = _grad_in(plan, grads[gi], (b,))
+                gr = _grad_in(plan, grads[gi], (b,), io=True)
                 gi += 1
             need_gx = ctx.needs_input_grad[3 + 1 + 8 + i] and mode == MODE_VALUE
             items.append((Xt, gu, gr, mode, coeffs, save, need_gx))
@@ -440,7 +452,7 @@ def solver_residual(plan: Plan, X, theta, mlp, coeffs, key=None):
 
 def solver_streams(plan: Plan, X, theta, mlp, coeffs=(1.0, 1.0, 1.0, -0.01, -0.01)):
     """No-grad helper for tests / evaluation: (u, r, streams[B,6])."""
-    Xt, tt = plan._t(X), plan._t(theta).reshape(-1)
+    Xt, tt = plan._io(X), plan._t(theta).reshape(-1)
     mt = [plan._t(w) for w in mlp]
     plan.prepare(tt, None)
     return plan.solver_forward(Xt, mt, MODE_RESIDUAL, tuple(coeffs), want_streams=True)

@@ -118,7 +118,10 @@ class DVPDESolver(nn.Module):
 
     def _plan(self, device) -> F.Plan:
         self._check_fused()
-        return self.quantum_layer.plan(device, hidden=self.classic_network[-2])
+        # the module's tensors are float32 (like the reference's): let a float64 plan read / write
+        # them directly instead of casting around every call
+        return self.quantum_layer.plan(device, hidden=self.classic_network[-2],
+                                       io_dtype=torch.float32)
 
     def _device_of(self, x):
         dev = self.quantum_layer.params.device

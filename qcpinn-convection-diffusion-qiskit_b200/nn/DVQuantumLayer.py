@@ -74,12 +74,12 @@ class DVQuantumLayer(nn.Module):
                 self.q_ansatz, self.num_qubits, self.num_quantum_layers, self.haar_seed1)
         return self._program
 
-    def plan(self, device, hidden=1) -> F.Plan:
-        key = (str(device), int(hidden), self.compute_dtype)
+    def plan(self, device, hidden=1, io_dtype=None) -> F.Plan:
+        key = (str(device), int(hidden), self.compute_dtype, io_dtype)
         plan = self._plans.get(key)
         if plan is None:
             plan = F.Plan(self.program, F.encoding_code(self.encoding), self.compute_dtype,
-                          hidden, torch.device(device))
+                          hidden, torch.device(device), io_dtype=io_dtype)
             self._plans[key] = plan
         return plan
 

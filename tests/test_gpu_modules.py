@@ -100,7 +100,8 @@ def test_solver_module_forward_and_residual_match_oracle(tmp_path):
     Xc = X.cpu().double()
     uo, ro = osolver.diffusion_operator(oracle, Xc[:, 0:1].clone(), Xc[:, 1:2].clone(), Xc[:, 2:3].clone())
     assert rel_err(uu, uo) < 1e-6 and rel_err(r, ro) < 1e-6
-    assert rel_err(model.taylor_streams(X), osolver.diffusion_streams(oracle, Xc)) < 1e-10
+    # the module reads / writes float32 tensors (float64 arithmetic inside): float32 rounding only
+    assert rel_err(model.taylor_streams(X), osolver.diffusion_streams(oracle, Xc)) < 1e-6
     log = open(os.path.join(model.log_path, "output.log")).read()
     assert "The circuit used in the study:" in log and "CRX[3,0] theta[8]" in log
 
