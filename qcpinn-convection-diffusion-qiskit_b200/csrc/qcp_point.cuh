@@ -61,7 +61,8 @@ struct TuneValues {
   static constexpr bool kTwoPass = kPasses != 0;
   // keep the loop over the A-half feature index rolled (9x less code, runtime-selected factors:
   // wins in float32 where the unrolled body thrashed the instruction cache; loses in float64)
-  static constexpr bool kRollA = (V % 10) != 0;
+  static constexpr int kRollMode = V % 10;   // 0: unrolled, 1: rolled, 2: outer trit rolled only
+  static constexpr bool kRollA = kRollMode != 0;
 };
 template <typename T, int S>
 struct Tune : TuneValues<1111100> {};
@@ -291,11 +292,15 @@ struct PA {
   Jet<T, S> f0, f1, p;
   int s0, s1;
   __device__ __forceinline__ void set(const AngleFeat<T, NQ, S>& f, int a) {
+    if constexpr (A::NA == 1) set2(f, a, 0);
+    else set2(f, a / 3, a % 3);
+  }
+  // (s0, s1) = trits of the first / second A-half qubit (s1 ignored when the half has one qubit)
+  __device__ __forceinline__ void set2(const AngleFeat<T, NQ, S>& f, int t0, int t1) {
+    s0 = t0; s1 = t1;
     if constexpr (A::NA == 1) {
-      s0 = a; s1 = 0;
       p = bloch_select<T, S>(s0, f.y[0], f.w[0]);
     } else {
-      s0 = a / 3; s1 = a - 3 * s0;
       f0 = bloch_select<T, S>(s0, f.y[0], f.w[0]);
       f1 = bloch_select<T, S>(s1, f.y[1], f.w[1]);
       p = jmul(f0, f1);
@@ -318,6 +323,35 @@ struct PA {
     }
   }
 };
+
+// loop over the A-half feature index a = 3*s0 + s1 (or a = s0 for a one-qubit half), rolled /
+// unrolled per Tune<>::kRollMode; body(a, s0, s1)
+template <typename T, int NQ, int S, typename Body>
+__device__ __forceinline__ void for_each_a(Body&& body) {
+  using A = AngleShape<NQ>;
+  constexpr int mode = Tune<T, (S == 1 ? 1 : 6)>::kRollMode;
+  if constexpr (A::NA == 1) {
+    if constexpr (mode == 1) {
+#pragma unroll 1
+      for (int a = 0; a < 3; ++a) body(a, a, 0);
+    } else {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) body(a, a, 0);
+    }
+  } else if constexpr (mode == 1) {
+#pragma unroll 1
+    for (int a = 0; a < 9; ++a) body(a, a / 3, a % 3);
+  } else if constexpr (mode == 2) {
+#pragma unroll 1
+    for (int t0 = 0; t0 < 3; ++t0) {
+#pragma unroll
+      for (int t1 = 0; t1 < 3; ++t1) body(3 * t0 + t1, t0, t1);
+    }
+  } else {
+#pragma unroll
+    for (int a = 0; a < 9; ++a) body(a, a / 3, a % 3);
+  }
+}
 
 template <typename T, int NQ>
 __device__ __forceinline__ void angle_sincos(const T (&z0)[NQ], T (&sn)[NQ], T (&cs)[NQ]) {
@@ -380,9 +414,9 @@ __device__ __forceinline__ void angle_contract(const T* sC, const AngleFeat<T, N
   using A = AngleShape<NQ>;
 #pragma unroll
   for (int i = 0; i < NQ; ++i) jzero(q[i]);
-  auto body = [&](int a) {
+  auto body = [&](int a, int t0, int t1) {
     PA<T, NQ, S> pa;
-    pa.set(f, a);
+    pa.set2(f, t0, t1);
 #pragma unroll
     for (int i = 0; i < NQ; ++i) {
       CRow<T, NQ> c;
@@ -391,13 +425,7 @@ __device__ __forceinline__ void angle_contract(const T* sC, const AngleFeat<T, N
       jmul_acc(q[i], pa.p, t);
     }
   };
-  if constexpr (Tune<T, (S == 1 ? 1 : 6)>::kRollA) {
-#pragma unroll 1
-    for (int a = 0; a < A::FA; ++a) body(a);
-  } else {
-#pragma unroll
-    for (int a = 0; a < A::FA; ++a) body(a);
-  }
+  for_each_a<T, NQ, S>(body);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -538,9 +566,9 @@ __device__ __forceinline__ void angle_backward(const T* sC, const Jet<T, S> (&z)
 #pragma unroll
   for (int b = 0; b < A::FB; ++b) jzero(Qb[b]);
 
-  auto body = [&](int a) {
+  auto body = [&](int a, int t0, int t1) {
     PA<T, NQ, S> pa;
-    pa.set(f, a);
+    pa.set2(f, t0, t1);
     Jet<T, S> pab;
     jzero(pab);
 #pragma unroll
@@ -563,13 +591,7 @@ __device__ __forceinline__ void angle_backward(const T* sC, const Jet<T, S> (&z)
     }
     pa.pull(pab, yb, wb);
   };
-  if constexpr (Tune<T, (S == 1 ? 1 : 6)>::kRollA) {
-#pragma unroll 1
-    for (int a = 0; a < A::FA; ++a) body(a);
-  } else {
-#pragma unroll
-    for (int a = 0; a < A::FA; ++a) body(a);
-  }
+  for_each_a<T, NQ, S>(body);
   prod_pull<T, S, A::NB>(Qb, f.y + A::NA, f.w + A::NA, yb + A::NA, wb + A::NA);
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {
