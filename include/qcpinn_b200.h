@@ -81,6 +81,13 @@ int qcp_plan_create(qcp_plan_t** out, int n_qubits, int encoding, int dtype, int
 int qcp_plan_destroy(qcp_plan_t* plan);
 int qcp_plan_num_features(const qcp_plan_t* plan);
 
+/* Which kernels a plan runs on: QCP_ENGINE_FEATURE (n <= 4: observables pre-multiplied into a real
+ * feature matrix), QCP_ENGINE_REGISTER (5 <= n <= 10, float64: <= 9: per-sample statevectors in
+ * registers, one warp per Taylor stream) or QCP_ENGINE_GLOBAL (larger n: per-sample statevectors in
+ * shared / L2-resident global memory). */
+enum qcp_engine { QCP_ENGINE_FEATURE = 0, QCP_ENGINE_GLOBAL = 1, QCP_ENGINE_REGISTER = 2 };
+int qcp_plan_engine(const qcp_plan_t* plan);
+
 /* Element type of the caller-facing arrays of the solver entry points (X, u, r, streams, grad_u,
  * grad_r, grad_X).  Default = the plan dtype.  A QCP_F64 plan (n <= 4) may be switched to QCP_F32
  * I/O: arithmetic, weights, gradients and the saved jets stay float64, but the float32 tensors of

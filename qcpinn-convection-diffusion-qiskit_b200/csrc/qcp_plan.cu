@@ -553,6 +553,7 @@ struct qcp_plan {
   int pend_fused[kMaxPending];
   int io_f32;               // caller-facing arrays are float32 although the plan is float64
   bool engine_l;
+  RegPlan* reg;             // engine R context (5 <= n <= 10) or null => engine L kernels
   void* d_theta;            // copy of the angles taken by qcp_prepare()
   void* d_ws;               // internal saved-jet workspace (when the caller gives none)
   size_t ws_elems;
@@ -674,6 +675,11 @@ int qcp_plan_create(qcp_plan_t** out, int n_qubits, int encoding, int dtype, int
     qcp_plan_destroy(p);
     return 1;
   }
+  if (p->engine_l && reg_supported(n_qubits, dtype)) {
+    p->reg = reg_create(n_qubits, encoding, dtype, reinterpret_cast<const GateOp*>(ops), n_ops, n_theta,
+                        n_consts, p->d_ops, p->d_consts, p->num_sms);
+    if (!p->reg) { qcp_plan_destroy(p); return 1; }
+  }
   *out = p;
   return 0;
 }
@@ -683,11 +689,17 @@ int qcp_plan_destroy(qcp_plan_t* p) {
   cudaFree(p->d_ops); cudaFree(p->d_consts); cudaFree(p->d_V); cudaFree(p->d_O); cudaFree(p->d_Lam);
   cudaFree(p->d_C64); cudaFree(p->d_C); cudaFree(p->d_Cbar); cudaFree(p->d_partials);
   cudaFree(p->d_theta); cudaFree(p->d_ws); cudaFree(p->d_slab); cudaFree(p->d_theta_partials);
+  reg_destroy(p->reg);
   delete p;
   return 0;
 }
 
 int qcp_plan_num_features(const qcp_plan_t* p) { return p ? p->F : -1; }
+
+int qcp_plan_engine(const qcp_plan_t* p) {
+  if (!p) return -1;
+  return !p->engine_l ? QCP_ENGINE_FEATURE : (p->reg ? QCP_ENGINE_REGISTER : QCP_ENGINE_GLOBAL);
+}
 
 int qcp_plan_set_io_dtype(qcp_plan_t* p, int io_dtype) {
   if (!p || (io_dtype != QCP_F32 && io_dtype != QCP_F64)) { set_error("qcp_plan_set_io_dtype: bad argument"); return 1; }
@@ -708,6 +720,7 @@ int qcp_prepare(qcp_plan_t* p, const void* theta, void* stream) {
     if (p->n_theta > 0)
       QCP_CUDA(cudaMemcpyAsync(p->d_theta, theta, elem_size(p->dtype) * p->n_theta,
                                cudaMemcpyDeviceToDevice, s));
+    if (p->reg && reg_prepare(p->reg, p->d_theta, s)) return 1;
     p->prepared = true;
     return 0;
   }
@@ -802,6 +815,22 @@ static void* internal_ws(qcp_plan* p, long long B, int S) {
   return p->d_ws;
 }
 
+// the per-sample circuit stage: engine R when the plan has one, engine L otherwise.  `state` is the
+// optional saved-final-psi workspace of engine R (ignored by engine L).
+static int circuit_run(qcp_plan* p, int S, bool backward, void* ws, long long B, void* state,
+                       void* grad_theta, cudaStream_t s) {
+  if (p->reg) return reg_run(p->reg, S, backward, ws, B, state, grad_theta, s);
+  SvLaunch L{};
+  if (sv_configure(p, S, B, L)) return 1;
+  L.ws = ws; L.grad_theta = grad_theta;
+  return sv_run(p->dtype, S, backward, L, s);
+}
+
+static void* state_of(const qcp_plan* p, void* save, long long B, int mode) {
+  if (!p->reg || !save) return nullptr;
+  return static_cast<char*>(save) + elem_size(p->dtype) * 2 * (size_t)p->n * mode * (size_t)B;
+}
+
 static int mlp_grid(const qcp_plan* p, long long B, bool backward) {
   long long blocks = (B + kThreads - 1) / kThreads;
   const long long cap = (long long)p->num_sms * (backward ? 2 : 8);
@@ -840,10 +869,7 @@ int qcp_layer_forward(qcp_plan_t* p, const void* z, long long B, void* q, void* 
     const size_t es = elem_size(p->dtype);
     launch_transpose(p->dtype, z, ws, B, p->n, 1, s);
     QCP_CUDA(cudaGetLastError());
-    SvLaunch L{};
-    if (sv_configure(p, 1, B, L)) return 1;
-    L.ws = ws;
-    if (sv_run(p->dtype, 1, false, L, s)) return 1;
+    if (circuit_run(p, 1, false, ws, B, nullptr, nullptr, s)) return 1;
     // slot 1 is q in [n][B] order == the (n, B) output orientation
     QCP_CUDA(cudaMemcpyAsync(q, static_cast<char*>(ws) + es * (size_t)p->n * B, es * (size_t)p->n * B,
                              cudaMemcpyDeviceToDevice, s));
@@ -890,10 +916,7 @@ int qcp_layer_backward(qcp_plan_t* p, const void* theta, const void* z, const vo
     QCP_CUDA(cudaGetLastError());
     QCP_CUDA(cudaMemcpyAsync(static_cast<char*>(ws) + es * (size_t)p->n * B, grad_q, es * (size_t)p->n * B,
                              cudaMemcpyDeviceToDevice, s));
-    SvLaunch L{};
-    if (sv_configure(p, 1, B, L)) return 1;
-    L.ws = ws; L.grad_theta = grad_theta;
-    if (sv_run(p->dtype, 1, true, L, s)) return 1;
+    if (circuit_run(p, 1, true, ws, B, nullptr, grad_theta, s)) return 1;
     if (grad_z) {
       launch_transpose(p->dtype, ws, grad_z, B, p->n, 0, s);
       QCP_CUDA(cudaGetLastError());
@@ -934,7 +957,9 @@ static int check_mode(int mode, const double* coeffs, const char* who) {
 
 long long qcp_solver_workspace_elems(const qcp_plan_t* p, long long B, int mode) {
   if (!p || B < 0 || (mode != QCP_MODE_VALUE && mode != QCP_MODE_RESIDUAL)) return -1;
-  return 2LL * p->n * mode * B;
+  long long e = 2LL * p->n * mode * B;
+  if (p->reg) e += reg_state_elems(p->reg, B, mode);   // engine R also saves the final psi streams
+  return e;
 }
 
 int qcp_solver_forward(qcp_plan_t* p, const qcp_mlp_t* w, const void* X, long long B, int mode,
@@ -955,10 +980,7 @@ int qcp_solver_forward(qcp_plan_t* p, const qcp_mlp_t* w, const void* X, long lo
     MlpLaunch M{};
     M.n = p->n; M.H = p->H; M.grid = mlp_grid(p, B, false); M.args = a;
     if (mlp_pre_forward(p->dtype, mode, M, s)) return 1;
-    SvLaunch L{};
-    if (sv_configure(p, mode, B, L)) return 1;
-    L.ws = a.ws;
-    if (sv_run(p->dtype, mode, false, L, s)) return 1;
+    if (circuit_run(p, mode, false, a.ws, B, state_of(p, save, B, mode), nullptr, s)) return 1;
     return mlp_post_forward(p->dtype, mode, M, s);
   }
   const int grid = forward_grid(p, B);
@@ -1110,22 +1132,18 @@ int qcp_solver_backward(qcp_plan_t* p, const qcp_mlp_t* w, const void* theta, co
   if (B > 0) {
     MlpLaunch M{};
     M.n = p->n; M.H = p->H; M.args = a;
-    SvLaunch L{};
-    if (sv_configure(p, mode, B, L)) return 1;
     if (!M.args.ws) {
       // no saved jets: rebuild them (pre MLP + statevector forward) in the internal workspace
       M.args.ws = internal_ws(p, B, mode);
       if (!M.args.ws) return 1;
       M.grid = mlp_grid(p, B, false);
       if (mlp_pre_forward(p->dtype, mode, M, s)) return 1;
-      L.ws = M.args.ws;
-      if (sv_run(p->dtype, mode, false, L, s)) return 1;
+      if (circuit_run(p, mode, false, M.args.ws, B, nullptr, nullptr, s)) return 1;
     }
-    L.ws = M.args.ws; L.grad_theta = grad_theta;
     M.grid = gb;
     M.args.partials = p0;
     if (mlp_post_backward(p->dtype, mode, M, s)) return 1;
-    if (sv_run(p->dtype, mode, true, L, s)) return 1;
+    if (circuit_run(p, mode, true, M.args.ws, B, state_of(p, save, B, mode), grad_theta, s)) return 1;
     M.args.partials = p2;
     if (mlp_pre_backward(p->dtype, mode, M, s)) return 1;
   } else {

@@ -1,0 +1,353 @@
+// qcpinn_b200 -- engine R host side: physical-program compiler, phase-table builder, gradient
+// projection of the diagonal blocks, launch plumbing.  Device code: qcp_reg.cuh.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "qcp_reg.cuh"
+
+namespace qcp {
+
+using namespace rg;
+
+// ---------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------
+struct BlkPos {
+  int32_t pos[kMaxQubitsReg];
+};
+
+// phase tables of the diagonal blocks: D[(blk << n) + i * G + lane] = exp(i * sum_g angle_g(k)),
+// RZ(t) = diag(e^{-it/2}, e^{+it/2}), CRZ likewise on the control = 1 half
+template <typename T>
+__global__ void rg_diag_build_kernel(int n, int LB, int n_blk, const BlkPos* __restrict__ bpos,
+                                     const DiagGate* __restrict__ dg, int n_dg,
+                                     const T* __restrict__ theta, C2A<T>* __restrict__ out) {
+  const int G = 1 << (n - LB);
+  const int total = n_blk << n;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int blk = idx >> n, e = idx & ((1 << n) - 1);
+    const int phys = ((e % G) << LB) | (e / G);
+    const BlkPos bp = bpos[blk];
+    double ang = 0.0;
+    for (int g = 0; g < n_dg; ++g) {
+      const DiagGate d = dg[g];
+      if (d.blk != blk) continue;
+      const double half = 0.5 * (double)theta[d.p];
+      if (d.kind == QCP_GATE_RZ) {
+        ang += ((phys >> bp.pos[d.a]) & 1) ? half : -half;
+      } else if ((phys >> bp.pos[d.a]) & 1) {
+        ang += ((phys >> bp.pos[d.b]) & 1) ? half : -half;
+      }
+    }
+    double s, c;
+    sincos(ang, &s, &c);
+    out[idx] = {(T)c, (T)s};
+  }
+}
+
+template <typename T>
+__global__ void rg_reduce_theta_kernel(const double* __restrict__ partials, int grid, int n_theta,
+                                       T* __restrict__ gtheta) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_theta) return;
+  double s = 0.0;
+  for (int g = 0; g < grid; ++g) s += partials[(size_t)g * n_theta + p];
+  gtheta[p] = (T)s;
+}
+
+template <typename T>
+__global__ void rg_wsum_kernel(const T* __restrict__ wpart, int grid, int total, double* __restrict__ wsum) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= total) return;
+  double s = 0.0;
+  for (int g = 0; g < grid; ++g) s += (double)wpart[(size_t)g * total + j];
+  wsum[j] = s;
+}
+
+// dL/dtheta_g = 1/2 sum_k z_g(k) W_blk[k], z_g = eigenvalue of the generator (Z, or |1><1| (x) Z)
+template <typename T>
+__global__ void rg_diag_grad_kernel(int n, int LB, const BlkPos* __restrict__ bpos,
+                                    const DiagGate* __restrict__ dg, const double* __restrict__ wsum,
+                                    T* __restrict__ gtheta) {
+  __shared__ double red[8];
+  const DiagGate d = dg[blockIdx.x];
+  const BlkPos bp = bpos[d.blk];
+  const int G = 1 << (n - LB);
+  double acc = 0.0;
+  for (int e = threadIdx.x; e < (1 << n); e += blockDim.x) {
+    const int phys = ((e % G) << LB) | (e / G);
+    double z;
+    if (d.kind == QCP_GATE_RZ) z = ((phys >> bp.pos[d.a]) & 1) ? -1.0 : 1.0;
+    else z = ((phys >> bp.pos[d.a]) & 1) ? (((phys >> bp.pos[d.b]) & 1) ? -1.0 : 1.0) : 0.0;
+    acc += z * wsum[((size_t)d.blk << n) + e];
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    gtheta[d.p] = (T)(0.5 * s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
+struct RegPlan {
+  int n, enc, dtype, LB, G, n_gates, n_theta, n_consts, n_rops, n_blk, n_dg, num_sms;
+  int meas_pos[kMaxQubitsReg];
+  ROp* d_rops;
+  const GateOp* d_gates;      // borrowed from the owning plan
+  const double2* d_consts;    // borrowed
+  BlkPos* d_bpos;
+  DiagGate* d_dg;
+  void* d_diag;
+  void* d_wpart;
+  size_t wpart_bytes;
+  double* d_wsum;
+  double* d_tpart;
+  size_t tpart_bytes;
+  int occ[2][2];              // blocks/SM cache [S == 6][backward]
+  const void* theta;          // device copy owned by the plan (set by reg_prepare)
+};
+
+static size_t es_of(int dtype) { return dtype == QCP_F64 ? 8 : 4; }
+
+static bool is_diag(int kind) { return kind == QCP_GATE_RZ || kind == QCP_GATE_CRZ; }
+
+int reg_supported(int n, int dtype) {
+  const char* env = std::getenv("QCP_ENGINE");
+  if (env && (env[0] == 'L' || env[0] == 'l')) return 0;
+  if (n < 5) return 0;
+  return dtype == QCP_F64 ? n <= 9 : n <= kMaxQubitsReg;
+}
+
+// Translate the logical gate list into physical ops (see the header comment of qcp_reg.cuh).
+static void compile_physical(const GateOp* ops, int n_ops, int n, int LB, std::vector<ROp>& rops,
+                             std::vector<BlkPos>& bpos, std::vector<DiagGate>& dgs, int* meas_pos) {
+  std::vector<int> pos(n), qat(n);
+  for (int q = 0; q < n; ++q) { pos[q] = n - 1 - q; qat[n - 1 - q] = q; }
+  auto dense_target = [&](const GateOp& g, int q) {
+    switch (g.kind) {
+      case QCP_GATE_RX: case QCP_GATE_RY: case QCP_GATE_H: return g.a == q;
+      case QCP_GATE_CRX: case QCP_GATE_CNOT: return g.b == q;
+      case QCP_GATE_U4: return g.a == q || g.b == q;
+      default: return false;
+    }
+  };
+  auto next_use = [&](int q, int from) {
+    for (int g = from; g < n_ops; ++g)
+      if (dense_target(ops[g], q)) return g;
+    return n_ops + 1;
+  };
+  auto emit_swap = [&](int local, int lane) {
+    rops.push_back({R_SWAP, local, lane, 0, 0, -1});
+    const int ql = qat[local], qn = qat[lane];
+    qat[local] = qn; qat[lane] = ql;
+    pos[qn] = local; pos[ql] = lane;
+  };
+  auto make_local = [&](int q, int g_cur) {
+    if (pos[q] < LB) return;
+    int best = 0, best_use = -1;
+    for (int x = 0; x < LB; ++x) {
+      const int u = next_use(qat[x], g_cur + 1);
+      if (u > best_use) { best_use = u; best = x; }
+    }
+    emit_swap(best, pos[q]);
+  };
+  auto move_to = [&](int q, int X) {
+    if (pos[q] == X) return;
+    if (pos[q] >= LB) { emit_swap(X, pos[q]); return; }
+    const int Y = pos[q], Z = LB;   // hop through the first lane position
+    emit_swap(Y, Z);
+    emit_swap(X, Z);
+  };
+
+  int open = -1;
+  unsigned dirty = 0;
+  for (int g = 0; g < n_ops; ++g) {
+    const GateOp op = ops[g];
+    if (is_diag(op.kind)) {
+      unsigned qs = 1u << op.a;
+      if (op.kind == QCP_GATE_CRZ) qs |= 1u << op.b;
+      if (open < 0 || (qs & dirty)) {
+        open = (int)bpos.size();
+        BlkPos bp{};
+        for (int q = 0; q < n; ++q) bp.pos[q] = pos[q];
+        bpos.push_back(bp);
+        dirty = 0;
+        rops.push_back({R_DIAG, 0, -1, 0, open, -1});
+      }
+      dgs.push_back({open, op.kind, op.a, op.b, op.p});
+      continue;
+    }
+    dirty |= 1u << op.a;
+    if (op.b >= 0) dirty |= 1u << op.b;
+    switch (op.kind) {
+      case QCP_GATE_RX: case QCP_GATE_RY: case QCP_GATE_H:
+        make_local(op.a, g);
+        rops.push_back({R_L1, pos[op.a], -1, op.kind == QCP_GATE_RX ? T_X : T_R, g,
+                        op.kind == QCP_GATE_H ? -1 : op.p});
+        break;
+      case QCP_GATE_CRX:
+        make_local(op.b, g);
+        rops.push_back({R_L1, pos[op.b], pos[op.a], T_X, g, op.p});
+        break;
+      case QCP_GATE_CNOT:
+        make_local(op.b, g);
+        rops.push_back({R_CX, pos[op.b], pos[op.a], 0, g, -1});
+        break;
+      default:   // U4 on (wire_hi = a, wire_lo = b): local positions (1, 0)
+        move_to(op.a, 1);
+        move_to(op.b, 0);
+        rops.push_back({R_U4, 0, -1, 0, op.p, -1});
+        break;
+    }
+  }
+  for (int q = 0; q < n; ++q) meas_pos[q] = pos[q];
+}
+
+RegPlan* reg_create(int n, int enc, int dtype, const GateOp* host_ops, int n_ops, int n_theta,
+                    int n_consts, const GateOp* d_ops, const double2* d_consts, int num_sms) {
+  if (!reg_supported(n, dtype)) return nullptr;
+  RegPlan* r = new RegPlan();
+  memset(r, 0, sizeof(*r));
+  r->n = n; r->enc = enc; r->dtype = dtype; r->n_gates = n_ops; r->n_theta = n_theta;
+  r->n_consts = n_consts; r->num_sms = num_sms;
+  const int lbmax = dtype == QCP_F64 ? 4 : 5;
+  r->LB = n - 1 < lbmax ? n - 1 : lbmax;
+  r->G = 1 << (n - r->LB);
+  r->d_gates = d_ops; r->d_consts = d_consts;
+  std::vector<ROp> rops;
+  std::vector<BlkPos> bpos;
+  std::vector<DiagGate> dgs;
+  compile_physical(host_ops, n_ops, n, r->LB, rops, bpos, dgs, r->meas_pos);
+  r->n_rops = (int)rops.size(); r->n_blk = (int)bpos.size(); r->n_dg = (int)dgs.size();
+  const size_t es = es_of(dtype);
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes ? bytes : 16); };
+  alloc((void**)&r->d_rops, sizeof(ROp) * rops.size());
+  alloc((void**)&r->d_bpos, sizeof(BlkPos) * bpos.size());
+  alloc((void**)&r->d_dg, sizeof(DiagGate) * dgs.size());
+  alloc(&r->d_diag, 2 * es * ((size_t)r->n_blk << n));
+  alloc((void**)&r->d_wsum, sizeof(double) * ((size_t)r->n_blk << n));
+  auto put = [&](void* dst, const void* src, size_t bytes) {
+    if (e == cudaSuccess && bytes) e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+  };
+  put(r->d_rops, rops.data(), sizeof(ROp) * rops.size());
+  put(r->d_bpos, bpos.data(), sizeof(BlkPos) * bpos.size());
+  put(r->d_dg, dgs.data(), sizeof(DiagGate) * dgs.size());
+  if (e != cudaSuccess) {
+    set_error("engine R: CUDA allocation/copy failed: %s", cudaGetErrorString(e));
+    reg_destroy(r);
+    return nullptr;
+  }
+  return r;
+}
+
+void reg_destroy(RegPlan* r) {
+  if (!r) return;
+  cudaFree(r->d_rops); cudaFree(r->d_bpos); cudaFree(r->d_dg); cudaFree(r->d_diag);
+  cudaFree(r->d_wpart); cudaFree(r->d_wsum); cudaFree(r->d_tpart);
+  delete r;
+}
+
+int reg_prepare(RegPlan* r, const void* d_theta, cudaStream_t s) {
+  r->theta = d_theta;
+  if (r->n_blk == 0) return 0;
+  const int total = r->n_blk << r->n;
+  const int blocks = (total + 255) / 256;
+  if (r->dtype == QCP_F64)
+    rg_diag_build_kernel<double><<<blocks, 256, 0, s>>>(r->n, r->LB, r->n_blk, r->d_bpos, r->d_dg, r->n_dg,
+        static_cast<const double*>(d_theta), static_cast<C2A<double>*>(r->d_diag));
+  else
+    rg_diag_build_kernel<float><<<blocks, 256, 0, s>>>(r->n, r->LB, r->n_blk, r->d_bpos, r->d_dg, r->n_dg,
+        static_cast<const float*>(d_theta), static_cast<C2A<float>*>(r->d_diag));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("engine R: table build launch failed: %s", cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+
+long long reg_state_elems(const RegPlan* r, long long B, int S) {
+  return 2LL * S * B << r->n;
+}
+
+int reg_launch_count(const RegPlan* r, bool backward) {
+  if (!backward) return 1;
+  return r->n_blk > 0 ? 4 : 2;
+}
+
+static int grow(void** ptr, size_t* have, size_t want) {
+  if (want <= *have) return 0;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr; *have = 0;
+  cudaError_t e = cudaMalloc(ptr, want);
+  if (e != cudaSuccess) { set_error("engine R: cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); return 1; }
+  *have = want;
+  return 0;
+}
+
+int reg_run(RegPlan* r, int S, bool backward, void* ws, long long B, void* state, void* grad_theta,
+            cudaStream_t s) {
+  if (S != 1 && S != 6) { set_error("engine R: bad stream count %d", S); return 1; }
+  if (!r->theta && r->n_theta > 0) { set_error("engine R: qcp_prepare() has not run"); return 1; }
+  const size_t es = es_of(r->dtype);
+  const SmemLayout L = rg_layout(es, r->LB, S, r->n, r->n_rops, r->n_gates, r->n_consts, r->n_theta,
+                                 r->n_blk, backward);
+  if (L.total > 227 * 1024) {
+    set_error("engine R: gate program needs %zu bytes of shared memory", L.total);
+    return 1;
+  }
+  int& occ = r->occ[S == 6][backward];
+  if (occ == 0) {
+    const int rc = r->dtype == QCP_F64 ? rg_occupancy<double>(r->LB, S, backward, L.total, &occ)
+                                       : rg_occupancy<float>(r->LB, S, backward, L.total, &occ);
+    if (rc || occ < 1) { set_error("engine R: kernel does not fit on an SM (smem %zu)", L.total); occ = 0; return 1; }
+  }
+  const int PP = 32 / r->G, NPT = S == 6 ? PP : rg_warps(S) * PP;
+  long long want = (B + NPT - 1) / NPT;
+  int grid = r->num_sms * occ;
+  if ((long long)grid > want) grid = (int)want;
+  if (grid < 1) grid = 1;
+
+  RgArgs a{};
+  a.n = r->n; a.enc = r->enc; a.n_rops = r->n_rops; a.n_gates = r->n_gates; a.n_theta = r->n_theta;
+  a.n_blk = r->n_blk; a.n_consts = r->n_consts;
+  for (int q = 0; q < r->n; ++q) a.meas_pos[q] = r->meas_pos[q];
+  a.rops = r->d_rops; a.gates = r->d_gates; a.consts = r->d_consts; a.theta = r->theta;
+  a.diag = r->d_diag; a.ws = ws; a.B = B; a.state = state;
+  if (backward) {
+    const int nt = r->n_theta > 0 ? r->n_theta : 1;
+    if (grow((void**)&r->d_tpart, &r->tpart_bytes, sizeof(double) * (size_t)grid * nt)) return 1;
+    if (grow(&r->d_wpart, &r->wpart_bytes, es * ((size_t)grid * (r->n_blk > 0 ? r->n_blk : 1) << r->n))) return 1;
+    a.theta_partials = r->d_tpart;
+    a.w_partials = r->d_wpart;
+  }
+  const int rc = r->dtype == QCP_F64 ? rg_launch<double>(r->LB, S, backward, a, grid, L.total, s)
+                                     : rg_launch<float>(r->LB, S, backward, a, grid, L.total, s);
+  if (rc) return rc;
+  if (!backward) return 0;
+
+  const int tb = (r->n_theta + 127) / 128;
+  const int total = r->n_blk << r->n;
+  if (r->dtype == QCP_F64) {
+    if (tb) rg_reduce_theta_kernel<double><<<tb, 128, 0, s>>>(r->d_tpart, grid, r->n_theta, static_cast<double*>(grad_theta));
+    if (total) {
+      rg_wsum_kernel<double><<<(total + 127) / 128, 128, 0, s>>>(static_cast<const double*>(r->d_wpart), grid, total, r->d_wsum);
+      rg_diag_grad_kernel<double><<<r->n_dg, 256, 0, s>>>(r->n, r->LB, r->d_bpos, r->d_dg, r->d_wsum, static_cast<double*>(grad_theta));
+    }
+  } else {
+    if (tb) rg_reduce_theta_kernel<float><<<tb, 128, 0, s>>>(r->d_tpart, grid, r->n_theta, static_cast<float*>(grad_theta));
+    if (total) {
+      rg_wsum_kernel<float><<<(total + 127) / 128, 128, 0, s>>>(static_cast<const float*>(r->d_wpart), grid, total, r->d_wsum);
+      rg_diag_grad_kernel<float><<<r->n_dg, 256, 0, s>>>(r->n, r->LB, r->d_bpos, r->d_dg, r->d_wsum, static_cast<float*>(grad_theta));
+    }
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("engine R: reduction launch failed: %s", cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+
+}  // namespace qcp

@@ -1,0 +1,28 @@
+// qcpinn_b200 -- engine R kernels, float64 / complex128 instantiations (see qcp_reg.cuh).
+#include "qcp_reg.cuh"
+
+namespace qcp {
+namespace rg {
+
+template <>
+int rg_launch<double>(int LB, int S, bool backward, const RgArgs& a, int grid, size_t smem, cudaStream_t s) {
+#define RG_CALL(K, T, LBV, SV) rg_launch_one(&K<T, LBV, SV>, a, grid, rg_warps(SV) * 32, smem, s, #K)
+  
+  RG_INSTANTIATE(double, 4)
+#undef RG_CALL
+  set_error("engine R: no float64 kernel for %d local bits", LB);
+  return 1;
+}
+
+template <>
+int rg_occupancy<double>(int LB, int S, bool backward, size_t smem, int* blocks_per_sm) {
+#define RG_CALL(K, T, LBV, SV) rg_occ_one(&K<T, LBV, SV>, rg_warps(SV) * 32, smem, blocks_per_sm)
+  
+  RG_INSTANTIATE(double, 4)
+#undef RG_CALL
+  *blocks_per_sm = 0;
+  return 1;
+}
+
+}  // namespace rg
+}  // namespace qcp

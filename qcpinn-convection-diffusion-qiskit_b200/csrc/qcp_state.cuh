@@ -6,6 +6,7 @@
 namespace qcp {
 
 constexpr int kMaxQubitsSv = 16;      // largest statevector engine L handles (2^16 amplitudes)
+constexpr int kMaxQubitsReg = 10;     // largest statevector engine R keeps in registers (qcp_reg.cuh)
 
 struct SvLaunch {
   int n, enc, n_ops, n_theta, grid;
@@ -22,6 +23,17 @@ struct SvLaunch {
 size_t sv_state_bytes_rt(int dtype, int n, int S);
 size_t sv_fixed_smem_rt(int dtype, int n, int S, int n_ops, int n_theta);
 int sv_run(int dtype, int S, bool backward, const SvLaunch& L, cudaStream_t s);
+
+// engine R (qcp_reg.cu): register-resident statevectors for 5 <= n <= 10 (float64: <= 9)
+struct RegPlan;
+int reg_supported(int n, int dtype);
+RegPlan* reg_create(int n, int enc, int dtype, const GateOp* host_ops, int n_ops, int n_theta,
+                    int n_consts, const GateOp* d_ops, const double2* d_consts, int num_sms);
+void reg_destroy(RegPlan* r);
+int reg_prepare(RegPlan* r, const void* d_theta, cudaStream_t s);       // phase tables of the diagonal blocks
+long long reg_state_elems(const RegPlan* r, long long B, int S);       // saved final psi, elements of T
+int reg_run(RegPlan* r, int S, bool backward, void* ws, long long B, void* state, void* grad_theta,
+            cudaStream_t s);
 
 // generic-n MLP stages (one thread per point, jets through the workspace)
 struct MlpLaunch {

@@ -22,6 +22,14 @@ CASES = [
     ("cross_mesh", 5, 1, "angle", None),
     ("cascade", 6, 1, "amplitude", 1),
     ("cross_mesh", 5, 2, "amplitude", None),
+    # larger registers-resident shapes (engine R: lane/local swaps, diagonal blocks, Haar hops);
+    # float64 n = 10 runs on engine L
+    ("cross_mesh", 10, 2, "angle", None),
+    ("sim_circ_15", 8, 1, "angle", 1),
+    ("layered", 9, 1, "angle", None),
+    ("cascade", 7, 1, "amplitude", None),
+    ("farhi", 10, 1, "angle", 1),
+    ("alternate", 7, 1, "angle", None),
 ]
 DTYPES = [torch.float64, torch.float32]
 
@@ -43,6 +51,8 @@ def test_layer_forward_backward(case, dtype):
     (qo * cot).sum().backward()
 
     plan = F.Plan(prog, F.encoding_code(enc), dtype, 50, DEV)
+    reg_max = 10 if dtype == torch.float32 else 9
+    assert plan.engine == ("register" if n <= reg_max else "global")
     zd = z.to(DEV, dtype).requires_grad_(True)
     th = w["theta"].to(DEV, dtype).requires_grad_(True)
     qd = F.layer_apply(plan, zd, th)
