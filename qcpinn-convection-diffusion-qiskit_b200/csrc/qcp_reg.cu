@@ -143,7 +143,7 @@ static void compile_physical(const GateOp* ops, int n_ops, int n, int LB, std::v
     return n_ops + 1;
   };
   auto emit_swap = [&](int local, int lane) {
-    rops.push_back({R_SWAP, local, lane, 0, 0, -1});
+    rops.push_back({R_SWAP, local, lane, 0, 0, -1, 0, 0});
     const int ql = qat[local], qn = qat[lane];
     qat[local] = qn; qat[lane] = ql;
     pos[qn] = local; pos[ql] = lane;
@@ -165,6 +165,16 @@ static void compile_physical(const GateOp* ops, int n_ops, int n, int LB, std::v
     emit_swap(X, Z);
   };
 
+  // pairs h (target bit removed) whose amplitudes have the LOCAL control bit set
+  auto pair_mask = [&](int pt, int pc) {
+    if (pc >= LB) return 0;
+    int m = 0;
+    for (int h = 0; h < (1 << (LB - 1)); ++h) {
+      const int i0 = ((h >> pt) << (pt + 1)) | (h & ((1 << pt) - 1));
+      if ((i0 >> pc) & 1) m |= 1 << h;
+    }
+    return m;
+  };
   int open = -1;
   unsigned dirty = 0;
   for (int g = 0; g < n_ops; ++g) {
@@ -178,7 +188,7 @@ static void compile_physical(const GateOp* ops, int n_ops, int n, int LB, std::v
         for (int q = 0; q < n; ++q) bp.pos[q] = pos[q];
         bpos.push_back(bp);
         dirty = 0;
-        rops.push_back({R_DIAG, 0, -1, 0, open, -1});
+        rops.push_back({R_DIAG, 0, -1, 0, open, -1, 0, 0});
       }
       dgs.push_back({open, op.kind, op.a, op.b, op.p});
       continue;
@@ -189,20 +199,20 @@ static void compile_physical(const GateOp* ops, int n_ops, int n, int LB, std::v
       case QCP_GATE_RX: case QCP_GATE_RY: case QCP_GATE_H:
         make_local(op.a, g);
         rops.push_back({R_L1, pos[op.a], -1, op.kind == QCP_GATE_RX ? T_X : T_R, g,
-                        op.kind == QCP_GATE_H ? -1 : op.p});
+                        op.kind == QCP_GATE_H ? -1 : op.p, 0, 0});
         break;
       case QCP_GATE_CRX:
         make_local(op.b, g);
-        rops.push_back({R_L1, pos[op.b], pos[op.a], T_X, g, op.p});
+        rops.push_back({R_L1, pos[op.b], pos[op.a], T_X, g, op.p, pair_mask(pos[op.b], pos[op.a]), 0});
         break;
       case QCP_GATE_CNOT:
         make_local(op.b, g);
-        rops.push_back({R_CX, pos[op.b], pos[op.a], 0, g, -1});
+        rops.push_back({R_CX, pos[op.b], pos[op.a], 0, g, -1, pair_mask(pos[op.b], pos[op.a]), 0});
         break;
       default:   // U4 on (wire_hi = a, wire_lo = b): local positions (1, 0)
         move_to(op.a, 1);
         move_to(op.b, 0);
-        rops.push_back({R_U4, 0, -1, 0, op.p, -1});
+        rops.push_back({R_U4, 0, -1, 0, op.p, -1, 0, 0});
         break;
     }
   }
@@ -297,14 +307,14 @@ int reg_run(RegPlan* r, int S, bool backward, void* ws, long long B, void* state
   const SmemLayout L = rg_layout(es, r->LB, S, r->n, r->n_rops, r->n_gates, r->n_consts, r->n_theta,
                                  r->n_blk, backward);
   if (L.total > 227 * 1024) {
-    set_error("engine R: gate program needs %zu bytes of shared memory", L.total);
+    set_error("engine R: gate program needs %d bytes of shared memory", L.total);
     return 1;
   }
   int& occ = r->occ[S == 6][backward];
   if (occ == 0) {
     const int rc = r->dtype == QCP_F64 ? rg_occupancy<double>(r->LB, S, backward, L.total, &occ)
                                        : rg_occupancy<float>(r->LB, S, backward, L.total, &occ);
-    if (rc || occ < 1) { set_error("engine R: kernel does not fit on an SM (smem %zu)", L.total); occ = 0; return 1; }
+    if (rc || occ < 1) { set_error("engine R: kernel does not fit on an SM (smem %d)", L.total); occ = 0; return 1; }
   }
   const int PP = 32 / r->G, NPT = S == 6 ? PP : rg_warps(S) * PP;
   long long want = (B + NPT - 1) / NPT;
@@ -313,6 +323,7 @@ int reg_run(RegPlan* r, int S, bool backward, void* ws, long long B, void* state
   if (grid < 1) grid = 1;
 
   RgArgs a{};
+  a.lay = L;
   a.n = r->n; a.enc = r->enc; a.n_rops = r->n_rops; a.n_gates = r->n_gates; a.n_theta = r->n_theta;
   a.n_blk = r->n_blk; a.n_consts = r->n_consts;
   for (int q = 0; q < r->n; ++q) a.meas_pos[q] = r->meas_pos[q];

@@ -46,13 +46,21 @@ struct ROp {
   int32_t type;   // L1: RType
   int32_t g;      // L1: original gate index (coefficient table)  DIAG: block  U4: const index
   int32_t p;      // L1: theta index for the gradient or -1
+  int32_t m;      // L1/CX with a LOCAL control: bit h set = pair h (target bit removed) is active
+  int32_t pad;
 };
 
 struct DiagGate {   // one diagonal gate of a block (table builder + gradient projection)
   int32_t blk, kind, a, b, p;
 };
 
+// shared-memory carve-up (byte offsets; computed on the host, read from the constant bank)
+struct SmemLayout {
+  int rops, cs, u4, zj, qj, rj, tab, exch, atab, tabbar, rbar, gth, wacc, total;
+};
+
 struct RgArgs {
+  SmemLayout lay;
   int n, enc, n_rops, n_gates, n_theta, n_blk, n_consts;
   int meas_pos[kMaxQubitsReg];   // final position of logical qubit q
   const ROp* rops;
@@ -84,18 +92,14 @@ __host__ __device__ constexpr int rg_warps(int S) { return S == 6 ? 6 : 4; }
 // ---------------------------------------------------------------------------------------------
 // shared-memory carve-up (identical on host and device)
 // ---------------------------------------------------------------------------------------------
-struct SmemLayout {
-  size_t rops, cs, u4, zj, qj, rj, tab, exch, atab, tabbar, rbar, gth, wacc, total;
-};
-
-__host__ __device__ inline size_t rg_align(size_t v) { return (v + 15) & ~size_t(15); }
+__host__ __device__ inline int rg_align(size_t v) { return (int)((v + 15) & ~size_t(15)); }
 
 __host__ __device__ inline SmemLayout rg_layout(size_t es, int LB, int S, int n, int n_rops, int n_gates,
                                                 int n_consts, int n_theta, int n_blk, bool backward) {
   const int NA = 1 << LB, G = 1 << (n - LB), PP = 32 / G, NW = rg_warps(S);
   const int NPT = S == 6 ? PP : NW * PP;
   SmemLayout L{};
-  size_t o = 0;
+  int o = 0;
   L.rops = o; o = rg_align(o + sizeof(ROp) * (size_t)n_rops);
   L.cs = o; o = rg_align(o + es * 4 * (size_t)n_gates);
   L.u4 = o; o = rg_align(o + es * 32 * (size_t)n_consts);
@@ -119,31 +123,56 @@ __host__ __device__ inline SmemLayout rg_layout(size_t es, int LB, int S, int n,
 // ---------------------------------------------------------------------------------------------
 // register-level gate primitives.  PT = local target position (compile time), NA = 2^LB.
 // ---------------------------------------------------------------------------------------------
+// resident CTAs per SM the register allocation is bounded for (S = 6: 192 threads, S = 1: 128)
+#ifndef RG_MINB_F6
+#define RG_MINB_F6 3
+#endif
+#ifndef RG_MINB_B6
+#define RG_MINB_B6 2
+#endif
+#ifndef RG_MINB_F1
+#define RG_MINB_F1 4
+#endif
+#ifndef RG_MINB_B1
+#define RG_MINB_B1 3
+#endif
+__host__ __device__ constexpr int rg_min_blocks(int S, bool backward) {
+  return S == 6 ? (backward ? RG_MINB_B6 : RG_MINB_F6) : (backward ? RG_MINB_B1 : RG_MINB_F1);
+}
+
 #define RG_PAIR(h, PT) \
   const int i0 = (((h) >> (PT)) << ((PT) + 1)) | ((h) & ((1 << (PT)) - 1)), i1 = i0 | (1 << (PT))
 
+// Controlled gates with a LANE control are a per-lane predicate around the plain variant; with a
+// LOCAL control the host precomputes cmask (bit h = pair h is active) and the MASKED variant
+// selects identity coefficients for the inactive pairs -- no per-(target, control) code variants.
+
 // dense one-qubit gate on a local position.  m = (c, s, -, -) for T_X, (m00, m01, m10, m11) for T_R
-// (already daggered by the caller when un-applying).  pcl = local control position or -1.
-template <typename T, int LB, int PT>
+// (already daggered by the caller when un-applying).
+template <typename T, int LB, int PT, bool MASKED>
 __device__ __forceinline__ void l1_apply(T (&ax)[1 << LB], T (&ay)[1 << LB], int type, T m0, T m1,
-                                         T m2, T m3, int pcl) {
+                                         T m2, T m3, unsigned cmask) {
   constexpr int NA = 1 << LB;
-  if (type == T_X) {
+  if (MASKED || type == T_X) {     // only RX-like gates are ever controlled (CRX)
 #pragma unroll
     for (int h = 0; h < NA / 2; ++h) {
       RG_PAIR(h, PT);
-      if (pcl >= 0 && !((i0 >> pcl) & 1)) continue;
+      T c = m0, s = m1;
+      if constexpr (MASKED) {
+        const bool act = (cmask >> h) & 1;
+        c = act ? m0 : T(1);
+        s = act ? m1 : T(0);
+      }
       const T x0 = ax[i0], y0 = ay[i0], x1 = ax[i1], y1 = ay[i1];
-      ax[i0] = fma(m0, x0, m1 * y1);
-      ay[i0] = fma(m0, y0, -m1 * x1);
-      ax[i1] = fma(m0, x1, m1 * y0);
-      ay[i1] = fma(m0, y1, -m1 * x0);
+      ax[i0] = fma(c, x0, s * y1);
+      ay[i0] = fma(c, y0, -s * x1);
+      ax[i1] = fma(c, x1, s * y0);
+      ay[i1] = fma(c, y1, -s * x0);
     }
   } else {
 #pragma unroll
     for (int h = 0; h < NA / 2; ++h) {
       RG_PAIR(h, PT);
-      if (pcl >= 0 && !((i0 >> pcl) & 1)) continue;
       const T x0 = ax[i0], y0 = ay[i0], x1 = ax[i1], y1 = ay[i1];
       ax[i0] = fma(m0, x0, m1 * x1);
       ay[i0] = fma(m0, y0, m1 * y1);
@@ -155,59 +184,70 @@ __device__ __forceinline__ void l1_apply(T (&ax)[1 << LB], T (&ay)[1 << LB], int
 
 // generator expectation Im<lambda|H|psi> over this lane's pairs (both vectors AFTER the gate):
 // H = X for T_X (RX, CRX), H = Y for T_R (RY)
-template <typename T, int LB, int PT>
+template <typename T, int LB, int PT, bool MASKED>
 __device__ __forceinline__ T l1_grad(const T (&ax)[1 << LB], const T (&ay)[1 << LB],
                                      const T (&lx)[1 << LB], const T (&ly)[1 << LB], int type,
-                                     int pcl) {
+                                     unsigned cmask) {
   constexpr int NA = 1 << LB;
-  T part = T(0);
-  if (type == T_X) {
+  T p0 = T(0), p1 = T(0);
+  if (MASKED || type == T_X) {
 #pragma unroll
     for (int h = 0; h < NA / 2; ++h) {
       RG_PAIR(h, PT);
-      if (pcl >= 0 && !((i0 >> pcl) & 1)) continue;
-      part = fma(lx[i0], ay[i1], part);
-      part = fma(-ly[i0], ax[i1], part);
-      part = fma(lx[i1], ay[i0], part);
-      part = fma(-ly[i1], ax[i0], part);
+      if constexpr (MASKED) {
+        const bool act = (cmask >> h) & 1;
+        const T t0 = fma(lx[i0], ay[i1], lx[i1] * ay[i0]);
+        const T t1 = fma(ly[i0], ax[i1], ly[i1] * ax[i0]);
+        p0 += act ? t0 : T(0);
+        p1 += act ? t1 : T(0);
+      } else {
+        p0 = fma(lx[i0], ay[i1], p0);
+        p1 = fma(ly[i0], ax[i1], p1);
+        p0 = fma(lx[i1], ay[i0], p0);
+        p1 = fma(ly[i1], ax[i0], p1);
+      }
     }
-  } else {
+  } else if constexpr (!MASKED) {
 #pragma unroll
     for (int h = 0; h < NA / 2; ++h) {
       RG_PAIR(h, PT);
-      if (pcl >= 0 && !((i0 >> pcl) & 1)) continue;
-      part = fma(-lx[i0], ax[i1], part);
-      part = fma(-ly[i0], ay[i1], part);
-      part = fma(lx[i1], ax[i0], part);
-      part = fma(ly[i1], ay[i0], part);
+      p0 = fma(lx[i1], ax[i0], p0);
+      p1 = fma(lx[i0], ax[i1], p1);
+      p0 = fma(ly[i1], ay[i0], p0);
+      p1 = fma(ly[i0], ay[i1], p1);
     }
   }
-  return part;
+  return p0 - p1;
 }
 
+// CNOT with a local target: conditional exchange of the two amplitudes of every active pair
 template <typename T, int LB, int PT>
-__device__ __forceinline__ void cx_apply(T (&ax)[1 << LB], T (&ay)[1 << LB], int pcl) {
+__device__ __forceinline__ void cx_apply(T (&ax)[1 << LB], T (&ay)[1 << LB], unsigned cmask) {
   constexpr int NA = 1 << LB;
 #pragma unroll
   for (int h = 0; h < NA / 2; ++h) {
     RG_PAIR(h, PT);
-    if (pcl >= 0 && !((i0 >> pcl) & 1)) continue;
-    const T tx = ax[i0], ty = ay[i0];
-    ax[i0] = ax[i1]; ay[i0] = ay[i1];
-    ax[i1] = tx; ay[i1] = ty;
+    const bool act = (cmask >> h) & 1;
+    const T x0 = ax[i0], y0 = ay[i0], x1 = ax[i1], y1 = ay[i1];
+    ax[i0] = act ? x1 : x0; ay[i0] = act ? y1 : y0;
+    ax[i1] = act ? x0 : x1; ay[i1] = act ? y0 : y1;
   }
 }
 
 // exchange the roles of local position PT and the lane position whose xor mask is lmask
+// (branch free: every lane sends one amplitude of each pair and overwrites the slot it sent)
 template <typename T, int LB, int PT>
 __device__ __forceinline__ void swap_ll(T (&ax)[1 << LB], T (&ay)[1 << LB], int lmask, bool mybit) {
   constexpr int NA = 1 << LB;
 #pragma unroll
   for (int h = 0; h < NA / 2; ++h) {
     RG_PAIR(h, PT);
-    const T sx = mybit ? ax[i0] : ax[i1], sy = mybit ? ay[i0] : ay[i1];
-    const T rx = shx(sx, lmask), ry = shx(sy, lmask);
-    if (mybit) { ax[i0] = rx; ay[i0] = ry; } else { ax[i1] = rx; ay[i1] = ry; }
+    const T rx = shx(mybit ? ax[i0] : ax[i1], lmask);
+    const T ry = shx(mybit ? ay[i0] : ay[i1], lmask);
+    ax[i0] = mybit ? rx : ax[i0];
+    ax[i1] = mybit ? ax[i1] : rx;
+    ay[i0] = mybit ? ry : ay[i0];
+    ay[i1] = mybit ? ay[i1] : ry;
   }
 }
 
@@ -263,48 +303,36 @@ __device__ __forceinline__ void u4_apply(T (&ax)[1 << LB], T (&ay)[1 << LB], con
 // ---------------------------------------------------------------------------------------------
 // per-CTA context (shared-memory views)
 // ---------------------------------------------------------------------------------------------
+extern __shared__ __align__(16) unsigned char rg_smem[];
+
+// Pointers are rebuilt from the constant-bank offsets at every use: the hot gate loop keeps 128+
+// registers of amplitudes live, so nothing else should be pinned in registers across it.
 template <typename T, int S>
 struct Ctx {
-  const ROp* rops;
-  const T* cs;          // [n_gates][4]
-  const C2<T>* u4;      // [n_consts][16]
-  T* zj;                // [NPT][n*S]   slot-major
-  T* qj;                // [NPT][n*S]
-  Jet<T, S>* rj;        // [NPT][n][2]
-  Jet<T, S>* tab;       // [NPT][NA + G]
-  C2<T>* exch;          // [NW][32 * NA]
-  T* atab;              // [NPT][S][NA]
-  Jet<T, S>* tabbar;    // [NPT][NA + G]
-  Jet<T, S>* rbar;      // [NPT][n][2]
-  double* gth;          // [n_theta]
-  T* wacc;              // [n_blk << n]
+  const RgArgs& a;
+  template <typename U>
+  __device__ __forceinline__ U* at(int off) const { return reinterpret_cast<U*>(rg_smem + off); }
+  __device__ __forceinline__ const ROp* rops() const { return at<const ROp>(a.lay.rops); }
+  __device__ __forceinline__ const T* cs() const { return at<const T>(a.lay.cs); }              // [n_gates][4]
+  __device__ __forceinline__ const C2<T>* u4() const { return at<const C2<T>>(a.lay.u4); }      // [n_consts][16]
+  __device__ __forceinline__ T* zj() const { return at<T>(a.lay.zj); }                          // [NPT][n*S]
+  __device__ __forceinline__ T* qj() const { return at<T>(a.lay.qj); }                          // [NPT][n*S]
+  __device__ __forceinline__ Jet<T, S>* rj() const { return at<Jet<T, S>>(a.lay.rj); }          // [NPT][n][2]
+  __device__ __forceinline__ Jet<T, S>* tab() const { return at<Jet<T, S>>(a.lay.tab); }        // [NPT][NA+G]
+  __device__ __forceinline__ C2<T>* exch() const { return at<C2<T>>(a.lay.exch); }              // [NW][32*NA]
+  __device__ __forceinline__ T* atab() const { return at<T>(a.lay.atab); }                      // [NPT][S][NA]
+  __device__ __forceinline__ Jet<T, S>* tabbar() const { return at<Jet<T, S>>(a.lay.tabbar); }  // [NPT][NA+G]
+  __device__ __forceinline__ Jet<T, S>* rbar() const { return at<Jet<T, S>>(a.lay.rbar); }      // [NPT][n][2]
+  __device__ __forceinline__ double* gth() const { return at<double>(a.lay.gth); }              // [n_theta]
+  __device__ __forceinline__ T* wacc() const { return at<T>(a.lay.wacc); }                      // [n_blk << n]
 };
-
-template <typename T, int S>
-__device__ __forceinline__ Ctx<T, S> make_ctx(unsigned char* base, const SmemLayout& L) {
-  Ctx<T, S> c;
-  c.rops = reinterpret_cast<const ROp*>(base + L.rops);
-  c.cs = reinterpret_cast<const T*>(base + L.cs);
-  c.u4 = reinterpret_cast<const C2<T>*>(base + L.u4);
-  c.zj = reinterpret_cast<T*>(base + L.zj);
-  c.qj = reinterpret_cast<T*>(base + L.qj);
-  c.rj = reinterpret_cast<Jet<T, S>*>(base + L.rj);
-  c.tab = reinterpret_cast<Jet<T, S>*>(base + L.tab);
-  c.exch = reinterpret_cast<C2<T>*>(base + L.exch);
-  c.atab = reinterpret_cast<T*>(base + L.atab);
-  c.tabbar = reinterpret_cast<Jet<T, S>*>(base + L.tabbar);
-  c.rbar = reinterpret_cast<Jet<T, S>*>(base + L.rbar);
-  c.gth = reinterpret_cast<double*>(base + L.gth);
-  c.wacc = reinterpret_cast<T*>(base + L.wacc);
-  return c;
-}
 
 // rops, gate coefficients and the Haar constants -> shared memory (once per CTA)
 template <typename T, int S>
-__device__ void load_program(unsigned char* base, const SmemLayout& L, const RgArgs& a) {
-  ROp* rops = reinterpret_cast<ROp*>(base + L.rops);
-  T* cs = reinterpret_cast<T*>(base + L.cs);
-  C2<T>* u4 = reinterpret_cast<C2<T>*>(base + L.u4);
+__device__ void load_program(const RgArgs& a) {
+  ROp* rops = reinterpret_cast<ROp*>(rg_smem + a.lay.rops);
+  T* cs = reinterpret_cast<T*>(rg_smem + a.lay.cs);
+  C2<T>* u4 = reinterpret_cast<C2<T>*>(rg_smem + a.lay.u4);
   for (int r = threadIdx.x; r < a.n_rops; r += blockDim.x) rops[r] = a.rops[r];
   const T* theta = static_cast<const T*>(a.theta);
   for (int g = threadIdx.x; g < a.n_gates; g += blockDim.x) {
@@ -338,27 +366,20 @@ __device__ __forceinline__ void run_forward(T (&ax)[1 << LB], T (&ay)[1 << LB], 
                                             const RgArgs& a, int lig, int G) {
   const C2A<T>* diag = static_cast<const C2A<T>*>(a.diag);
   for (int r = 0; r < a.n_rops; ++r) {
-    const ROp op = c.rops[r];
+    const ROp op = c.rops()[r];
     switch (op.kind) {
       case R_L1: {
-        int pcl = -1;
-        bool on = true;
-        if (op.pc >= 0) {
-          if (op.pc < LB) pcl = op.pc;
-          else on = (lig >> (op.pc - LB)) & 1;
-        }
-        if (on) {
-          const T m0 = c.cs[4 * op.g], m1 = c.cs[4 * op.g + 1], m2 = c.cs[4 * op.g + 2], m3 = c.cs[4 * op.g + 3];
-          RG_PT_SWITCH(op.pt, l1_apply<T, LB, PT>(ax, ay, op.type, m0, m1, m2, m3, pcl))
+        const T m0 = c.cs()[4 * op.g], m1 = c.cs()[4 * op.g + 1], m2 = c.cs()[4 * op.g + 2], m3 = c.cs()[4 * op.g + 3];
+        if (op.pc >= 0 && op.pc < LB) {
+          RG_PT_SWITCH(op.pt, l1_apply<T, LB, PT, true>(ax, ay, op.type, m0, m1, m2, m3, (unsigned)op.m))
+        } else if (op.pc < 0 || ((lig >> (op.pc - LB)) & 1)) {
+          RG_PT_SWITCH(op.pt, l1_apply<T, LB, PT, false>(ax, ay, op.type, m0, m1, m2, m3, 0u))
         }
         break;
       }
       case R_CX: {
-        int pcl = -1;
-        bool on = true;
-        if (op.pc < LB) pcl = op.pc;
-        else on = (lig >> (op.pc - LB)) & 1;
-        if (on) { RG_PT_SWITCH(op.pt, cx_apply<T, LB, PT>(ax, ay, pcl)) }
+        const unsigned cm = op.pc < LB ? (unsigned)op.m : (((lig >> (op.pc - LB)) & 1) ? 0xffffu : 0u);
+        RG_PT_SWITCH(op.pt, cx_apply<T, LB, PT>(ax, ay, cm))
         break;
       }
       case R_SWAP: {
@@ -371,7 +392,7 @@ __device__ __forceinline__ void run_forward(T (&ax)[1 << LB], T (&ay)[1 << LB], 
         diag_apply<T, LB>(ax, ay, diag + ((size_t)op.g << a.n) + lig, G, false);
         break;
       default:
-        u4_apply<T, LB>(ax, ay, c.u4 + 16 * op.g, false);
+        u4_apply<T, LB>(ax, ay, c.u4() + 16 * op.g, false);
         break;
     }
   }
@@ -389,14 +410,14 @@ __device__ void encode_qubit_jets(const Ctx<T, S>& c, int n, int enc, int NPT) {
       const int slot = e / n, j = e % n;
       Jet<T, S> z;
 #pragma unroll
-      for (int k = 0; k < S; ++k) z.c[k] = c.zj[(size_t)slot * n * S + j * S + k];
+      for (int k = 0; k < S; ++k) z.c[k] = c.zj()[(size_t)slot * n * S + j * S + k];
       T sn, cs;
       Math<T>::sincos_(T(0.5) * z.c[0], &sn, &cs);
       Jet<T, S> h = z;     // jet of z/2
 #pragma unroll
       for (int k = 0; k < S; ++k) h.c[k] = T(0.5) * z.c[k];
-      c.rj[((size_t)slot * n + j) * 2] = jfunc(h, cs, -sn, -cs);
-      c.rj[((size_t)slot * n + j) * 2 + 1] = jfunc(h, sn, cs, -sn);
+      c.rj()[((size_t)slot * n + j) * 2] = jfunc(h, cs, -sn, -cs);
+      c.rj()[((size_t)slot * n + j) * 2 + 1] = jfunc(h, sn, cs, -sn);
     }
   } else {
     for (int slot = threadIdx.x; slot < NPT; slot += blockDim.x) {
@@ -405,7 +426,7 @@ __device__ void encode_qubit_jets(const Ctx<T, S>& c, int n, int enc, int NPT) {
       for (int j = 0; j < n; ++j) {
         Jet<T, S> f;
 #pragma unroll
-        for (int k = 0; k < S; ++k) f.c[k] = c.zj[(size_t)slot * n * S + j * S + k];
+        for (int k = 0; k < S; ++k) f.c[k] = c.zj()[(size_t)slot * n * S + j * S + k];
         jmul_acc(nrm, f, f);
       }
       // padded lanes carry z = 0: keep them finite (their outputs are never stored)
@@ -416,8 +437,8 @@ __device__ void encode_qubit_jets(const Ctx<T, S>& c, int n, int enc, int NPT) {
       for (int j = 0; j < n; ++j) {
         Jet<T, S> f;
 #pragma unroll
-        for (int k = 0; k < S; ++k) f.c[k] = c.zj[(size_t)slot * n * S + j * S + k];
-        c.rj[((size_t)slot * n + j) * 2] = jmul(f, inv);
+        for (int k = 0; k < S; ++k) f.c[k] = c.zj()[(size_t)slot * n * S + j * S + k];
+        c.rj()[((size_t)slot * n + j) * 2] = jmul(f, inv);
       }
     }
   }
@@ -435,10 +456,10 @@ __device__ void encode_tables(const Ctx<T, S>& c, int n, int NPT) {
     const int idx = lane_part ? ent - NA : ent;
     const int K = lane_part ? n - LB : LB;
     const int q0 = lane_part ? n - 1 - LB : n - 1;
-    Jet<T, S> acc = c.rj[((size_t)slot * n + q0) * 2 + (idx & 1)];
+    Jet<T, S> acc = c.rj()[((size_t)slot * n + q0) * 2 + (idx & 1)];
     for (int k = 1; k < K; ++k)
-      acc = jmul(acc, c.rj[((size_t)slot * n + (q0 - k)) * 2 + ((idx >> k) & 1)]);
-    c.tab[(size_t)slot * NE + ent] = acc;
+      acc = jmul(acc, c.rj()[((size_t)slot * n + (q0 - k)) * 2 + ((idx >> k) & 1)]);
+    c.tab()[(size_t)slot * NE + ent] = acc;
   }
 }
 
@@ -461,7 +482,7 @@ __device__ __forceinline__ void encode_stream(T (&ax)[1 << LB], T (&ay)[1 << LB]
   constexpr int NA = 1 << LB;
   const int G = 1 << (n - LB), NE = NA + G;
   if (enc == QCP_ENC_ANGLE) {
-    const Jet<T, S>* tab = c.tab + (size_t)slot * NE;
+    const Jet<T, S>* tab = c.tab() + (size_t)slot * NE;
     const Jet<T, S>& Lj = tab[NA + lig];
     const T L0 = Lj.c[0], Ls = Lj.c[s], Lp2 = (S == 6 && s >= 4) ? T(2) * Lj.c[s - 2] : T(0);
     const int pl = __popc(lig) & 3;
@@ -481,7 +502,7 @@ __device__ __forceinline__ void encode_stream(T (&ax)[1 << LB], T (&ay)[1 << LB]
 #pragma unroll
     for (int i = 0; i < NA; ++i) {
       const int k = (lig << LB) | i;
-      ax[i] = k < n ? c.rj[((size_t)slot * n + k) * 2].c[s] : T(0);
+      ax[i] = k < n ? c.rj()[((size_t)slot * n + k) * 2].c[s] : T(0);
       ay[i] = T(0);
     }
   }
@@ -526,14 +547,12 @@ __device__ __forceinline__ void signed_sums(const T (&w)[1 << LB], const RgArgs&
 // forward kernel
 // ---------------------------------------------------------------------------------------------
 template <typename T, int LB, int S>
-__global__ void __launch_bounds__(rg_warps(S) * 32)
-rg_forward_kernel(const RgArgs a) {
+__global__ void __launch_bounds__(rg_warps(S) * 32, rg_min_blocks(S, false))
+rg_forward_kernel(const __grid_constant__ RgArgs a) {
   constexpr int NA = 1 << LB, NW = rg_warps(S);
-  extern __shared__ __align__(16) unsigned char rg_smem[];
   const int n = a.n, G = 1 << (n - LB), PP = 32 / G, NPT = S == 6 ? PP : NW * PP;
-  const SmemLayout L = rg_layout(sizeof(T), LB, S, n, a.n_rops, a.n_gates, a.n_consts, a.n_theta, a.n_blk, false);
-  const Ctx<T, S> c = make_ctx<T, S>(rg_smem, L);
-  load_program<T, S>(rg_smem, L, a);
+  const Ctx<T, S> c{a};
+  load_program<T, S>(a);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lig = lane & (G - 1), sub = lane / G;
   const int slot = S == 6 ? sub : warp * PP + sub;
@@ -547,7 +566,7 @@ rg_forward_kernel(const RgArgs a) {
     for (int e = threadIdx.x; e < NPT * nS; e += blockDim.x) {
       const int sl = e % NPT, rem = e / NPT;
       const long long p = base + sl;
-      c.zj[(size_t)sl * nS + rem] = p < a.B ? ws[(size_t)rem * a.B + p] : T(0);
+      c.zj()[(size_t)sl * nS + rem] = p < a.B ? ws[(size_t)rem * a.B + p] : T(0);
     }
     __syncthreads();
     encode_qubit_jets<T, S>(c, n, a.enc, NPT);
@@ -566,7 +585,7 @@ rg_forward_kernel(const RgArgs a) {
 #pragma unroll
       for (int i = 0; i < NA; ++i) st[i * G] = {ax[i], ay[i]};
     }
-    C2<T>* ex = c.exch;
+    C2<T>* ex = c.exch();
     if constexpr (S == 6) {
       if (s < 4) {
 #pragma unroll
@@ -605,16 +624,14 @@ rg_forward_kernel(const RgArgs a) {
 // backward kernel
 // ---------------------------------------------------------------------------------------------
 template <typename T, int LB, int S>
-__global__ void __launch_bounds__(rg_warps(S) * 32)
-rg_backward_kernel(const RgArgs a) {
+__global__ void __launch_bounds__(rg_warps(S) * 32, rg_min_blocks(S, true))
+rg_backward_kernel(const __grid_constant__ RgArgs a) {
   constexpr int NA = 1 << LB, NW = rg_warps(S);
-  extern __shared__ __align__(16) unsigned char rg_smem[];
   const int n = a.n, G = 1 << (n - LB), PP = 32 / G, NPT = S == 6 ? PP : NW * PP, NE = NA + G;
-  const SmemLayout L = rg_layout(sizeof(T), LB, S, n, a.n_rops, a.n_gates, a.n_consts, a.n_theta, a.n_blk, true);
-  const Ctx<T, S> c = make_ctx<T, S>(rg_smem, L);
-  load_program<T, S>(rg_smem, L, a);
-  for (int p = threadIdx.x; p < a.n_theta; p += blockDim.x) c.gth[p] = 0.0;
-  for (int e = threadIdx.x; e < (a.n_blk << n); e += blockDim.x) c.wacc[e] = T(0);
+  const Ctx<T, S> c{a};
+  load_program<T, S>(a);
+  for (int p = threadIdx.x; p < a.n_theta; p += blockDim.x) c.gth()[p] = 0.0;
+  for (int e = threadIdx.x; e < (a.n_blk << n); e += blockDim.x) c.wacc()[e] = T(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lig = lane & (G - 1), sub = lane / G;
   const int slot = S == 6 ? sub : warp * PP + sub;
@@ -632,11 +649,11 @@ rg_backward_kernel(const RgArgs a) {
       const int sl = e % NPT, rem = e / NPT;
       const long long p = base + sl;
       const bool ok = p < a.B;
-      c.zj[(size_t)sl * nS + rem] = ok ? ws[(size_t)rem * a.B + p] : T(0);
-      c.qj[(size_t)sl * nS + rem] = ok ? ws[(size_t)(nS + rem) * a.B + p] : T(0);
+      c.zj()[(size_t)sl * nS + rem] = ok ? ws[(size_t)rem * a.B + p] : T(0);
+      c.qj()[(size_t)sl * nS + rem] = ok ? ws[(size_t)(nS + rem) * a.B + p] : T(0);
     }
-    for (int e = threadIdx.x; e < NPT * NE * S; e += blockDim.x) reinterpret_cast<T*>(c.tabbar)[e] = T(0);
-    for (int e = threadIdx.x; e < NPT * n * 2 * S; e += blockDim.x) reinterpret_cast<T*>(c.rbar)[e] = T(0);
+    for (int e = threadIdx.x; e < NPT * NE * S; e += blockDim.x) reinterpret_cast<T*>(c.tabbar())[e] = T(0);
+    for (int e = threadIdx.x; e < NPT * n * 2 * S; e += blockDim.x) reinterpret_cast<T*>(c.rbar())[e] = T(0);
     __syncthreads();
     // ---- B2/B3: encoding tables, local part of the sign sums -----------------------------------
     encode_qubit_jets<T, S>(c, n, a.enc, NPT);
@@ -646,11 +663,11 @@ rg_backward_kernel(const RgArgs a) {
       for (int q = 0; q < n; ++q) {
         const int pos = a.meas_pos[q];
         if (pos < LB) {
-          const T v = c.qj[(size_t)sl * nS + q * S + k];
+          const T v = c.qj()[(size_t)sl * nS + q * S + k];
           acc += ((i >> pos) & 1) ? -v : v;
         }
       }
-      c.atab[e] = acc;
+      c.atab()[e] = acc;
     }
     __syncthreads();
     if (a.enc == QCP_ENC_ANGLE) encode_tables<T, LB, S>(c, n, NPT);
@@ -672,7 +689,7 @@ rg_backward_kernel(const RgArgs a) {
       encode_stream<T, LB, S>(ax, ay, c, n, a.enc, slot, lig, s);
       run_forward<T, LB, S>(ax, ay, c, a, lig, G);
     }
-    C2<T>* ex = c.exch;
+    C2<T>* ex = c.exch();
     if constexpr (S == 6) {
 #pragma unroll
       for (int i = 0; i < NA; ++i) ex[(size_t)s * 32 * NA + i * 32 + lane] = {ax[i], ay[i]};
@@ -690,12 +707,12 @@ rg_backward_kernel(const RgArgs a) {
           const bool neg = (lig >> (pos - LB)) & 1;
 #pragma unroll
           for (int k = 0; k < S; ++k) {
-            const T v = c.qj[(size_t)slot * nS + q * S + k];
+            const T v = c.qj()[(size_t)slot * nS + q * S + k];
             bl[k] += neg ? -v : v;
           }
         }
       }
-      const T* at = c.atab + (size_t)slot * S * NA;
+      const T* at = c.atab() + (size_t)slot * S * NA;
       if (s == 0) {
 #pragma unroll
         for (int i = 0; i < NA; ++i) {
@@ -729,43 +746,38 @@ rg_backward_kernel(const RgArgs a) {
     }
     // ---- B6: gate program in reverse --------------------------------------------------------------
     for (int r = a.n_rops - 1; r >= 0; --r) {
-      const ROp op = c.rops[r];
+      const ROp op = c.rops()[r];
       switch (op.kind) {
         case R_L1: {
-          int pcl = -1;
-          bool on = true;
-          if (op.pc >= 0) {
-            if (op.pc < LB) pcl = op.pc;
-            else on = (lig >> (op.pc - LB)) & 1;
-          }
-          const T m0 = c.cs[4 * op.g], m1 = c.cs[4 * op.g + 1], m2 = c.cs[4 * op.g + 2], m3 = c.cs[4 * op.g + 3];
+          const T m0 = c.cs()[4 * op.g], m1 = c.cs()[4 * op.g + 1], m2 = c.cs()[4 * op.g + 2], m3 = c.cs()[4 * op.g + 3];
+          // dagger: T_X -> s = -s ; T_R -> transpose
+          const T d1 = op.type == T_X ? -m1 : m2, d2 = op.type == T_X ? m2 : m1;
           T part = T(0);
-          if (on) {
-            // dagger: T_X -> s = -s ; T_R -> transpose
-            const T d1 = op.type == T_X ? -m1 : m2, d2 = op.type == T_X ? m2 : m1;
+          if (op.pc >= 0 && op.pc < LB) {
             RG_PT_SWITCH(op.pt, {
-              if (op.p >= 0) part = l1_grad<T, LB, PT>(ax, ay, lx, ly, op.type, pcl);
-              l1_apply<T, LB, PT>(ax, ay, op.type, m0, d1, d2, m3, pcl);
-              l1_apply<T, LB, PT>(lx, ly, op.type, m0, d1, d2, m3, pcl);
+              part = l1_grad<T, LB, PT, true>(ax, ay, lx, ly, op.type, (unsigned)op.m);
+              l1_apply<T, LB, PT, true>(ax, ay, op.type, m0, d1, d2, m3, (unsigned)op.m);
+              l1_apply<T, LB, PT, true>(lx, ly, op.type, m0, d1, d2, m3, (unsigned)op.m);
+            })
+          } else if (op.pc < 0 || ((lig >> (op.pc - LB)) & 1)) {
+            RG_PT_SWITCH(op.pt, {
+              if (op.p >= 0) part = l1_grad<T, LB, PT, false>(ax, ay, lx, ly, op.type, 0u);
+              l1_apply<T, LB, PT, false>(ax, ay, op.type, m0, d1, d2, m3, 0u);
+              l1_apply<T, LB, PT, false>(lx, ly, op.type, m0, d1, d2, m3, 0u);
             })
           }
           if (op.p >= 0) {
             for (int m = 16; m > 0; m >>= 1) part += shx(part, m);
-            if (lane == 0) atomicAdd(&c.gth[op.p], 0.5 * (double)part);
+            if (lane == 0) atomicAdd(&c.gth()[op.p], 0.5 * (double)part);
           }
           break;
         }
         case R_CX: {
-          int pcl = -1;
-          bool on = true;
-          if (op.pc < LB) pcl = op.pc;
-          else on = (lig >> (op.pc - LB)) & 1;
-          if (on) {
-            RG_PT_SWITCH(op.pt, {
-              cx_apply<T, LB, PT>(ax, ay, pcl);
-              cx_apply<T, LB, PT>(lx, ly, pcl);
-            })
-          }
+          const unsigned cm = op.pc < LB ? (unsigned)op.m : (((lig >> (op.pc - LB)) & 1) ? 0xffffu : 0u);
+          RG_PT_SWITCH(op.pt, {
+            cx_apply<T, LB, PT>(ax, ay, cm);
+            cx_apply<T, LB, PT>(lx, ly, cm);
+          })
           break;
         }
         case R_SWAP: {
@@ -778,7 +790,7 @@ rg_backward_kernel(const RgArgs a) {
           break;
         }
         case R_DIAG: {
-          T* wa = c.wacc + ((size_t)op.g << n) + lig;
+          T* wa = c.wacc() + ((size_t)op.g << n) + lig;
 #pragma unroll
           for (int i = 0; i < NA; ++i) atomicAdd(wa + i * G, fma(lx[i], ay[i], -ly[i] * ax[i]));
           const C2A<T>* tb = diag + ((size_t)op.g << n) + lig;
@@ -787,14 +799,14 @@ rg_backward_kernel(const RgArgs a) {
           break;
         }
         default:
-          u4_apply<T, LB>(ax, ay, c.u4 + 16 * op.g, true);
-          u4_apply<T, LB>(lx, ly, c.u4 + 16 * op.g, true);
+          u4_apply<T, LB>(ax, ay, c.u4() + 16 * op.g, true);
+          u4_apply<T, LB>(lx, ly, c.u4() + 16 * op.g, true);
           break;
       }
     }
     // ---- B7: pull lambda0 back through the encoding ---------------------------------------------
     __syncthreads();   // every warp is done reading the psi exchange rows
-    T* rb = reinterpret_cast<T*>(c.exch);       // [NW][32 * NA] real cotangents
+    T* rb = reinterpret_cast<T*>(c.exch());       // [NW][32 * NA] real cotangents
     if (a.enc == QCP_ENC_ANGLE) {
       const int pl = __popc(lig) & 3;
       const T bx = pl == 0 ? T(1) : (pl == 2 ? T(-1) : T(0));
@@ -811,7 +823,7 @@ rg_backward_kernel(const RgArgs a) {
         const int k = e % S, ent = (e / S) % NE, sl = e / (S * NE);
         const int rw = S == 6 ? k : sl / PP, sb = S == 6 ? sl : sl % PP;
         const T* rr = rb + (size_t)rw * 32 * NA + sb * G;
-        const Jet<T, S>* tab = c.tab + (size_t)sl * NE;
+        const Jet<T, S>* tab = c.tab() + (size_t)sl * NE;
         T a0 = T(0), as = T(0), ap = T(0);
         if (ent >= NA) {          // lane entry: sum over the local index
           const int l = ent - NA;
@@ -831,7 +843,7 @@ rg_backward_kernel(const RgArgs a) {
             if (k >= 4) ap = fma(T(2) * rho, Lj.c[k - 2], ap);
           }
         }
-        Jet<T, S>& tb = c.tabbar[(size_t)sl * NE + ent];
+        Jet<T, S>& tb = c.tabbar()[(size_t)sl * NE + ent];
         atomicAdd(&tb.c[0], a0);
         if (k > 0) atomicAdd(&tb.c[k], as);
         if (k >= 4) atomicAdd(&tb.c[k - 2], ap);
@@ -844,12 +856,12 @@ rg_backward_kernel(const RgArgs a) {
         const int idx = lane_part ? ent - NA : ent;
         const int K = lane_part ? n - LB : LB;
         const int q0 = lane_part ? n - 1 - LB : n - 1;
-        const Jet<T, S> eb = c.tabbar[(size_t)sl * NE + ent];
+        const Jet<T, S> eb = c.tabbar()[(size_t)sl * NE + ent];
         Jet<T, S> suf[6];
         jzero(suf[K]);
         suf[K].c[0] = T(1);
         for (int k = K - 1; k >= 0; --k)
-          suf[k] = jmul(c.rj[((size_t)sl * n + (q0 - k)) * 2 + ((idx >> k) & 1)], suf[k + 1]);
+          suf[k] = jmul(c.rj()[((size_t)sl * n + (q0 - k)) * 2 + ((idx >> k) & 1)], suf[k + 1]);
         Jet<T, S> pre;
         jzero(pre);
         pre.c[0] = T(1);
@@ -859,10 +871,10 @@ rg_backward_kernel(const RgArgs a) {
           Jet<T, S> fb;
           jzero(fb);
           jmul_pull_acc(fb, eb, other);
-          Jet<T, S>& dst = c.rbar[((size_t)sl * n + jq) * 2 + bit];
+          Jet<T, S>& dst = c.rbar()[((size_t)sl * n + jq) * 2 + bit];
 #pragma unroll
           for (int m = 0; m < S; ++m) atomicAdd(&dst.c[m], fb.c[m]);
-          pre = jmul(pre, c.rj[((size_t)sl * n + jq) * 2 + bit]);
+          pre = jmul(pre, c.rj()[((size_t)sl * n + jq) * 2 + bit]);
         }
       }
       __syncthreads();
@@ -872,13 +884,13 @@ rg_backward_kernel(const RgArgs a) {
         if (pp >= a.B) continue;
         Jet<T, S> h;
 #pragma unroll
-        for (int k = 0; k < S; ++k) h.c[k] = T(0.5) * c.zj[(size_t)sl * nS + j * S + k];
+        for (int k = 0; k < S; ++k) h.c[k] = T(0.5) * c.zj()[(size_t)sl * nS + j * S + k];
         T sn, cs;
         Math<T>::sincos_(h.c[0], &sn, &cs);
         Jet<T, S> hb;
         jzero(hb);
-        jfunc_pull_acc(hb, c.rbar[((size_t)sl * n + j) * 2], h, -sn, -cs, sn);
-        jfunc_pull_acc(hb, c.rbar[((size_t)sl * n + j) * 2 + 1], h, cs, -sn, -cs);
+        jfunc_pull_acc(hb, c.rbar()[((size_t)sl * n + j) * 2], h, -sn, -cs, sn);
+        jfunc_pull_acc(hb, c.rbar()[((size_t)sl * n + j) * 2 + 1], h, cs, -sn, -cs);
 #pragma unroll
         for (int k = 0; k < S; ++k) ws_out[(size_t)(j * S + k) * a.B + pp] = T(0.5) * hb.c[k];
       }
@@ -887,7 +899,7 @@ rg_backward_kernel(const RgArgs a) {
 #pragma unroll
       for (int i = 0; i < NA; ++i) {
         const int k = (lig << LB) | i;
-        if (k < n) c.rbar[((size_t)slot * n + k) * 2].c[s] = lx[i];
+        if (k < n) c.rbar()[((size_t)slot * n + k) * 2].c[s] = lx[i];
       }
       __syncthreads();
       for (int sl = threadIdx.x; sl < NPT; sl += blockDim.x) {
@@ -898,7 +910,7 @@ rg_backward_kernel(const RgArgs a) {
         for (int j = 0; j < n; ++j) {
           Jet<T, S> f;
 #pragma unroll
-          for (int k = 0; k < S; ++k) f.c[k] = c.zj[(size_t)sl * nS + j * S + k];
+          for (int k = 0; k < S; ++k) f.c[k] = c.zj()[(size_t)sl * nS + j * S + k];
           jmul_acc(nrm, f, f);
         }
         const T r = T(1) / sqrt(nrm.c[0]);
@@ -908,16 +920,16 @@ rg_backward_kernel(const RgArgs a) {
         for (int j = 0; j < n; ++j) {
           Jet<T, S> f;
 #pragma unroll
-          for (int k = 0; k < S; ++k) f.c[k] = c.zj[(size_t)sl * nS + j * S + k];
-          jmul_pull_acc(invb, c.rbar[((size_t)sl * n + j) * 2], f);
+          for (int k = 0; k < S; ++k) f.c[k] = c.zj()[(size_t)sl * nS + j * S + k];
+          jmul_pull_acc(invb, c.rbar()[((size_t)sl * n + j) * 2], f);
         }
         jfunc_pull_acc(nb, invb, nrm, g1, g2, g3);
         for (int j = 0; j < n; ++j) {
           Jet<T, S> f, fb;
 #pragma unroll
-          for (int k = 0; k < S; ++k) f.c[k] = c.zj[(size_t)sl * nS + j * S + k];
+          for (int k = 0; k < S; ++k) f.c[k] = c.zj()[(size_t)sl * nS + j * S + k];
           jzero(fb);
-          jmul_pull_acc(fb, c.rbar[((size_t)sl * n + j) * 2], inv);
+          jmul_pull_acc(fb, c.rbar()[((size_t)sl * n + j) * 2], inv);
           jmul_pull_acc(fb, nb, f);
           jmul_pull_acc(fb, nb, f);
 #pragma unroll
@@ -929,9 +941,9 @@ rg_backward_kernel(const RgArgs a) {
   }
   // ---- per-CTA partial sums -------------------------------------------------------------------------
   double* out = a.theta_partials + (size_t)blockIdx.x * (a.n_theta > 0 ? a.n_theta : 1);
-  for (int p = threadIdx.x; p < a.n_theta; p += blockDim.x) out[p] = c.gth[p];
+  for (int p = threadIdx.x; p < a.n_theta; p += blockDim.x) out[p] = c.gth()[p];
   T* wout = static_cast<T*>(a.w_partials) + ((size_t)blockIdx.x * a.n_blk << n);
-  for (int e = threadIdx.x; e < (a.n_blk << n); e += blockDim.x) wout[e] = c.wacc[e];
+  for (int e = threadIdx.x; e < (a.n_blk << n); e += blockDim.x) wout[e] = c.wacc()[e];
 }
 
 // per-dtype launchers (qcp_reg_f32.cu / qcp_reg_f64.cu)
