@@ -335,6 +335,10 @@ int reg_run(RegPlan* r, int S, bool backward, void* ws, long long B, void* state
     if (grow(&r->d_wpart, &r->wpart_bytes, es * ((size_t)grid * (r->n_blk > 0 ? r->n_blk : 1) << r->n))) return 1;
     a.theta_partials = r->d_tpart;
     a.w_partials = r->d_wpart;
+    cudaError_t ez = cudaMemsetAsync(r->d_tpart, 0, sizeof(double) * (size_t)grid * nt, s);
+    if (ez == cudaSuccess && r->n_blk > 0)
+      ez = cudaMemsetAsync(r->d_wpart, 0, es * ((size_t)grid * r->n_blk << r->n), s);
+    if (ez != cudaSuccess) { set_error("engine R: cudaMemsetAsync failed: %s", cudaGetErrorString(ez)); return 1; }
   }
   const int rc = r->dtype == QCP_F64 ? rg_launch<double>(r->LB, S, backward, a, grid, L.total, s)
                                      : rg_launch<float>(r->LB, S, backward, a, grid, L.total, s);

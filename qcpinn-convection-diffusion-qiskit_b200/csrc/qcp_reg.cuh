@@ -113,8 +113,6 @@ __host__ __device__ inline SmemLayout rg_layout(size_t es, int LB, int S, int n,
     L.atab = o; o = rg_align(o + es * (size_t)NPT * S * NA);
     L.tabbar = o; o = rg_align(o + es * (size_t)NPT * (NA + G) * S);
     L.rbar = o; o = rg_align(o + es * (size_t)NPT * n * 2 * S);
-    L.gth = o; o = rg_align(o + sizeof(double) * (size_t)(n_theta > 0 ? n_theta : 1));
-    L.wacc = o; o = rg_align(o + es * ((size_t)(n_blk > 0 ? n_blk : 0) << n));
   }
   L.total = o;
   return L;
@@ -323,8 +321,6 @@ struct Ctx {
   __device__ __forceinline__ T* atab() const { return at<T>(a.lay.atab); }                      // [NPT][S][NA]
   __device__ __forceinline__ Jet<T, S>* tabbar() const { return at<Jet<T, S>>(a.lay.tabbar); }  // [NPT][NA+G]
   __device__ __forceinline__ Jet<T, S>* rbar() const { return at<Jet<T, S>>(a.lay.rbar); }      // [NPT][n][2]
-  __device__ __forceinline__ double* gth() const { return at<double>(a.lay.gth); }              // [n_theta]
-  __device__ __forceinline__ T* wacc() const { return at<T>(a.lay.wacc); }                      // [n_blk << n]
 };
 
 // rops, gate coefficients and the Haar constants -> shared memory (once per CTA)
@@ -474,7 +470,8 @@ __device__ __forceinline__ void phase_rot(int m4, T vx, T vy, T& ox, T& oy) {
   }
 }
 
-__host__ __device__ constexpr int popc_c(int v) { return v == 0 ? 0 : (v & 1) + popc_c(v >> 1); }
+// popcount of a 5-bit constant, written so that it folds after unrolling
+#define RG_POPC5(v) (((v) & 1) + (((v) >> 1) & 1) + (((v) >> 2) & 1) + (((v) >> 3) & 1) + (((v) >> 4) & 1))
 
 template <typename T, int LB, int S>
 __device__ __forceinline__ void encode_stream(T (&ax)[1 << LB], T (&ay)[1 << LB], const Ctx<T, S>& c,
@@ -496,7 +493,7 @@ __device__ __forceinline__ void encode_stream(T (&ax)[1 << LB], T (&ay)[1 << LB]
         if (s > 0) v = fma(L0, R.c[s], v);
         if (s >= 4) v = fma(Lp2, R.c[s - 2], v);
       }
-      phase_rot<T>(popc_c(i), v * bx, v * by, ax[i], ay[i]);
+      phase_rot<T>(RG_POPC5(i), v * bx, v * by, ax[i], ay[i]);
     }
   } else {
 #pragma unroll
@@ -630,8 +627,10 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
   const int n = a.n, G = 1 << (n - LB), PP = 32 / G, NPT = S == 6 ? PP : NW * PP, NE = NA + G;
   const Ctx<T, S> c{a};
   load_program<T, S>(a);
-  for (int p = threadIdx.x; p < a.n_theta; p += blockDim.x) c.gth()[p] = 0.0;
-  for (int e = threadIdx.x; e < (a.n_blk << n); e += blockDim.x) c.wacc()[e] = T(0);
+  // per-CTA accumulator rows in global memory (zeroed by the host): fire-and-forget RED.ADD, which
+  // shared memory only offers as a compare-and-swap loop for floating point
+  double* const gth = a.theta_partials + (size_t)blockIdx.x * (a.n_theta > 0 ? a.n_theta : 1);
+  T* const wacc = static_cast<T*>(a.w_partials) + ((size_t)blockIdx.x * a.n_blk << n);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lig = lane & (G - 1), sub = lane / G;
   const int slot = S == 6 ? sub : warp * PP + sub;
@@ -768,7 +767,7 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
           }
           if (op.p >= 0) {
             for (int m = 16; m > 0; m >>= 1) part += shx(part, m);
-            if (lane == 0) atomicAdd(&c.gth()[op.p], 0.5 * (double)part);
+            if (lane == 0) atomicAdd(gth + op.p, 0.5 * (double)part);
           }
           break;
         }
@@ -790,7 +789,7 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
           break;
         }
         case R_DIAG: {
-          T* wa = c.wacc() + ((size_t)op.g << n) + lig;
+          T* wa = wacc + ((size_t)op.g << n) + lig;
 #pragma unroll
           for (int i = 0; i < NA; ++i) atomicAdd(wa + i * G, fma(lx[i], ay[i], -ly[i] * ax[i]));
           const C2A<T>* tb = diag + ((size_t)op.g << n) + lig;
@@ -814,7 +813,7 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
 #pragma unroll
       for (int i = 0; i < NA; ++i) {
         T fx, fy;
-        phase_rot<T>(popc_c(i), bx, by, fx, fy);
+        phase_rot<T>(RG_POPC5(i), bx, by, fx, fy);
         rb[(size_t)row * 32 * NA + i * 32 + lane] = fma(lx[i], fx, ly[i] * fy);
       }
       __syncthreads();
@@ -939,11 +938,6 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
     }
     __syncthreads();
   }
-  // ---- per-CTA partial sums -------------------------------------------------------------------------
-  double* out = a.theta_partials + (size_t)blockIdx.x * (a.n_theta > 0 ? a.n_theta : 1);
-  for (int p = threadIdx.x; p < a.n_theta; p += blockDim.x) out[p] = c.gth()[p];
-  T* wout = static_cast<T*>(a.w_partials) + ((size_t)blockIdx.x * a.n_blk << n);
-  for (int e = threadIdx.x; e < (a.n_blk << n); e += blockDim.x) wout[e] = c.wacc()[e];
 }
 
 // per-dtype launchers (qcp_reg_f32.cu / qcp_reg_f64.cu)
