@@ -83,9 +83,10 @@ int qcp_plan_num_features(const qcp_plan_t* plan);
 
 /* Which kernels a plan runs on: QCP_ENGINE_FEATURE (n <= 4: observables pre-multiplied into a real
  * feature matrix), QCP_ENGINE_REGISTER (5 <= n <= 10, float64: <= 9: per-sample statevectors in
- * registers, one warp per Taylor stream) or QCP_ENGINE_GLOBAL (larger n: per-sample statevectors in
- * shared / L2-resident global memory). */
-enum qcp_engine { QCP_ENGINE_FEATURE = 0, QCP_ENGINE_GLOBAL = 1, QCP_ENGINE_REGISTER = 2 };
+ * registers, one warp per Taylor stream), QCP_ENGINE_TILED (up to 16 qubits: per-sample statevectors
+ * in an HBM/L2-resident slab, swept tile by tile through registers) or QCP_ENGINE_GLOBAL (the
+ * gate-by-gate fallback, selected with QCP_ENGINE=L in the environment). */
+enum qcp_engine { QCP_ENGINE_FEATURE = 0, QCP_ENGINE_GLOBAL = 1, QCP_ENGINE_REGISTER = 2, QCP_ENGINE_TILED = 3 };
 int qcp_plan_engine(const qcp_plan_t* plan);
 
 /* Element type of the caller-facing arrays of the solver entry points (X, u, r, streams, grad_u,

@@ -553,7 +553,8 @@ struct qcp_plan {
   int pend_fused[kMaxPending];
   int io_f32;               // caller-facing arrays are float32 although the plan is float64
   bool engine_l;
-  RegPlan* reg;             // engine R context (5 <= n <= 10) or null => engine L kernels
+  RegPlan* reg;             // engine R context (5 <= n <= 10) or null
+  TilePlan* tile;           // engine T context (n up to 16) or null; neither => engine L kernels
   void* d_theta;            // copy of the angles taken by qcp_prepare()
   void* d_ws;               // internal saved-jet workspace (when the caller gives none)
   size_t ws_elems;
@@ -679,6 +680,10 @@ int qcp_plan_create(qcp_plan_t** out, int n_qubits, int encoding, int dtype, int
     p->reg = reg_create(n_qubits, encoding, dtype, reinterpret_cast<const GateOp*>(ops), n_ops, n_theta,
                         n_consts, p->d_ops, p->d_consts, p->num_sms);
     if (!p->reg) { qcp_plan_destroy(p); return 1; }
+  } else if (p->engine_l && tile_supported(n_qubits, dtype)) {
+    p->tile = tile_create(n_qubits, encoding, dtype, reinterpret_cast<const GateOp*>(ops), n_ops, n_theta,
+                          n_consts, p->d_ops, p->d_consts, p->num_sms);
+    if (!p->tile) { qcp_plan_destroy(p); return 1; }
   }
   *out = p;
   return 0;
@@ -690,6 +695,7 @@ int qcp_plan_destroy(qcp_plan_t* p) {
   cudaFree(p->d_C64); cudaFree(p->d_C); cudaFree(p->d_Cbar); cudaFree(p->d_partials);
   cudaFree(p->d_theta); cudaFree(p->d_ws); cudaFree(p->d_slab); cudaFree(p->d_theta_partials);
   reg_destroy(p->reg);
+  tile_destroy(p->tile);
   delete p;
   return 0;
 }
@@ -698,7 +704,8 @@ int qcp_plan_num_features(const qcp_plan_t* p) { return p ? p->F : -1; }
 
 int qcp_plan_engine(const qcp_plan_t* p) {
   if (!p) return -1;
-  return !p->engine_l ? QCP_ENGINE_FEATURE : (p->reg ? QCP_ENGINE_REGISTER : QCP_ENGINE_GLOBAL);
+  if (!p->engine_l) return QCP_ENGINE_FEATURE;
+  return p->reg ? QCP_ENGINE_REGISTER : (p->tile ? QCP_ENGINE_TILED : QCP_ENGINE_GLOBAL);
 }
 
 int qcp_plan_set_io_dtype(qcp_plan_t* p, int io_dtype) {
@@ -721,6 +728,7 @@ int qcp_prepare(qcp_plan_t* p, const void* theta, void* stream) {
       QCP_CUDA(cudaMemcpyAsync(p->d_theta, theta, elem_size(p->dtype) * p->n_theta,
                                cudaMemcpyDeviceToDevice, s));
     if (p->reg && reg_prepare(p->reg, p->d_theta, s)) return 1;
+    if (p->tile && tile_prepare(p->tile, p->d_theta, s)) return 1;
     p->prepared = true;
     return 0;
   }
@@ -820,6 +828,7 @@ static void* internal_ws(qcp_plan* p, long long B, int S) {
 static int circuit_run(qcp_plan* p, int S, bool backward, void* ws, long long B, void* state,
                        void* grad_theta, cudaStream_t s) {
   if (p->reg) return reg_run(p->reg, S, backward, ws, B, state, grad_theta, s);
+  if (p->tile) return tile_run(p->tile, S, backward, ws, B, grad_theta, s);
   SvLaunch L{};
   if (sv_configure(p, S, B, L)) return 1;
   L.ws = ws; L.grad_theta = grad_theta;

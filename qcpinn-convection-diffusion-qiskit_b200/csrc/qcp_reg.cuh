@@ -36,7 +36,7 @@ namespace qcp {
 namespace rg {
 
 enum RKind { R_L1 = 0, R_CX = 1, R_SWAP = 2, R_DIAG = 3, R_U4 = 4 };
-enum RType { T_X = 0, T_R = 1 };   // RX-like (c, -is; -is, c)  |  real 2x2 (RY, H)
+enum RType { T_X = 0, T_R = 1, T_Z = 2 };   // RX-like (c, -is; -is, c) | real 2x2 (RY, H) | RZ-like diag(c - is, c + is)
 
 // physical op: positions are bit positions of the amplitude index (0..LB-1 local, LB.. lane)
 struct ROp {
@@ -151,7 +151,7 @@ template <typename T, int LB, int PT, bool MASKED>
 __device__ __forceinline__ void l1_apply(T (&ax)[1 << LB], T (&ay)[1 << LB], int type, T m0, T m1,
                                          T m2, T m3, unsigned cmask) {
   constexpr int NA = 1 << LB;
-  if (MASKED || type == T_X) {     // only RX-like gates are ever controlled (CRX)
+  if (type == T_X) {
 #pragma unroll
     for (int h = 0; h < NA / 2; ++h) {
       RG_PAIR(h, PT);
@@ -167,7 +167,23 @@ __device__ __forceinline__ void l1_apply(T (&ax)[1 << LB], T (&ay)[1 << LB], int
       ax[i1] = fma(c, x1, s * y0);
       ay[i1] = fma(c, y1, -s * x0);
     }
-  } else {
+  } else if (type == T_Z) {
+#pragma unroll
+    for (int h = 0; h < NA / 2; ++h) {
+      RG_PAIR(h, PT);
+      T c = m0, s = m1;
+      if constexpr (MASKED) {
+        const bool act = (cmask >> h) & 1;
+        c = act ? m0 : T(1);
+        s = act ? m1 : T(0);
+      }
+      const T x0 = ax[i0], y0 = ay[i0], x1 = ax[i1], y1 = ay[i1];
+      ax[i0] = fma(c, x0, s * y0);
+      ay[i0] = fma(c, y0, -s * x0);
+      ax[i1] = fma(c, x1, -s * y1);
+      ay[i1] = fma(c, y1, s * x1);
+    }
+  } else if constexpr (!MASKED) {   // real 2x2 gates are never controlled
 #pragma unroll
     for (int h = 0; h < NA / 2; ++h) {
       RG_PAIR(h, PT);
@@ -181,14 +197,14 @@ __device__ __forceinline__ void l1_apply(T (&ax)[1 << LB], T (&ay)[1 << LB], int
 }
 
 // generator expectation Im<lambda|H|psi> over this lane's pairs (both vectors AFTER the gate):
-// H = X for T_X (RX, CRX), H = Y for T_R (RY)
+// H = X for T_X (RX, CRX), H = Y for T_R (RY), H = Z for T_Z (RZ, CRZ)
 template <typename T, int LB, int PT, bool MASKED>
 __device__ __forceinline__ T l1_grad(const T (&ax)[1 << LB], const T (&ay)[1 << LB],
                                      const T (&lx)[1 << LB], const T (&ly)[1 << LB], int type,
                                      unsigned cmask) {
   constexpr int NA = 1 << LB;
   T p0 = T(0), p1 = T(0);
-  if (MASKED || type == T_X) {
+  if (type == T_X) {
 #pragma unroll
     for (int h = 0; h < NA / 2; ++h) {
       RG_PAIR(h, PT);
@@ -203,6 +219,22 @@ __device__ __forceinline__ T l1_grad(const T (&ax)[1 << LB], const T (&ay)[1 << 
         p1 = fma(ly[i0], ax[i1], p1);
         p0 = fma(lx[i1], ay[i0], p0);
         p1 = fma(ly[i1], ax[i0], p1);
+      }
+    }
+  } else if (type == T_Z) {
+#pragma unroll
+    for (int h = 0; h < NA / 2; ++h) {
+      RG_PAIR(h, PT);
+      // Im(conj(l0) a0) - Im(conj(l1) a1)
+      const T t0 = fma(lx[i0], ay[i0], ly[i1] * ax[i1]);
+      const T t1 = fma(ly[i0], ax[i0], lx[i1] * ay[i1]);
+      if constexpr (MASKED) {
+        const bool act = (cmask >> h) & 1;
+        p0 += act ? t0 : T(0);
+        p1 += act ? t1 : T(0);
+      } else {
+        p0 += t0;
+        p1 += t1;
       }
     }
   } else if constexpr (!MASKED) {
@@ -337,7 +369,7 @@ __device__ void load_program(const RgArgs& a) {
     if (op.p >= 0 && op.kind != QCP_GATE_U4) sincos(0.5 * (double)theta[op.p], &s, &c);
     T m0 = T(0), m1 = T(0), m2 = T(0), m3 = T(0);
     switch (op.kind) {
-      case QCP_GATE_RX: case QCP_GATE_CRX: m0 = (T)c; m1 = (T)s; break;
+      case QCP_GATE_RX: case QCP_GATE_CRX: case QCP_GATE_RZ: case QCP_GATE_CRZ: m0 = (T)c; m1 = (T)s; break;
       case QCP_GATE_RY: m0 = (T)c; m1 = (T)(-s); m2 = (T)s; m3 = (T)c; break;
       case QCP_GATE_H: {
         const T h = (T)0.70710678118654752440;
@@ -750,7 +782,7 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
         case R_L1: {
           const T m0 = c.cs()[4 * op.g], m1 = c.cs()[4 * op.g + 1], m2 = c.cs()[4 * op.g + 2], m3 = c.cs()[4 * op.g + 3];
           // dagger: T_X -> s = -s ; T_R -> transpose
-          const T d1 = op.type == T_X ? -m1 : m2, d2 = op.type == T_X ? m2 : m1;
+          const T d1 = op.type == T_R ? m2 : -m1, d2 = op.type == T_R ? m1 : m2;
           T part = T(0);
           if (op.pc >= 0 && op.pc < LB) {
             RG_PT_SWITCH(op.pt, {

@@ -35,6 +35,16 @@ long long reg_state_elems(const RegPlan* r, long long B, int S);       // saved 
 int reg_run(RegPlan* r, int S, bool backward, void* ws, long long B, void* state, void* grad_theta,
             cudaStream_t s);
 
+// engine T (qcp_tile.cu): tiled statevector sweeps for 11 <= n <= 16 (float64: 10 <= n <= 16)
+struct TilePlan;
+int tile_supported(int n, int dtype);
+TilePlan* tile_create(int n, int enc, int dtype, const GateOp* host_ops, int n_ops, int n_theta,
+                      int n_consts, const GateOp* d_ops, const double2* d_consts, int num_sms);
+void tile_destroy(TilePlan* r);
+int tile_prepare(TilePlan* r, const void* d_theta, cudaStream_t s);
+int tile_num_sweeps(const TilePlan* r);
+int tile_run(TilePlan* r, int S, bool backward, void* ws, long long B, void* grad_theta, cudaStream_t s);
+
 // generic-n MLP stages (one thread per point, jets through the workspace)
 struct MlpLaunch {
   int n, H, grid;

@@ -1,0 +1,342 @@
+// qcpinn_b200 -- engine T host side: sweep planner and launch plumbing.  Device code: qcp_tile.cuh.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "qcp_tile.cuh"
+
+namespace qcp {
+
+using namespace tl;
+using rg::R_CX;
+using rg::R_L1;
+using rg::R_SWAP;
+using rg::R_U4;
+using rg::T_R;
+using rg::T_X;
+using rg::T_Z;
+
+template <typename T>
+__global__ void tl_reduce_theta_kernel(const double* __restrict__ partials, int grid, int n_theta,
+                                       T* __restrict__ gtheta) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_theta) return;
+  double s = 0.0;
+  for (int g = 0; g < grid; ++g) s += partials[(size_t)g * n_theta + p];
+  gtheta[p] = (T)s;
+}
+
+struct TilePlan {
+  int n, enc, dtype, LB, TB, n_gates, n_theta, n_consts, n_rops, n_sweeps, num_sms;
+  int final_bit[kMaxQubitsSv];
+  ROp* d_rops;
+  Sweep* d_sweeps;
+  const GateOp* d_gates;      // borrowed from the owning plan
+  const double2* d_consts;    // borrowed
+  void* d_slab;
+  size_t slab_bytes;
+  double* d_tpart;
+  size_t tpart_bytes;
+  const void* theta;
+};
+
+static size_t es_of(int dtype) { return dtype == QCP_F64 ? 8 : 4; }
+
+int tile_supported(int n, int dtype) {
+  const char* env = std::getenv("QCP_ENGINE");
+  if (env && (env[0] == 'L' || env[0] == 'l')) return 0;
+  const int tb = dtype == QCP_F64 ? 9 : 10;
+  return n > tb && n <= kMaxQubitsSv && n - tb < kMaxOther;
+}
+
+// qubits a gate needs INSIDE the tile (its dense / diagonal target; both wires of a Haar block)
+static void gate_targets(const GateOp& g, int* t, int* nt) {
+  *nt = 0;
+  switch (g.kind) {
+    case QCP_GATE_RX: case QCP_GATE_RY: case QCP_GATE_RZ: case QCP_GATE_H: t[(*nt)++] = g.a; break;
+    case QCP_GATE_CRX: case QCP_GATE_CRZ: case QCP_GATE_CNOT: t[(*nt)++] = g.b; break;
+    default: t[(*nt)++] = g.a; t[(*nt)++] = g.b; break;
+  }
+}
+
+// Greedy prefix: the longest run of gates from g0 whose targets fit into `cap` tile qubits, starting
+// from the qubits in `seed`.  Returns the end index; `Q` receives the tile qubits in order of first use.
+static int grow_tile(const GateOp* ops, int n_ops, int g0, int cap, const std::vector<int>& seed,
+                     std::vector<int>& Q) {
+  Q = seed;
+  int g = g0;
+  for (; g < n_ops; ++g) {
+    int t[2], nt;
+    gate_targets(ops[g], t, &nt);
+    int add = 0;
+    for (int k = 0; k < nt; ++k)
+      if (std::find(Q.begin(), Q.end(), t[k]) == Q.end() && (k == 0 || t[k] != t[0])) ++add;
+    if ((int)Q.size() + add > cap) break;
+    for (int k = 0; k < nt; ++k)
+      if (std::find(Q.begin(), Q.end(), t[k]) == Q.end()) Q.push_back(t[k]);
+  }
+  return g;
+}
+
+static void plan_sweeps(const GateOp* ops, int n_ops, int n, int LB, std::vector<ROp>& rops,
+                        std::vector<Sweep>& sweeps, int* final_bit) {
+  const int TB = LB + 5, NA = 1 << LB;
+  std::vector<int> mbit(n), qatm(n);               // memory bit of qubit q / qubit at memory bit b
+  for (int q = 0; q < n; ++q) { mbit[q] = n - 1 - q; qatm[n - 1 - q] = q; }
+  int g = 0;
+  while (g < n_ops) {
+    // ---- tile qubits of this sweep: the two on memory bits 0 / 1 are always inside ------------------
+    std::vector<int> seed = {qatm[0], qatm[1]}, Q;
+    const int g_end = grow_tile(ops, n_ops, g, TB, seed, Q);
+    // pad to TB qubits with the ones used next (keeps them handy; the tile always has TB bits)
+    for (int gg = g_end; gg < n_ops && (int)Q.size() < TB; ++gg) {
+      int t[2], nt;
+      gate_targets(ops[gg], t, &nt);
+      for (int k = 0; k < nt && (int)Q.size() < TB; ++k)
+        if (std::find(Q.begin(), Q.end(), t[k]) == Q.end()) Q.push_back(t[k]);
+    }
+    for (int q = 0; q < n && (int)Q.size() < TB; ++q)
+      if (std::find(Q.begin(), Q.end(), q) == Q.end()) Q.push_back(q);
+    // ---- seeds of the NEXT sweep: two of this tile's qubits, preferably ones it needs anyway -----------
+    std::vector<int> next_seed;
+    if (g_end < n_ops) {
+      std::vector<int> Qn;
+      grow_tile(ops, n_ops, g_end, TB - 2, {}, Qn);
+      for (int q : Qn)
+        if ((int)next_seed.size() < 2 && std::find(Q.begin(), Q.end(), q) != Q.end()) next_seed.push_back(q);
+    }
+    for (int k = (int)Q.size() - 1; k >= 0 && (int)next_seed.size() < 2; --k)
+      if (std::find(next_seed.begin(), next_seed.end(), Q[k]) == next_seed.end()) next_seed.push_back(Q[k]);
+
+    // ---- load mapping: tile position j <-> memory bit ---------------------------------------------------
+    std::vector<int> pos(n, -1), qat(TB, -1);          // tile position of qubit / qubit at tile position
+    auto place = [&](int q, int j) { pos[q] = j; qat[j] = q; };
+    place(qatm[0], LB);
+    place(qatm[1], LB + 1);
+    {
+      int next_local = 0, next_lane = LB + 2;
+      for (int q : Q) {
+        if (pos[q] >= 0) continue;
+        if (next_local < LB) place(q, next_local++);
+        else place(q, next_lane++);
+      }
+    }
+    Sweep sw{};
+    std::vector<int> ldbit(TB), other;
+    for (int j = 0; j < TB; ++j) ldbit[j] = mbit[qat[j]];
+    for (int b = 0; b < n; ++b)
+      if (std::find(ldbit.begin(), ldbit.end(), b) == ldbit.end()) other.push_back(b);
+    sw.n_other = (int)other.size();
+    for (int k = 0; k < sw.n_other; ++k) sw.other[k] = other[k];
+    auto ctl_pos = [&](int q) {
+      if (pos[q] >= 0) return pos[q];
+      const int b = mbit[q];
+      return TB + (int)(std::find(other.begin(), other.end(), b) - other.begin());
+    };
+
+    // ---- gates of the sweep in tile positions (engine R style: dense targets on local positions) ------
+    sw.r0 = (int)rops.size();
+    auto dense_target = [&](const GateOp& o, int q) {
+      int t[2], nt;
+      gate_targets(o, t, &nt);
+      return (nt > 0 && t[0] == q) || (nt > 1 && t[1] == q);
+    };
+    auto next_use = [&](int q, int from) {
+      for (int gg = from; gg < g_end; ++gg)
+        if (dense_target(ops[gg], q)) return gg;
+      return n_ops + 1;
+    };
+    auto emit_swap = [&](int local, int lane) {
+      rops.push_back({R_SWAP, local, lane, 0, 0, -1, 0, 0});
+      const int ql = qat[local], qn = qat[lane];
+      qat[local] = qn; qat[lane] = ql;
+      pos[qn] = local; pos[ql] = lane;
+    };
+    auto make_local = [&](int q, int g_cur) {
+      if (pos[q] < LB) return;
+      int best = 0, best_use = -1;
+      for (int x = 0; x < LB; ++x) {
+        const int u = next_use(qat[x], g_cur + 1);
+        if (u > best_use) { best_use = u; best = x; }
+      }
+      emit_swap(best, pos[q]);
+    };
+    auto move_to = [&](int q, int X) {
+      if (pos[q] == X) return;
+      if (pos[q] >= LB) { emit_swap(X, pos[q]); return; }
+      const int Y = pos[q], Z = LB + 4;
+      emit_swap(Y, Z);
+      emit_swap(X, Z);
+    };
+    auto pair_mask = [&](int pt, int pc) {
+      if (pc >= LB) return 0;
+      int m = 0;
+      for (int h = 0; h < NA / 2; ++h) {
+        const int i0 = ((h >> pt) << (pt + 1)) | (h & ((1 << pt) - 1));
+        if ((i0 >> pc) & 1) m |= 1 << h;
+      }
+      return m;
+    };
+    for (int gg = g; gg < g_end; ++gg) {
+      const GateOp op = ops[gg];
+      switch (op.kind) {
+        case QCP_GATE_RX: case QCP_GATE_RY: case QCP_GATE_RZ: case QCP_GATE_H: {
+          make_local(op.a, gg);
+          const int type = op.kind == QCP_GATE_RX ? T_X : (op.kind == QCP_GATE_RZ ? T_Z : T_R);
+          rops.push_back({R_L1, pos[op.a], -1, type, gg, op.kind == QCP_GATE_H ? -1 : op.p, 0, 0});
+          break;
+        }
+        case QCP_GATE_CRX: case QCP_GATE_CRZ: {
+          make_local(op.b, gg);
+          const int pc = ctl_pos(op.a);
+          rops.push_back({R_L1, pos[op.b], pc, op.kind == QCP_GATE_CRX ? T_X : T_Z, gg, op.p,
+                          pair_mask(pos[op.b], pc), 0});
+          break;
+        }
+        case QCP_GATE_CNOT: {
+          make_local(op.b, gg);
+          const int pc = ctl_pos(op.a);
+          rops.push_back({R_CX, pos[op.b], pc, 0, gg, -1, pair_mask(pos[op.b], pc), 0});
+          break;
+        }
+        default:
+          move_to(op.a, 1);
+          move_to(op.b, 0);
+          rops.push_back({R_U4, 0, -1, 0, op.p, -1, 0, 0});
+          break;
+      }
+    }
+    // ---- the next sweep's seeds go to lane positions LB / LB + 1 (memory bits 0 / 1 at the store) ------
+    for (int k = 0; k < 2; ++k) {
+      const int P = LB + k, q = next_seed[k];
+      if (pos[q] == P) continue;
+      if (pos[q] < LB) { emit_swap(pos[q], P); continue; }
+      // lane -> lane: hop through a local position that does not hold the other seed
+      int x = 0;
+      while (qat[x] == next_seed[1 - k]) ++x;
+      emit_swap(x, pos[q]);
+      emit_swap(x, P);
+    }
+    sw.r1 = (int)rops.size();
+    // ---- store mapping: same memory bits, positions LB / LB + 1 on bits 0 / 1 -----------------------------
+    std::vector<int> rest;
+    for (int j = 0; j < TB; ++j)
+      if (ldbit[j] != 0 && ldbit[j] != 1) rest.push_back(ldbit[j]);
+    std::sort(rest.begin(), rest.end());
+    std::vector<int> stbit(TB);
+    {
+      int r = 0;
+      for (int j = 0; j < TB; ++j) stbit[j] = j == LB ? 0 : (j == LB + 1 ? 1 : rest[r++]);
+    }
+    for (int i = 0; i < 32; ++i) {
+      int lo = 0, so = 0, ll = 0, sl = 0;
+      for (int x = 0; x < LB; ++x)
+        if ((i >> x) & 1) { lo |= 1 << ldbit[x]; so |= 1 << stbit[x]; }
+      for (int y = 0; y < 5; ++y)
+        if ((i >> y) & 1) { ll |= 1 << ldbit[LB + y]; sl |= 1 << stbit[LB + y]; }
+      sw.ld_loc[i] = lo; sw.st_loc[i] = so; sw.ld_lane[i] = ll; sw.st_lane[i] = sl;
+    }
+    for (int j = 0; j < TB; ++j) { mbit[qat[j]] = stbit[j]; qatm[stbit[j]] = qat[j]; }
+    sweeps.push_back(sw);
+    g = g_end;
+  }
+  for (int q = 0; q < n; ++q) final_bit[q] = mbit[q];
+}
+
+TilePlan* tile_create(int n, int enc, int dtype, const GateOp* host_ops, int n_ops, int n_theta,
+                      int n_consts, const GateOp* d_ops, const double2* d_consts, int num_sms) {
+  if (!tile_supported(n, dtype)) return nullptr;
+  TilePlan* r = new TilePlan();
+  memset(r, 0, sizeof(*r));
+  r->n = n; r->enc = enc; r->dtype = dtype; r->n_gates = n_ops; r->n_theta = n_theta;
+  r->n_consts = n_consts; r->num_sms = num_sms;
+  r->LB = dtype == QCP_F64 ? 4 : 5;
+  r->TB = r->LB + 5;
+  r->d_gates = d_ops; r->d_consts = d_consts;
+  std::vector<ROp> rops;
+  std::vector<Sweep> sweeps;
+  plan_sweeps(host_ops, n_ops, n, r->LB, rops, sweeps, r->final_bit);
+  r->n_rops = (int)rops.size(); r->n_sweeps = (int)sweeps.size();
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes ? bytes : 16); };
+  alloc((void**)&r->d_rops, sizeof(ROp) * rops.size());
+  alloc((void**)&r->d_sweeps, sizeof(Sweep) * sweeps.size());
+  if (e == cudaSuccess && !rops.empty())
+    e = cudaMemcpy(r->d_rops, rops.data(), sizeof(ROp) * rops.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && !sweeps.empty())
+    e = cudaMemcpy(r->d_sweeps, sweeps.data(), sizeof(Sweep) * sweeps.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    set_error("engine T: CUDA allocation/copy failed: %s", cudaGetErrorString(e));
+    tile_destroy(r);
+    return nullptr;
+  }
+  return r;
+}
+
+void tile_destroy(TilePlan* r) {
+  if (!r) return;
+  cudaFree(r->d_rops); cudaFree(r->d_sweeps); cudaFree(r->d_slab); cudaFree(r->d_tpart);
+  delete r;
+}
+
+int tile_prepare(TilePlan* r, const void* d_theta, cudaStream_t) {
+  r->theta = d_theta;
+  return 0;
+}
+
+int tile_num_sweeps(const TilePlan* r) { return r ? r->n_sweeps : 0; }
+
+static int grow(void** ptr, size_t* have, size_t want) {
+  if (want <= *have) return 0;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr; *have = 0;
+  cudaError_t e = cudaMalloc(ptr, want);
+  if (e != cudaSuccess) { set_error("engine T: cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); return 1; }
+  *have = want;
+  return 0;
+}
+
+int tile_run(TilePlan* r, int S, bool backward, void* ws, long long B, void* grad_theta, cudaStream_t s) {
+  if (S != 1 && S != 6) { set_error("engine T: bad stream count %d", S); return 1; }
+  if (!r->theta && r->n_theta > 0) { set_error("engine T: qcp_prepare() has not run"); return 1; }
+  const size_t es = es_of(r->dtype);
+  const TlLayout L = tl_layout(es, r->LB, S, r->n, r->n_rops, r->n_gates, r->n_consts, backward);
+  if (L.total > 227 * 1024) { set_error("engine T: gate program needs %d bytes of shared memory", L.total); return 1; }
+  int grid = r->num_sms;
+  if ((long long)grid > B) grid = (int)B;
+  if (grid < 1) grid = 1;
+  const size_t stride = (size_t)(backward ? 2 : 1) * S << r->n;          // complex elements per CTA
+  if (grow(&r->d_slab, &r->slab_bytes, 2 * es * stride * (size_t)grid)) return 1;
+
+  TlArgs a{};
+  a.lay = L;
+  a.n = r->n; a.enc = r->enc; a.n_rops = r->n_rops; a.n_gates = r->n_gates; a.n_theta = r->n_theta;
+  a.n_consts = r->n_consts; a.n_sweeps = r->n_sweeps;
+  for (int q = 0; q < r->n; ++q) a.final_bit[q] = r->final_bit[q];
+  a.rops = r->d_rops; a.sweeps = r->d_sweeps; a.gates = r->d_gates; a.consts = r->d_consts;
+  a.theta = r->theta; a.ws = ws; a.B = B; a.slab = r->d_slab; a.slab_stride = stride;
+  if (backward) {
+    const int nt = r->n_theta > 0 ? r->n_theta : 1;
+    if (grow((void**)&r->d_tpart, &r->tpart_bytes, sizeof(double) * (size_t)grid * nt)) return 1;
+    a.theta_partials = r->d_tpart;
+    cudaError_t ez = cudaMemsetAsync(r->d_tpart, 0, sizeof(double) * (size_t)grid * nt, s);
+    if (ez != cudaSuccess) { set_error("engine T: cudaMemsetAsync failed: %s", cudaGetErrorString(ez)); return 1; }
+  }
+  const int rc = r->dtype == QCP_F64 ? tl_launch<double>(r->LB, S, backward, a, grid, L.total, s)
+                                     : tl_launch<float>(r->LB, S, backward, a, grid, L.total, s);
+  if (rc) return rc;
+  if (!backward) return 0;
+  const int tb = (r->n_theta + 127) / 128;
+  if (tb) {
+    if (r->dtype == QCP_F64)
+      tl_reduce_theta_kernel<double><<<tb, 128, 0, s>>>(r->d_tpart, grid, r->n_theta, static_cast<double*>(grad_theta));
+    else
+      tl_reduce_theta_kernel<float><<<tb, 128, 0, s>>>(r->d_tpart, grid, r->n_theta, static_cast<float*>(grad_theta));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("engine T: reduction launch failed: %s", cudaGetErrorString(e)); return 1; }
+  }
+  return 0;
+}
+
+}  // namespace qcp

@@ -1,0 +1,17 @@
+// qcpinn_b200 -- engine T kernels, float32 / complex64 instantiations (see qcp_tile.cuh).
+#include "qcp_tile.cuh"
+
+namespace qcp {
+namespace tl {
+
+template <>
+int tl_launch<float>(int LB, int S, bool backward, const TlArgs& a, int grid, size_t smem, cudaStream_t s) {
+#define TL_CALL(K, T, LBV, SV, BW) tl_launch_one(&K<T, LBV, SV>, a, grid, tl_warps(BW) * 32, smem, s, #K)
+  TL_INSTANTIATE(float, 5)
+#undef TL_CALL
+  set_error("engine T: no float32 kernel for %d local bits", LB);
+  return 1;
+}
+
+}  // namespace tl
+}  // namespace qcp

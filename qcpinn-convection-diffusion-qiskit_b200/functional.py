@@ -77,8 +77,9 @@ class Plan:
         _lib.check(rc, "qcp_plan_create")
         self.num_features = self.lib.qcp_plan_num_features(self._handle)
         self.fused_engine = self.n <= 4      # n > 4 runs on the per-sample statevector engines
-        # "feature" (n <= 4) | "register" (5..10 qubits in registers) | "global" (state in smem / L2)
-        self.engine = ("feature", "global", "register")[self.lib.qcp_plan_engine(self._handle)]
+        # "feature" (n <= 4) | "register" (5..10 qubits in registers) | "tiled" (up to 16 qubits,
+        # HBM slab swept through registers) | "global" (gate-by-gate fallback, QCP_ENGINE=L)
+        self.engine = ("feature", "global", "register", "tiled")[self.lib.qcp_plan_engine(self._handle)]
         # element type of X / u / r / grad_u / grad_r / grad_X (weights, jets, grads stay `dtype`)
         self.io_dtype = dtype
         if io_dtype is not None and io_dtype != dtype and self.fused_engine and dtype == torch.float64:

@@ -23,13 +23,18 @@ CASES = [
     ("cascade", 6, 1, "amplitude", 1),
     ("cross_mesh", 5, 2, "amplitude", None),
     # larger registers-resident shapes (engine R: lane/local swaps, diagonal blocks, Haar hops);
-    # float64 n = 10 runs on engine L
+    # float64 n = 10 runs on the tiled engine
     ("cross_mesh", 10, 2, "angle", None),
     ("sim_circ_15", 8, 1, "angle", 1),
     ("layered", 9, 1, "angle", None),
     ("cascade", 7, 1, "amplitude", None),
     ("farhi", 10, 1, "angle", 1),
     ("alternate", 7, 1, "angle", None),
+    # tiled engine (engine T: HBM slab swept through registers, controls on tile-index bits)
+    ("cross_mesh", 11, 1, "angle", None),
+    ("cascade", 12, 1, "angle", 1),
+    ("layered", 11, 1, "amplitude", None),
+    ("sim_circ_15", 13, 1, "angle", None),
 ]
 DTYPES = [torch.float64, torch.float32]
 
@@ -52,7 +57,7 @@ def test_layer_forward_backward(case, dtype):
 
     plan = F.Plan(prog, F.encoding_code(enc), dtype, 50, DEV)
     reg_max = 10 if dtype == torch.float32 else 9
-    assert plan.engine == ("register" if n <= reg_max else "global")
+    assert plan.engine == ("register" if n <= reg_max else "tiled")
     zd = z.to(DEV, dtype).requires_grad_(True)
     th = w["theta"].to(DEV, dtype).requires_grad_(True)
     qd = F.layer_apply(plan, zd, th)
