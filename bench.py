@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--no-secondary", action="store_true", help="skip the other dtype's line")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="eager steps (no CUDA-graph replay)")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the short runs of BASELINE configs 2-4 (other_configs)")
     ap.add_argument("--cpu-points", type=int, default=65_536)
     ap.add_argument("--cpu-steps", type=int, default=3)
     return ap.parse_args()
@@ -122,6 +124,78 @@ class ClockSampler:
             out.update(sm_mhz=statistics.median(hi), sm_max_mhz=max(mx), samples=len(sm))
         out["reasons"] = sorted(reasons)
         return out
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs 2-4: short runs of the same TrainStep at the other named shapes
+# ------------------------------------------------------------------------------------------------
+OTHER_CONFIGS = [
+    # key, ansatz, qubits, layers, residual points, plan dtype, timed steps
+    ("cfg2", "layered", 4, 1, 65_536, "f64", 10),
+    ("cfg3", "cross_mesh", 10, 2, 262_144, "f32", 3),
+    ("cfg4", "sim_circ_15", 16, 2, 16_384, "f32", 1),
+]
+
+
+def measure_other_configs(torch, qb, device, peaks, hbm_gbs):
+    """One JSON object per config: full train steps (sampling .. Adam .. loss.item()) of the named
+    shape on one GPU, with the SURVEY section 8(d) roofline of that shape beside it."""
+    from oracle.solver import flops_per_point
+    from qcpinn_b200.trainer.diffusion_train import TrainStep
+
+    out = {}
+    for key, ansatz, n, layers, pts, dname, steps in OTHER_CONFIGS:
+        try:
+            args = model_args(dname)
+            args.update(num_qubits=n, num_quantum_layers=layers, q_ansatz=ansatz)
+            torch.manual_seed(0)
+            logger = qb.Logging(os.path.join(tempfile.gettempdir(), "qcpinn_bench_cfg"))
+            model = qb.DVPDESolver(args, logger, device=device)
+            step = TrainStep(model, pts, None, use_graph=None if n <= 4 else False)
+            torch.manual_seed(1234)
+            for _ in range(5 if n <= 4 else 2):     # n <= 4: three eager steps, then graph replays
+                step()
+            torch.cuda.synchronize(device)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize(device)
+            ms = e0.elapsed_time(e1) / steps
+            value = pts / (ms * 1e-3)
+            fl_pt, _, _ = flops_per_point(n, layers, ansatz, haar=False, hidden=HIDDEN)
+            plan = model._plan(device)
+            entry = {
+                "workload": f"DVPDESolver {ansatz} {n}q L={layers} angle, Haar off, {pts} residual "
+                            f"points (+2x{pts // 3} IC/BC)",
+                "engine": plan.engine, "dtype": dname, "steps": steps, "ms_per_step": ms,
+                "value": value, "unit": "points/s",
+                "roofline_fma": {"flops_per_point": fl_pt, "achieved_tflops": value * fl_pt / 1e12,
+                                 "peak_tflops": peaks[dname] / 1e12,
+                                 "frac": value * fl_pt / peaks[dname]},
+            }
+            if n >= 11:
+                # SURVEY 8(d): bytes_per_point = 12 L * 2 * 2^n * sizeof(complex) * (6 + 2/3)
+                cbytes = 8 if dname == "f32" else 16
+                by_pt = 12 * layers * 2 * (2 ** n) * cbytes * (6 + 2 / 3)
+                entry["roofline_hbm"] = {"bytes_per_point": by_pt, "achieved_gbs": value * by_pt / 1e9,
+                                         "peak_gbs": hbm_gbs, "frac": value * by_pt / 1e9 / hbm_gbs}
+            out[key] = entry
+            del model, step
+            torch.cuda.empty_cache()
+        except Exception as exc:      # a failing side config must not take the headline line down
+            out[key] = {"error": f"{type(exc).__name__}: {exc}"}
+    return out
+
+
+def measured_hbm_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -323,6 +397,10 @@ def run_ours(ns):
             "roofline": roof(secondary, other), "roofline_step": step_roof(secondary, other),
             "clocks": {k: secondary["clocks"][k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
         }
+    if world == 1 and not ns.no_configs:
+        hbm, src = measured_hbm_gbs()
+        line["other_configs"] = measure_other_configs(torch, qb, device, peaks, hbm)
+        line["other_configs"]["hbm_peak_source"] = src
     if world == 1 and not ns.no_cpu:
         line["cpu_baseline"] = cpu_baseline(ns.cpu_points, ns.cpu_steps)
     print(json.dumps(line), flush=True)
