@@ -154,6 +154,18 @@ int qcp_solver_backward_finish(qcp_plan_t* plan, const void* theta, const qcp_ml
 int qcp_sample_targets(const float* rnd, long long n, const float* lo_hi, int kind,
                        double diffusion, double v_x, double v_y, float* X, float* y, void* stream);
 
+/* One MSELoss term of the train objective (reference trainer/diffusion_train.py:44-47) and its
+ * cotangent in one launch: *loss_slot += mean((pred - target)^2) (DEVICE double, zeroed by the
+ * caller), grad[i] = 2 * weight * (pred[i] - target[i]) / n.  float32 like the module tensors. */
+int qcp_mse_seed(const float* pred, const float* target, long long n, double weight, float* grad,
+                 double* loss_slot, void* stream);
+
+/* Finish the flat float32 gradient [n_grad | n_extra scalars] of a data-parallel step in one launch:
+ * scale everything by pre_scale (1 / world size after the sum all-reduce), then clip the gradient
+ * part to max_norm exactly like torch.nn.utils.clip_grad_norm_ (reference :85). */
+int qcp_clip_grads(float* flat, int n_grad, int n_extra, double pre_scale, double max_norm,
+                   void* stream);
+
 /* FMA-pipe micro-benchmark used as the roofline denominator: runs
  * ``iters`` dependent-chain FMA rounds on every SM and returns achieved FLOP/s. */
 int qcp_bench_fma(int dtype, int iters, double* flops_per_s, void* stream);

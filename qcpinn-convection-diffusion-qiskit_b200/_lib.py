@@ -57,6 +57,10 @@ SIGNATURES = {
     "qcp_sample_targets": (_c_int, [_c_void_p, _c_ll, ctypes.POINTER(ctypes.c_float), _c_int,
                                     ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                     _c_void_p, _c_void_p, _c_void_p]),
+    "qcp_mse_seed": (_c_int, [_c_void_p, _c_void_p, _c_ll, ctypes.c_double, _c_void_p, _c_void_p,
+                              _c_void_p]),
+    "qcp_clip_grads": (_c_int, [_c_void_p, _c_int, _c_int, ctypes.c_double, ctypes.c_double,
+                                _c_void_p]),
     "qcp_bench_fma": (_c_int, [_c_int, _c_int, _dptr, _c_void_p]),
 }
 

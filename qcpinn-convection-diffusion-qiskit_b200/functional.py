@@ -285,6 +285,30 @@ def solver_backward_many(plan: Plan, items, mlp, theta):
     return views, gxs
 
 
+def mse_seed(plan: Plan, pred, target, weight, grad_out, loss_slot):
+    """loss_slot (device float64 scalar view) += mean((pred - target)^2);
+    grad_out = 2 * weight * (pred - target) / n.  All arrays float32, contiguous."""
+    n = pred.numel()
+    if n == 0:
+        return
+    with torch.cuda.device(plan.device):
+        rc = plan.lib.qcp_mse_seed(
+            ctypes.c_void_p(pred.data_ptr()), ctypes.c_void_p(target.data_ptr()), n, float(weight),
+            ctypes.c_void_p(grad_out.data_ptr()), ctypes.c_void_p(loss_slot.data_ptr()),
+            plan._stream())
+    _lib.check(rc, "qcp_mse_seed")
+    _count(1)
+
+
+def clip_grads(plan: Plan, flat, n_grad, n_extra, pre_scale, max_norm):
+    """In place on the flat float32 buffer [grads | extras]: x pre_scale, then clip_grad_norm_."""
+    with torch.cuda.device(plan.device):
+        rc = plan.lib.qcp_clip_grads(ctypes.c_void_p(flat.data_ptr()), int(n_grad), int(n_extra),
+                                     float(pre_scale), float(max_norm), plan._stream())
+    _lib.check(rc, "qcp_clip_grads")
+    _count(1)
+
+
 def _grad_in(plan: Plan, g, like, io=False):
     if g is None:
         return None

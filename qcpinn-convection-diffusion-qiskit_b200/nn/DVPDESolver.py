@@ -191,6 +191,77 @@ class DVPDESolver(nn.Module):
             self.logger.print(f"Forward pass failed: {str(e)}")
             raise
 
+    # -- fused train step (no autograd graph) ------------------------------------------------------
+    N_LOSS_SLOTS = 4            # loss, loss_r, loss_bc, loss_ic behind the flat gradient
+
+    def flat_grad_buffer(self):
+        """One persistent float32 buffer [all parameter gradients | 4 loss scalars]; every
+        ``p.grad`` is a view into it, in ``parameters()`` order (= the kernels' gradient order)."""
+        buf = getattr(self, "_flat_grad", None)
+        params = [p for p in self.parameters() if p.requires_grad]
+        numel = sum(p.numel() for p in params)
+        if buf is None or buf.numel() != numel + self.N_LOSS_SLOTS or buf.device != params[0].device:
+            buf = torch.zeros(numel + self.N_LOSS_SLOTS, dtype=torch.float32, device=params[0].device)
+            self._flat_grad = buf
+        off = 0
+        for p in params:
+            n = p.numel()
+            view = buf[off:off + n].view_as(p)
+            if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                p.grad = view
+            off += n
+        return buf, numel
+
+    def supports_fused_step(self):
+        try:
+            dev = self.quantum_layer.params.device
+            return dev.type == "cuda" and self._plan(dev).fused_engine and \
+                all(p.dtype == torch.float32 for p in self.parameters())
+        except Exception:
+            return False
+
+    def train_step_grads(self, batch, coeffs, weights=(2.0, 4.0, 2.0)):
+        """The reference objective ``w_r MSE_r + w_bc MSE_bc + w_ic MSE_ic`` (reference
+        trainer/diffusion_train.py:30-49) and ALL its parameter gradients without an autograd
+        graph: forward kernels -> MSE seeds -> adjoint kernels -> one cast into the flat gradient
+        buffer.  ``batch`` = (X_ics, u_ics, X_bcs, u_bcs, X_res, r_res), float32 on the model's
+        device.  Returns the flat buffer and the number of gradient elements; the buffer's last
+        four slots hold (loss, loss_r, loss_bc, loss_ic)."""
+        X_ics, u_ics, X_bcs, u_bcs, X_res, r_res = batch
+        dev = self._device_of(X_res)
+        plan = self._plan(dev)
+        if not plan.fused_engine:
+            raise NotImplementedError("train_step_grads covers the n <= 4 engine")
+        key = self.quantum_layer.theta_key()
+        tt, mt = plan.typed_weights(self.quantum_layer.params, self._mlp_tensors(), key)
+        plan.prepare(tt, key)
+        w_r, w_bc, w_ic = weights
+        nb, ni, nr = X_bcs.shape[0], X_ics.shape[0], X_res.shape[0]
+        X_val = torch.cat([X_bcs.detach(), X_ics.detach()]).to(plan.io_dtype)
+        X_r = X_res.detach().to(plan.io_dtype).contiguous()
+        ws_v = plan.workspace(nb + ni, F.MODE_VALUE)
+        ws_r = plan.workspace(nr, F.MODE_RESIDUAL)
+        u_v, _, _ = plan.solver_forward(X_val, mt, F.MODE_VALUE, save=ws_v)
+        _, r_r, _ = plan.solver_forward(X_r, mt, F.MODE_RESIDUAL, coeffs, save=ws_r)
+        terms = torch.zeros(3, dtype=torch.float64, device=dev)            # r, bc, ic
+        gu_v = torch.empty_like(u_v)
+        gr = torch.empty_like(r_r)
+        F.mse_seed(plan, u_v[:nb], u_bcs.detach().reshape(-1).contiguous(), w_bc, gu_v[:nb], terms[1:2])
+        F.mse_seed(plan, u_v[nb:], u_ics.detach().reshape(-1).contiguous(), w_ic, gu_v[nb:], terms[2:3])
+        F.mse_seed(plan, r_r, r_res.detach().reshape(-1).contiguous(), w_r, gr, terms[0:1])
+        views, _ = F.solver_backward_many(
+            plan, [(X_val, gu_v, None, F.MODE_VALUE, None, ws_v, False),
+                   (X_r, None, gr, F.MODE_RESIDUAL, coeffs, ws_r, False)], mt, tt)
+        flat, numel = self.flat_grad_buffer()
+        flat[:numel].copy_(views[0]._base)                                   # one cast kernel
+        wvec = getattr(self, "_loss_weights", None)
+        if wvec is None or wvec.device != dev:
+            wvec = torch.tensor([w_r, w_bc, w_ic], dtype=torch.float64, device=dev)
+            self._loss_weights = wvec
+        flat[numel + 1:numel + 4].copy_(terms)
+        flat[numel:numel + 1].copy_((terms * wvec).sum().reshape(1))
+        return flat, numel
+
     def taylor_streams(self, X: torch.Tensor):
         """No-grad evaluation helper: (B,6) = u, u_t, u_x, u_y, u_xx, u_yy."""
         plan = self._plan(self._device_of(X))

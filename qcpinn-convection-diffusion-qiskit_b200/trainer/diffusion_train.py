@@ -60,6 +60,11 @@ class TrainStep:
             use_graph = bool(model.args.get("cuda_graph", True))
         self.use_graph = bool(use_graph) and on_cuda
         self.fuse_calls = bool(model.args.get("fuse_model_calls", True))
+        # whole-step fast path: forward -> MSE seeds -> adjoint kernels -> flat gradient, without an
+        # autograd graph (same numbers; args["fuse_step"] = False keeps the autograd route)
+        self.fuse_step = (bool(model.args.get("fuse_step", True)) and on_cuda
+                          and getattr(model, "supports_fused_step", lambda: False)()
+                          and model.optimizer is not None)
         self._eager_calls = 0
         self._graphs = {}          # "device" / "host" -> (graph, static outputs, static batch)
         self.last_terms = None     # (loss, loss_r, loss_bc, loss_ic) tensors of the last step
@@ -108,6 +113,32 @@ class TrainStep:
             model.optimizer.step()
         return loss.detach()
 
+    def _fused_device_step(self, batch=None):
+        """sample -> train_step_grads -> (all-reduce) -> average + clip -> Adam, on the flat
+        gradient buffer.  Returns (loss, loss_r, loss_bc, loss_ic) device scalars (rank-averaged
+        loss, local terms)."""
+        from .. import functional as F
+
+        model = self.model
+        if batch is None:
+            batch = self.sample()
+        flat, numel = model.train_step_grads(batch, DIFFUSION_COEFFS)
+        world = 1
+        if self.averager is not None:
+            import torch.distributed as dist
+
+            # gradients and the scheduler metric share one all-reduce; the local terms are kept
+            local_terms = flat[numel + 1:numel + 4].clone()
+            dist.all_reduce(flat[:numel + 1], op=dist.ReduceOp.SUM, group=self.averager.group)
+            world = self.averager.world
+            self.averager.calls += 1
+        else:
+            local_terms = flat[numel + 1:numel + 4]
+        plan = model._plan(model.quantum_layer.params.device)
+        F.clip_grads(plan, flat, numel, 1, 1.0 / world, self.max_norm)
+        model.optimizer.step()
+        return flat[numel].clone(), local_terms[0], local_terms[1], local_terms[2]
+
     def _host_update(self, loss):
         """plateau scheduler -> loss.item() -> history (needs the host value)."""
         model = self.model
@@ -136,8 +167,11 @@ class TrainStep:
         mode = "thread_local" if self.averager is not None else "global"
         launches0 = F.launch_counter
         with torch.cuda.graph(graph, capture_error_mode=mode):
-            loss, _, loss_r, loss_bc, loss_ic = self.objective(static_batch)
-            reduced = self._device_update(loss)
+            if self.fuse_step:
+                reduced, loss_r, loss_bc, loss_ic = self._fused_device_step(static_batch)
+            else:
+                loss, _, loss_r, loss_bc, loss_ic = self.objective(static_batch)
+                reduced = self._device_update(loss)
         plan.invalidate()
         outs = (reduced, loss_r.detach(), loss_bc.detach(), loss_ic.detach())
         # kernels of this library inside one replay (capture only recorded them)
@@ -167,8 +201,11 @@ class TrainStep:
         self._eager_calls += 1
         if batch is not None:
             batch = tuple(t.to(self.model.device, non_blocking=True) for t in batch)
-        loss, _, loss_r, loss_bc, loss_ic = self.objective(batch)
-        reduced = self._device_update(loss)
+        if self.fuse_step:
+            reduced, loss_r, loss_bc, loss_ic = self._fused_device_step(batch)
+        else:
+            loss, _, loss_r, loss_bc, loss_ic = self.objective(batch)
+            reduced = self._device_update(loss)
         self.last_terms = (reduced, loss_r.detach(), loss_bc.detach(), loss_ic.detach())
         return self._host_update(reduced)
 

@@ -305,3 +305,41 @@ def test_forward_many_equals_separate_calls(tmp_path, dtype):
     tol = 1e-9 if dtype == "float64" else 2e-5
     for a, b in zip(grads[True][1], grads[False][1]):
         assert rel_err(a, b) < max(tol, 2e-6)       # grads are float32 tensors
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_fused_step_equals_autograd_route(tmp_path, dtype):
+    """TrainStep's graph-free fast path (train_step_grads + qcp_mse_seed + qcp_clip_grads) against
+    the autograd route (objective -> loss.backward -> clip_grad_norm_): same loss terms, same
+    clipped gradients, same parameters after Adam."""
+    from qcpinn_b200.trainer.diffusion_train import DIFFUSION_COEFFS, TrainStep
+
+    batches = osolver.make_batches(96, seed=21)
+    batch = tuple(batches[k].to(DEV) for k in ("X_ic", "u_ic", "X_bc", "u_bc", "X_res", "r_res"))
+    ma = _model(tmp_path / "a", dtype=dtype)
+    mf = _model(tmp_path / "f", dtype=dtype)
+    mf.load_state_dict(ma.state_dict())
+    sa = TrainStep(ma, 96, use_graph=False)
+    sa.fuse_step = False
+    sf = TrainStep(mf, 96, use_graph=False)
+    assert sf.fuse_step and mf.supports_fused_step()
+
+    # gradients before clipping
+    loss, _, lr_, lbc, lic = sa.objective(tuple(t.clone() for t in batch))
+    loss.backward()
+    flat, numel = mf.train_step_grads(batch, DIFFUSION_COEFFS)
+    want = torch.cat([p.grad.reshape(-1) for p in ma.parameters()])
+    assert rel_err(flat[:numel], want) < 1e-5
+    got_terms = flat[numel:numel + 4].cpu()
+    for g, w in zip(got_terms, (loss, lr_, lbc, lic)):
+        assert abs(g.item() - w.item()) < 1e-5 * abs(w.item())
+    for p in ma.parameters():
+        p.grad = None
+
+    # full steps: parameters stay together
+    for _ in range(3):
+        va = sa(tuple(t.clone() for t in batch))
+        vf = sf(batch)
+        assert abs(va - vf) < 2e-5 * abs(va)
+    for pa, pf in zip(ma.parameters(), mf.parameters()):
+        assert rel_err(pf, pa) < 1e-4
