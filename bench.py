@@ -235,7 +235,7 @@ def run_ours(ns):
     from qcpinn_b200.trainer.diffusion_train import TrainStep, _make_averager
     import torch.distributed as dist
 
-    os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's banner off stdout (one JSON line)
+    os.environ.pop("NCCL_DEBUG", None)            # any level >= VERSION prints a banner on stdout
     rank, world, local = init_from_env()
     if world != ns.gpus and world > 1:
         raise SystemExit(f"--gpus {ns.gpus} but WORLD_SIZE={world}")
