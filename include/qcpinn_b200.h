@@ -89,6 +89,10 @@ int qcp_plan_num_features(const qcp_plan_t* plan);
 enum qcp_engine { QCP_ENGINE_FEATURE = 0, QCP_ENGINE_GLOBAL = 1, QCP_ENGINE_REGISTER = 2, QCP_ENGINE_TILED = 3 };
 int qcp_plan_engine(const qcp_plan_t* plan);
 
+/* One-line description of the compiled plan (engine, layout, sweep / op counts) for logs and tests;
+ * written to buf (HOST, NUL terminated, at most len bytes). */
+int qcp_plan_describe(const qcp_plan_t* plan, char* buf, int len);
+
 /* Element type of the caller-facing arrays of the solver entry points (X, u, r, streams, grad_u,
  * grad_r, grad_X).  Default = the plan dtype.  A QCP_F64 plan (n <= 4) may be switched to QCP_F32
  * I/O: arithmetic, weights, gradients and the saved jets stay float64, but the float32 tensors of

@@ -1,0 +1,130 @@
+// qcpinn_b200 -- host-side layout bookkeeping shared by the engine R / engine T planners.
+//
+// A register tile has LB "local" positions (bits of the per-lane amplitude index) and up to five
+// "lane" positions.  Dense gates need their target on a local position; the planners move qubits
+// with SWAP (one local <-> lane exchange through warp shuffles) or PERM (any permutation of the
+// positions through the warp's shared-memory buffer, cheaper from two exchanges on).
+#pragma once
+
+#include <algorithm>
+#include <utility>
+#include <vector>
+
+#include "qcp_reg.cuh"
+
+namespace qcp {
+
+struct LayoutTracker {
+  int LB = 0;
+  int perm_min = 4;        // exchanges from which one PERM beats a chain of SWAPs (measured)
+  std::vector<int> pos;    // position of qubit q inside the tile, or -1
+  std::vector<int> qat;    // qubit at tile position j
+  std::vector<rg::ROp>* rops = nullptr;
+
+  void exchange(int a, int b) {       // bookkeeping of one transposition of positions
+    const int qa = qat[a], qb = qat[b];
+    qat[a] = qb; qat[b] = qa;
+    if (qb >= 0) pos[qb] = a;
+    if (qa >= 0) pos[qa] = b;
+  }
+
+  void emit_swap(int local, int lane) {
+    rops->push_back({rg::R_SWAP, local, lane, 0, 0, -1, 0, 0});
+    exchange(local, lane);
+  }
+
+  // transpositions (any two positions each), applied in order
+  void emit_perm(const std::vector<std::pair<int, int>>& tr) {
+    if (tr.empty()) return;
+    if ((int)tr.size() < perm_min) {
+      // few exchanges: shuffle swaps are cheaper than the shared-memory round trip
+      for (const auto& t : tr) {
+        const int a = std::min(t.first, t.second), b = std::max(t.first, t.second);
+        if (a == b) continue;
+        if (a < LB && b >= LB) { emit_swap(a, b); continue; }
+        if (a >= LB) {                   // lane <-> lane through local position 0
+          emit_swap(0, a); emit_swap(0, b); emit_swap(0, a);
+        } else {                         // local <-> local through the first lane position
+          emit_swap(a, LB); emit_swap(b, LB); emit_swap(a, LB);
+        }
+      }
+      return;
+    }
+    int cur[16];                       // cur[j] = source position of what ends up at j
+    for (int j = 0; j < 16; ++j) cur[j] = j;
+    for (const auto& t : tr) {
+      std::swap(cur[t.first], cur[t.second]);
+      exchange(t.first, t.second);
+    }
+    int icur[16];
+    for (int j = 0; j < 16; ++j) icur[cur[j]] = j;
+    // PermMasks of `src` (src[j] = source position of destination position j)
+    auto masks = [&](const int* src, rg::ROp& op) {
+      // bank swizzle: a local source bit x that becomes lane bit y toggles column bit y
+      unsigned col[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int y = 0; y < 5; ++y)
+        if (src[LB + y] < LB) col[src[LB + y]] = 1u << y;
+      auto slot_mask = [&](int sp) {          // slot bits toggled by the bit of source position sp
+        return sp < LB ? ((32u << sp) | col[sp]) : (1u << (sp - LB));
+      };
+      uint32_t w[6] = {0, 0, 0, 0, 0, 0};
+      for (int x = 0; x < LB; ++x) w[x / 3] |= slot_mask(x) << (10 * (x % 3));
+      for (int j = 0; j < LB + 5; ++j) w[2 + j / 3] |= slot_mask(src[j]) << (10 * (j % 3));
+      op.pc = (int32_t)w[0]; op.type = (int32_t)w[1]; op.g = (int32_t)w[2]; op.p = (int32_t)w[3];
+      op.m = (int32_t)w[4]; op.pad = (int32_t)w[5];
+    };
+    rg::ROp fwd{rg::R_PERM, 0, 0, 0, 0, 0, 0, 0}, bwd{rg::R_PERMB, 0, 0, 0, 0, 0, 0, 0};
+    masks(cur, fwd);
+    masks(icur, bwd);
+    rops->push_back(fwd);
+    rops->push_back(bwd);
+  }
+
+  // Bring lane-resident qubit q (needed by gate g_cur) to a local position, together with the
+  // following lane-resident dense targets while that evicts only qubits needed later than them.
+  //   targets(g, t, &nt): dense targets of gate g (nt = 0 for gates that need none)
+  template <typename TargetsFn>
+  void make_local(int q, int g_cur, int g_limit, TargetsFn targets) {
+    if (pos[q] < LB) return;
+    auto next_use = [&](int qq, int from) {
+      for (int g = from; g < g_limit; ++g) {
+        int t[2], nt;
+        targets(g, t, &nt);
+        for (int k = 0; k < nt; ++k)
+          if (t[k] == qq) return g;
+      }
+      return g_limit + 1;
+    };
+    // without PERM every exchange is a shuffle swap of its own: bring in only what is needed now
+    const int max_in = perm_min > LB ? 1 : LB;
+    std::vector<int> incoming{q}, in_use{g_cur};
+    for (int g = g_cur + 1; g < g_limit && (int)incoming.size() < max_in; ++g) {
+      int t[2], nt;
+      targets(g, t, &nt);
+      for (int k = 0; k < nt && (int)incoming.size() < max_in; ++k)
+        if (pos[t[k]] >= LB && std::find(incoming.begin(), incoming.end(), t[k]) == incoming.end()) {
+          incoming.push_back(t[k]);
+          in_use.push_back(g);
+        }
+    }
+    std::vector<std::pair<int, int>> loc;          // (next use, local position), farthest first
+    for (int x = 0; x < LB; ++x) loc.push_back({next_use(qat[x], g_cur + 1), x});
+    std::sort(loc.begin(), loc.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+      return a.first != b.first ? a.first > b.first : a.second < b.second;
+    });
+    std::vector<std::pair<int, int>> tr;
+    for (size_t k = 0; k < incoming.size() && k < loc.size(); ++k) {
+      if (k > 0 && loc[k].first <= in_use[k]) break;   // that local qubit is needed sooner
+      tr.push_back({loc[k].second, pos[incoming[k]]});
+    }
+    emit_perm(tr);
+  }
+
+  // put qubit q on position X (any), displacing whatever sits there
+  void move_to(int q, int X) {
+    if (pos[q] == X) return;
+    emit_perm({{pos[q], X}});
+  }
+};
+
+}  // namespace qcp

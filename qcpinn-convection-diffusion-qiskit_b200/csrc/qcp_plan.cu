@@ -708,6 +708,14 @@ int qcp_plan_engine(const qcp_plan_t* p) {
   return p->reg ? QCP_ENGINE_REGISTER : (p->tile ? QCP_ENGINE_TILED : QCP_ENGINE_GLOBAL);
 }
 
+int qcp_plan_describe(const qcp_plan_t* p, char* buf, int len) {
+  if (!p || !buf || len < 1) { set_error("qcp_plan_describe: bad argument"); return 1; }
+  if (p->reg) reg_describe(p->reg, buf, len);
+  else if (p->tile) tile_describe(p->tile, buf, len);
+  else snprintf(buf, len, "engine=%s n=%d ops=%d features=%d", p->engine_l ? "global" : "feature", p->n, p->n_ops, p->F);
+  return 0;
+}
+
 int qcp_plan_set_io_dtype(qcp_plan_t* p, int io_dtype) {
   if (!p || (io_dtype != QCP_F32 && io_dtype != QCP_F64)) { set_error("qcp_plan_set_io_dtype: bad argument"); return 1; }
   if (io_dtype == p->dtype) { p->io_f32 = 0; return 0; }

@@ -1,9 +1,11 @@
 // qcpinn_b200 -- engine R host side: physical-program compiler, phase-table builder, gradient
 // projection of the diagonal blocks, launch plumbing.  Device code: qcp_reg.cuh.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 
+#include "qcp_layout.hpp"
 #include "qcp_reg.cuh"
 
 namespace qcp {
@@ -97,6 +99,7 @@ __global__ void rg_diag_grad_kernel(int n, int LB, const BlkPos* __restrict__ bp
 // ---------------------------------------------------------------------------------------------
 struct RegPlan {
   int n, enc, dtype, LB, G, n_gates, n_theta, n_consts, n_rops, n_blk, n_dg, num_sms;
+  int kind_count[8];
   int meas_pos[kMaxQubitsReg];
   ROp* d_rops;
   const GateOp* d_gates;      // borrowed from the owning plan
@@ -127,43 +130,24 @@ int reg_supported(int n, int dtype) {
 // Translate the logical gate list into physical ops (see the header comment of qcp_reg.cuh).
 static void compile_physical(const GateOp* ops, int n_ops, int n, int LB, std::vector<ROp>& rops,
                              std::vector<BlkPos>& bpos, std::vector<DiagGate>& dgs, int* meas_pos) {
-  std::vector<int> pos(n), qat(n);
-  for (int q = 0; q < n; ++q) { pos[q] = n - 1 - q; qat[n - 1 - q] = q; }
-  auto dense_target = [&](const GateOp& g, int q) {
-    switch (g.kind) {
-      case QCP_GATE_RX: case QCP_GATE_RY: case QCP_GATE_H: return g.a == q;
-      case QCP_GATE_CRX: case QCP_GATE_CNOT: return g.b == q;
-      case QCP_GATE_U4: return g.a == q || g.b == q;
-      default: return false;
+  LayoutTracker lt;
+  lt.LB = LB;
+  lt.pos.assign(n, -1);
+  lt.qat.assign(16, -1);
+  lt.rops = &rops;
+  for (int q = 0; q < n; ++q) { lt.pos[q] = n - 1 - q; lt.qat[n - 1 - q] = q; }
+  std::vector<int>& pos = lt.pos;
+  auto targets = [&](int g, int* t, int* nt) {
+    *nt = 0;
+    switch (ops[g].kind) {
+      case QCP_GATE_RX: case QCP_GATE_RY: case QCP_GATE_H: t[(*nt)++] = ops[g].a; break;
+      case QCP_GATE_CRX: case QCP_GATE_CNOT: t[(*nt)++] = ops[g].b; break;
+      case QCP_GATE_U4: t[(*nt)++] = ops[g].a; t[(*nt)++] = ops[g].b; break;
+      default: break;     // diagonal gates live in phase tables: no local target needed
     }
   };
-  auto next_use = [&](int q, int from) {
-    for (int g = from; g < n_ops; ++g)
-      if (dense_target(ops[g], q)) return g;
-    return n_ops + 1;
-  };
-  auto emit_swap = [&](int local, int lane) {
-    rops.push_back({R_SWAP, local, lane, 0, 0, -1, 0, 0});
-    const int ql = qat[local], qn = qat[lane];
-    qat[local] = qn; qat[lane] = ql;
-    pos[qn] = local; pos[ql] = lane;
-  };
-  auto make_local = [&](int q, int g_cur) {
-    if (pos[q] < LB) return;
-    int best = 0, best_use = -1;
-    for (int x = 0; x < LB; ++x) {
-      const int u = next_use(qat[x], g_cur + 1);
-      if (u > best_use) { best_use = u; best = x; }
-    }
-    emit_swap(best, pos[q]);
-  };
-  auto move_to = [&](int q, int X) {
-    if (pos[q] == X) return;
-    if (pos[q] >= LB) { emit_swap(X, pos[q]); return; }
-    const int Y = pos[q], Z = LB;   // hop through the first lane position
-    emit_swap(Y, Z);
-    emit_swap(X, Z);
-  };
+  auto make_local = [&](int q, int g_cur) { lt.make_local(q, g_cur, n_ops, targets); };
+  auto move_to = [&](int q, int X) { lt.move_to(q, X); };
 
   // pairs h (target bit removed) whose amplitudes have the LOCAL control bit set
   auto pair_mask = [&](int pt, int pc) {
@@ -235,6 +219,7 @@ RegPlan* reg_create(int n, int enc, int dtype, const GateOp* host_ops, int n_ops
   std::vector<DiagGate> dgs;
   compile_physical(host_ops, n_ops, n, r->LB, rops, bpos, dgs, r->meas_pos);
   r->n_rops = (int)rops.size(); r->n_blk = (int)bpos.size(); r->n_dg = (int)dgs.size();
+  for (const ROp& o : rops) r->kind_count[o.kind & 7]++;
   const size_t es = es_of(dtype);
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes ? bytes : 16); };
@@ -278,6 +263,12 @@ int reg_prepare(RegPlan* r, const void* d_theta, cudaStream_t s) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("engine R: table build launch failed: %s", cudaGetErrorString(e)); return 1; }
   return 0;
+}
+
+int reg_describe(const RegPlan* r, char* buf, int len) {
+  return snprintf(buf, len, "engine=register n=%d LB=%d lanes_per_vector=%d ops=%d (dense=%d cnot=%d swap=%d diag_blocks=%d "
+                  "covering %d diagonal gates, haar=%d)", r->n, r->LB, r->G, r->n_rops, r->kind_count[R_L1],
+                  r->kind_count[R_CX], r->kind_count[R_SWAP], r->n_blk, r->n_dg, r->kind_count[R_U4]);
 }
 
 long long reg_state_elems(const RegPlan* r, long long B, int S) {

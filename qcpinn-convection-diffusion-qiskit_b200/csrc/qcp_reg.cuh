@@ -35,7 +35,7 @@
 namespace qcp {
 namespace rg {
 
-enum RKind { R_L1 = 0, R_CX = 1, R_SWAP = 2, R_DIAG = 3, R_U4 = 4 };
+enum RKind { R_L1 = 0, R_CX = 1, R_SWAP = 2, R_DIAG = 3, R_U4 = 4, R_PERM = 5, R_PERMB = 6 };
 enum RType { T_X = 0, T_R = 1, T_Z = 2 };   // RX-like (c, -is; -is, c) | real 2x2 (RY, H) | RZ-like diag(c - is, c + is)
 
 // physical op: positions are bit positions of the amplitude index (0..LB-1 local, LB.. lane)
@@ -48,6 +48,8 @@ struct ROp {
   int32_t p;      // L1: theta index for the gradient or -1
   int32_t m;      // L1/CX with a LOCAL control: bit h set = pair h (target bit removed) is active
   int32_t pad;
+  // PERM / PERMB: two consecutive slots; pc .. pad (6 words) hold the PermMasks of the permutation
+  // (PERM, executed by the forward program) and of its inverse (PERMB, executed in reverse)
 };
 
 struct DiagGate {   // one diagonal gate of a block (table builder + gradient projection)
@@ -281,6 +283,61 @@ __device__ __forceinline__ void swap_ll(T (&ax)[1 << LB], T (&ay)[1 << LB], int 
   }
 }
 
+// Arbitrary permutation of the (local | lane) index bits of a register tile through a warp-private
+// shared-memory buffer of 32 * 2^LB complex values: ONE round trip instead of one shuffle swap per
+// exchanged pair.  Element (i, lane) is written at slot (i << 5 | lane) ^ W(i) and read back from
+// slot R(lane) ^ R(i): every destination bit contributes the slot mask of its source position, and
+// a per-op bank swizzle (a local source bit that becomes lane bit y toggles COLUMN bit y) makes the
+// lane -> column map of the permuted read a bijection, so the write and the read are both bank-
+// conflict free.  All masks are precomputed by the host (LayoutTracker::emit_perm):
+//   w[0..1]  write masks of the LB local bits (row bit | swizzle), 10 bits each, three per word
+//   w[2..5]  read masks of the 10 destination positions, 10 bits each, three per word
+struct PermMasks {
+  uint32_t w[6];
+};
+
+__device__ __forceinline__ PermMasks perm_masks_of(const ROp& op) {
+  return {{(uint32_t)op.pc, (uint32_t)op.type, (uint32_t)op.g, (uint32_t)op.p, (uint32_t)op.m, (uint32_t)op.pad}};
+}
+
+__device__ __forceinline__ unsigned perm_field(const PermMasks& pm, int base, int j) {
+  return (pm.w[base + j / 3] >> (10 * (j % 3))) & 1023u;
+}
+
+template <typename T, int LB>
+__device__ __forceinline__ void perm_apply(T (&ax)[1 << LB], T (&ay)[1 << LB], C2<T>* buf,
+                                           const PermMasks& pm, int lane) {
+  constexpr int NA = 1 << LB;
+  unsigned wl[LB], rl[LB];
+#pragma unroll
+  for (int x = 0; x < LB; ++x) {
+    wl[x] = perm_field(pm, 0, x);
+    rl[x] = perm_field(pm, 2, x);
+  }
+  unsigned rn = 0;
+#pragma unroll
+  for (int y = 0; y < 5; ++y) rn ^= ((lane >> y) & 1) ? perm_field(pm, 2, LB + y) : 0u;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < NA; ++i) {
+    unsigned sl = lane;
+#pragma unroll
+    for (int x = 0; x < LB; ++x)
+      if ((i >> x) & 1) sl ^= wl[x];
+    buf[sl] = {ax[i], ay[i]};
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < NA; ++i) {
+    unsigned sl = rn;
+#pragma unroll
+    for (int x = 0; x < LB; ++x)
+      if ((i >> x) & 1) sl ^= rl[x];
+    const C2<T> v = buf[sl];
+    ax[i] = v.x; ay[i] = v.y;
+  }
+}
+
 template <typename T, int LB>
 __device__ __forceinline__ void diag_apply(T (&ax)[1 << LB], T (&ay)[1 << LB], const C2A<T>* tab,
                                            int G, bool dag) {
@@ -418,6 +475,12 @@ __device__ __forceinline__ void run_forward(T (&ax)[1 << LB], T (&ay)[1 << LB], 
       }
       case R_DIAG:
         diag_apply<T, LB>(ax, ay, diag + ((size_t)op.g << a.n) + lig, G, false);
+        break;
+      case R_PERM:
+        perm_apply<T, LB>(ax, ay, c.exch() + (size_t)(threadIdx.x >> 5) * 32 * (1 << LB),
+                          perm_masks_of(op), threadIdx.x & 31);
+        break;
+      case R_PERMB:
         break;
       default:
         u4_apply<T, LB>(ax, ay, c.u4() + 16 * op.g, false);
@@ -776,6 +839,7 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
       }
     }
     // ---- B6: gate program in reverse --------------------------------------------------------------
+    __syncthreads();   // the exchange rows become the warps' private PERM buffers
     for (int r = a.n_rops - 1; r >= 0; --r) {
       const ROp op = c.rops()[r];
       switch (op.kind) {
@@ -829,6 +893,15 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
           diag_apply<T, LB>(lx, ly, tb, G, true);
           break;
         }
+        case R_PERMB: {
+          C2<T>* pb = c.exch() + (size_t)warp * 32 * NA;
+          const PermMasks pm = perm_masks_of(op);
+          perm_apply<T, LB>(ax, ay, pb, pm, lane);
+          perm_apply<T, LB>(lx, ly, pb, pm, lane);
+          break;
+        }
+        case R_PERM:
+          break;
         default:
           u4_apply<T, LB>(ax, ay, c.u4() + 16 * op.g, true);
           u4_apply<T, LB>(lx, ly, c.u4() + 16 * op.g, true);

@@ -31,6 +31,7 @@ RegPlan* reg_create(int n, int enc, int dtype, const GateOp* host_ops, int n_ops
                     int n_consts, const GateOp* d_ops, const double2* d_consts, int num_sms);
 void reg_destroy(RegPlan* r);
 int reg_prepare(RegPlan* r, const void* d_theta, cudaStream_t s);       // phase tables of the diagonal blocks
+int reg_describe(const RegPlan* r, char* buf, int len);
 long long reg_state_elems(const RegPlan* r, long long B, int S);       // saved final psi, elements of T
 int reg_run(RegPlan* r, int S, bool backward, void* ws, long long B, void* state, void* grad_theta,
             cudaStream_t s);
@@ -43,6 +44,7 @@ TilePlan* tile_create(int n, int enc, int dtype, const GateOp* host_ops, int n_o
 void tile_destroy(TilePlan* r);
 int tile_prepare(TilePlan* r, const void* d_theta, cudaStream_t s);
 int tile_num_sweeps(const TilePlan* r);
+int tile_describe(const TilePlan* r, char* buf, int len);
 int tile_run(TilePlan* r, int S, bool backward, void* ws, long long B, void* grad_theta, cudaStream_t s);
 
 // generic-n MLP stages (one thread per point, jets through the workspace)

@@ -1,9 +1,11 @@
 // qcpinn_b200 -- engine T host side: sweep planner and launch plumbing.  Device code: qcp_tile.cuh.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 
+#include "qcp_layout.hpp"
 #include "qcp_tile.cuh"
 
 namespace qcp {
@@ -29,6 +31,7 @@ __global__ void tl_reduce_theta_kernel(const double* __restrict__ partials, int 
 
 struct TilePlan {
   int n, enc, dtype, LB, TB, n_gates, n_theta, n_consts, n_rops, n_sweeps, num_sms;
+  int kind_count[8];
   int final_bit[kMaxQubitsSv];
   ROp* d_rops;
   Sweep* d_sweeps;
@@ -110,7 +113,16 @@ static void plan_sweeps(const GateOp* ops, int n_ops, int n, int LB, std::vector
       if (std::find(next_seed.begin(), next_seed.end(), Q[k]) == next_seed.end()) next_seed.push_back(Q[k]);
 
     // ---- load mapping: tile position j <-> memory bit ---------------------------------------------------
-    std::vector<int> pos(n, -1), qat(TB, -1);          // tile position of qubit / qubit at tile position
+    LayoutTracker lt;
+    lt.LB = LB;
+    // measured on cfg4 (16-qubit sim_circ_15): the tile kernels are issue-bound with one CTA per SM,
+    // and the shared-memory round trip of a PERM stalls longer than the shuffle swaps it replaces
+    lt.perm_min = 1 << 30;
+    lt.pos.assign(n, -1);
+    lt.qat.assign(16, -1);
+    lt.rops = &rops;
+    std::vector<int>& pos = lt.pos;
+    std::vector<int>& qat = lt.qat;
     auto place = [&](int q, int j) { pos[q] = j; qat[j] = q; };
     place(qatm[0], LB);
     place(qatm[1], LB + 1);
@@ -137,38 +149,9 @@ static void plan_sweeps(const GateOp* ops, int n_ops, int n, int LB, std::vector
 
     // ---- gates of the sweep in tile positions (engine R style: dense targets on local positions) ------
     sw.r0 = (int)rops.size();
-    auto dense_target = [&](const GateOp& o, int q) {
-      int t[2], nt;
-      gate_targets(o, t, &nt);
-      return (nt > 0 && t[0] == q) || (nt > 1 && t[1] == q);
-    };
-    auto next_use = [&](int q, int from) {
-      for (int gg = from; gg < g_end; ++gg)
-        if (dense_target(ops[gg], q)) return gg;
-      return n_ops + 1;
-    };
-    auto emit_swap = [&](int local, int lane) {
-      rops.push_back({R_SWAP, local, lane, 0, 0, -1, 0, 0});
-      const int ql = qat[local], qn = qat[lane];
-      qat[local] = qn; qat[lane] = ql;
-      pos[qn] = local; pos[ql] = lane;
-    };
-    auto make_local = [&](int q, int g_cur) {
-      if (pos[q] < LB) return;
-      int best = 0, best_use = -1;
-      for (int x = 0; x < LB; ++x) {
-        const int u = next_use(qat[x], g_cur + 1);
-        if (u > best_use) { best_use = u; best = x; }
-      }
-      emit_swap(best, pos[q]);
-    };
-    auto move_to = [&](int q, int X) {
-      if (pos[q] == X) return;
-      if (pos[q] >= LB) { emit_swap(X, pos[q]); return; }
-      const int Y = pos[q], Z = LB + 4;
-      emit_swap(Y, Z);
-      emit_swap(X, Z);
-    };
+    auto targets = [&](int gg, int* t, int* nt) { gate_targets(ops[gg], t, nt); };
+    auto make_local = [&](int q, int g_cur) { lt.make_local(q, g_cur, g_end, targets); };
+    auto move_to = [&](int q, int X) { lt.move_to(q, X); };
     auto pair_mask = [&](int pt, int pc) {
       if (pc >= LB) return 0;
       int m = 0;
@@ -211,12 +194,12 @@ static void plan_sweeps(const GateOp* ops, int n_ops, int n, int LB, std::vector
     for (int k = 0; k < 2; ++k) {
       const int P = LB + k, q = next_seed[k];
       if (pos[q] == P) continue;
-      if (pos[q] < LB) { emit_swap(pos[q], P); continue; }
+      if (pos[q] < LB) { lt.emit_swap(pos[q], P); continue; }
       // lane -> lane: hop through a local position that does not hold the other seed
       int x = 0;
       while (qat[x] == next_seed[1 - k]) ++x;
-      emit_swap(x, pos[q]);
-      emit_swap(x, P);
+      lt.emit_swap(x, pos[q]);
+      lt.emit_swap(x, P);
     }
     sw.r1 = (int)rops.size();
     // ---- store mapping: same memory bits, positions LB / LB + 1 on bits 0 / 1 -----------------------------
@@ -258,6 +241,7 @@ TilePlan* tile_create(int n, int enc, int dtype, const GateOp* host_ops, int n_o
   std::vector<Sweep> sweeps;
   plan_sweeps(host_ops, n_ops, n, r->LB, rops, sweeps, r->final_bit);
   r->n_rops = (int)rops.size(); r->n_sweeps = (int)sweeps.size();
+  for (const ROp& o : rops) r->kind_count[o.kind & 7]++;
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes ? bytes : 16); };
   alloc((void**)&r->d_rops, sizeof(ROp) * rops.size());
@@ -286,6 +270,12 @@ int tile_prepare(TilePlan* r, const void* d_theta, cudaStream_t) {
 }
 
 int tile_num_sweeps(const TilePlan* r) { return r ? r->n_sweeps : 0; }
+
+int tile_describe(const TilePlan* r, char* buf, int len) {
+  return snprintf(buf, len, "engine=tiled n=%d LB=%d tile_bits=%d sweeps=%d ops=%d (dense=%d cnot=%d swap=%d haar=%d)",
+                  r->n, r->LB, r->TB, r->n_sweeps, r->n_rops, r->kind_count[R_L1], r->kind_count[R_CX],
+                  r->kind_count[R_SWAP], r->kind_count[R_U4]);
+}
 
 static int grow(void** ptr, size_t* have, size_t want) {
   if (want <= *have) return 0;

@@ -21,6 +21,8 @@
 //             accumulation (global RED rows) -> cotangent pass (pull lambda0 back to the z jets)
 #pragma once
 
+#include <algorithm>
+
 #include "qcp_reg.cuh"
 
 namespace qcp {
@@ -42,7 +44,7 @@ struct Sweep {
 };
 
 struct TlLayout {
-  int rops, cs, u4, zj, qj, rj, tab, qacc, scr, tabbar, rbar, total;
+  int rops, cs, u4, zj, qj, rj, tab, qacc, scr, warp_bytes, tabbar, rbar, total;
 };
 
 struct TlArgs {
@@ -77,9 +79,14 @@ __host__ __device__ inline TlLayout tl_layout(size_t es, int LB, int S, int n, i
   L.rj = o; o = rg::rg_align(o + es * (size_t)n * 2 * S);
   L.tab = o; o = rg::rg_align(o + es * (size_t)NE * S);
   L.qacc = o; o = rg::rg_align(o + sizeof(double) * (size_t)n * S);
+  // per-warp scratch of the cotangent pass (rho tile + LT components).  The sweeps move qubits
+  // with shuffle SWAPs only: the shared-memory PERM of engine R measured slower here (one CTA per
+  // SM, issue-bound), so the planner never emits it for this engine.
+  const size_t per_warp = es * (32 * 33 + 32 * 4);
+  L.warp_bytes = (int)per_warp;
   L.scr = o; L.tabbar = o; L.rbar = o;
   if (backward) {
-    L.scr = o; o = rg::rg_align(o + es * (size_t)NW * (32 * 33 + 32 * 4));
+    L.scr = o; o = rg::rg_align(o + per_warp * (size_t)NW);
     L.tabbar = o; o = rg::rg_align(o + es * (size_t)NE * S);
     L.rbar = o; o = rg::rg_align(o + es * (size_t)n * 2 * S);
   }
@@ -102,7 +109,8 @@ struct Ctx {
   __device__ __forceinline__ Jet<T, S>* rj() const { return at<Jet<T, S>>(a.lay.rj); }          // [n][2]
   __device__ __forceinline__ Jet<T, S>* tab() const { return at<Jet<T, S>>(a.lay.tab); }        // [NA | 32 | NT]
   __device__ __forceinline__ double* qacc() const { return at<double>(a.lay.qacc); }            // [n*S]
-  __device__ __forceinline__ T* scr() const { return at<T>(a.lay.scr); }                        // [NW][32*33 + 128]
+  // this warp's private cotangent-pass scratch
+  __device__ __forceinline__ T* scr() const { return at<T>(a.lay.scr + (threadIdx.x >> 5) * a.lay.warp_bytes); }
   __device__ __forceinline__ Jet<T, S>* tabbar() const { return at<Jet<T, S>>(a.lay.tabbar); }
   __device__ __forceinline__ Jet<T, S>* rbar() const { return at<Jet<T, S>>(a.lay.rbar); }
 };
@@ -611,7 +619,7 @@ tl_backward_kernel(const __grid_constant__ TlArgs a) {
     }
     // ---- cotangent pass: lambda0 -> table cotangents -------------------------------------------------
     if (a.enc == QCP_ENC_ANGLE) {
-      T* rho = c.scr() + (size_t)warp * (32 * 33 + 128);   // [32][33] rho, then LT components [32][4]
+      T* rho = c.scr();                                     // [32][33] rho, then LT components [32][4]
       T* ltc = rho + 32 * 33;
       const Jet<T, S>* tab = c.tab();
       for (int it = warp; it < S * NT; it += NW) {

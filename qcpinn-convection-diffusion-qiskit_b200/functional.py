@@ -87,6 +87,11 @@ class Plan:
                        "qcp_plan_set_io_dtype")
             self.io_dtype = io_dtype
 
+    def describe(self) -> str:
+        buf = ctypes.create_string_buffer(512)
+        _lib.check(self.lib.qcp_plan_describe(self._handle, buf, 512), "qcp_plan_describe")
+        return buf.value.decode()
+
     def __del__(self):
         h = getattr(self, "_handle", None)
         try:
