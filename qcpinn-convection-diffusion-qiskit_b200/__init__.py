@@ -14,7 +14,8 @@ from . import _lib, functional, program  # noqa: F401
 from .data import diffusion_dataset  # noqa: F401
 from .nn.DVPDESolver import DVPDESolver  # noqa: F401
 from .nn.DVQuantumLayer import DVQuantumLayer  # noqa: F401
-from .nn.pde import diffusion_operator  # noqa: F401
+from .nn.pde import (diffusion_operator, helmholtz_operator, klein_gordon_operator,  # noqa: F401
+                     navier_stokes_2D_operator, wave_operator)
 from .utils.logger import Logging  # noqa: F401
 
 __version__ = "0.1.0"

@@ -107,14 +107,26 @@ class DVPDESolver(nn.Module):
     # -- fused path ----------------------------------------------------------------------------
     def _check_fused(self):
         net = self.classic_network
-        if net[0] != 3 or net[-1] != 1:
+        if net[0] not in (2, 3) or net[-1] != 1:
             raise NotImplementedError(
-                f"fused kernels cover classic_network=[3, H, 1]; got {net}")
+                f"fused kernels cover classic_network=[3, H, 1] and [2, H, 1]; got {net}")
 
     def _mlp_tensors(self):
         pre, post = self.preprocessor, self.postprocessor
-        return (pre[0].weight, pre[0].bias, pre[2].weight, pre[2].bias,
+        w1 = pre[0].weight
+        if w1.shape[1] == 2:
+            # two-input solvers (wave / Klein-Gordon / Helmholtz, reference nn/pde.py:26-52,73-95):
+            # the coordinates ride in the kernel's x / y slots behind a zero t column; autograd
+            # slices the gradient of the padded weight back
+            w1 = torch.nn.functional.pad(w1, (1, 0))
+        return (w1, pre[0].bias, pre[2].weight, pre[2].bias,
                 post[0].weight, post[0].bias, post[2].weight, post[2].bias)
+
+    def _kernel_input(self, x):
+        """(B, 3) kernel input: two-input solvers get a zero t column in front."""
+        if x.shape[1] == 2 and self.classic_network[0] == 2:
+            return torch.nn.functional.pad(x, (1, 0))
+        return x
 
     def _plan(self, device) -> F.Plan:
         self._check_fused()
@@ -137,8 +149,8 @@ class DVPDESolver(nn.Module):
                 self.draw_quantum_circuit(x)
                 self.draw_quantum_circuit_flag = False
             plan = self._plan(self._device_of(x))
-            u = F.solver_value(plan, x, self.quantum_layer.params, self._mlp_tensors(),
-                               self.quantum_layer.theta_key())
+            u = F.solver_value(plan, self._kernel_input(x), self.quantum_layer.params,
+                               self._mlp_tensors(), self.quantum_layer.theta_key())
             return u.to(torch.float32)
         except Exception as e:
             self.logger.print(f"Forward pass failed: {str(e)}")
@@ -153,8 +165,8 @@ class DVPDESolver(nn.Module):
                 self.draw_quantum_circuit(X)
                 self.draw_quantum_circuit_flag = False
             plan = self._plan(self._device_of(X))
-            u, r = F.solver_residual(plan, X, self.quantum_layer.params, self._mlp_tensors(),
-                                     coeffs, self.quantum_layer.theta_key())
+            u, r = F.solver_residual(plan, self._kernel_input(X), self.quantum_layer.params,
+                                     self._mlp_tensors(), coeffs, self.quantum_layer.theta_key())
             return u.to(torch.float32), r.to(torch.float32)
         except Exception as e:
             self.logger.print(f"Forward pass failed: {str(e)}")
@@ -176,6 +188,7 @@ class DVPDESolver(nn.Module):
             if not plan.fused_engine:
                 return [self.forward(X) if co is None else self.taylor_residual(X, co)
                         for X, co in batches]
+            batches = [(self._kernel_input(X), co) for X, co in batches]
             flat = F.solver_many(plan, batches, self.quantum_layer.params, self._mlp_tensors(),
                                  self.quantum_layer.theta_key())
             out, i = [], 0
@@ -215,7 +228,8 @@ class DVPDESolver(nn.Module):
     def supports_fused_step(self):
         try:
             dev = self.quantum_layer.params.device
-            return dev.type == "cuda" and self._plan(dev).fused_engine and \
+            return dev.type == "cuda" and self.classic_network[0] == 3 and \
+                self._plan(dev).fused_engine and \
                 all(p.dtype == torch.float32 for p in self.parameters())
         except Exception:
             return False
@@ -266,7 +280,8 @@ class DVPDESolver(nn.Module):
         """No-grad evaluation helper: (B,6) = u, u_t, u_x, u_y, u_xx, u_yy."""
         plan = self._plan(self._device_of(X))
         with torch.no_grad():
-            return F.solver_streams(plan, X, self.quantum_layer.params, self._mlp_tensors())[2]
+            return F.solver_streams(plan, self._kernel_input(X), self.quantum_layer.params,
+                                    self._mlp_tensors())[2]
 
     # -- data parallel -------------------------------------------------------------------------
     def enable_data_parallel(self, process_group=None):

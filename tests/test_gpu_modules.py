@@ -343,3 +343,54 @@ def test_fused_step_equals_autograd_route(tmp_path, dtype):
         assert abs(va - vf) < 2e-5 * abs(va)
     for pa, pf in zip(ma.parameters(), mf.parameters()):
         assert rel_err(pf, pa) < 1e-4
+
+
+def _two_input_model(tmp_path, dtype):
+    torch.manual_seed(3)
+    args = dict(ARGS, classic_network=[2, 50, 1], dtype=dtype)
+    return qb.DVPDESolver(args, qb.Logging(str(tmp_path)), device=DEV)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("name", ["wave", "klein_gordon", "helmholtz"])
+def test_two_input_operators_match_oracle(tmp_path, name, dtype):
+    """wave / Klein-Gordon / Helmholtz residuals (reference nn/pde.py:26-52,73-95) of a two-input
+    solver: fused Taylor kernel vs nested autograd on the CPU oracle, values and every gradient."""
+    from qcpinn_b200.nn import pde
+
+    model = _two_input_model(tmp_path, dtype)
+    oracle = _oracle_of(model)
+    g = torch.Generator().manual_seed(17)
+    a = torch.rand(33, 1, generator=g, dtype=torch.float64)
+    b = torch.rand(33, 1, generator=g, dtype=torch.float64)
+    cu = torch.randn(33, 1, generator=g, dtype=torch.float64)
+    cr = torch.randn(33, 1, generator=g, dtype=torch.float64)
+
+    ao, bo = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    uo = oracle.forward(torch.cat((ao, bo), 1))
+    ones = torch.ones_like(uo)
+    d = lambda out, wrt: torch.autograd.grad(out, wrt, ones, create_graph=True)[0]   # noqa: E731
+    u_aa, u_bb = d(d(uo, ao), ao), d(d(uo, bo), bo)
+    ro = {"wave": u_aa - 4.0 * u_bb,
+          "klein_gordon": u_aa - u_bb + uo ** 3,
+          "helmholtz": u_aa + u_bb + uo}[name]
+    ((uo * cu).sum() + (ro * cr).sum()).backward()
+
+    op = {"wave": pde.wave_operator, "klein_gordon": pde.klein_gordon_operator,
+          "helmholtz": pde.helmholtz_operator}[name]
+    ud, rd = op(model, a.to(DEV, torch.float32), b.to(DEV, torch.float32))
+    ((ud * cu.to(DEV, torch.float32)).sum() + (rd * cr.to(DEV, torch.float32)).sum()).backward()
+    tol = 2e-5 if dtype == "float32" else 5e-6        # module tensors / outputs are float32
+    assert rel_err(ud, uo) < tol and rel_err(rd, ro) < tol
+    for k, p in _weights_of(model).items():
+        assert rel_err(p.grad, oracle.w[k].grad) < 10 * tol, k
+    assert _weights_of(model)["w1"].grad.shape == (50, 2)
+
+
+def test_navier_stokes_operator_rejects_the_fused_solver(tmp_path):
+    from qcpinn_b200.nn import pde
+
+    model = _model(tmp_path)
+    t = torch.rand(4, 1, device=DEV)
+    with pytest.raises(NotImplementedError):
+        pde.navier_stokes_2D_operator(model, t, t.clone(), t.clone())

@@ -64,3 +64,38 @@ def test_haar_pair_is_scipy_reproducible():
     u1, u2 = P.haar_pair(1)
     r1, r2 = oc.haar_unitaries(1)
     assert np.array_equal(u1, r1) and np.array_equal(u2, r2)
+
+
+def test_generic_pde_operators_on_a_plain_module():
+    """nn/pde.py operators with an ordinary torch module (no fused path): closed-form check on
+    u = sin(a) * exp(b) (+ two more outputs for Navier-Stokes)."""
+    import torch
+
+    from qcpinn_b200.nn import pde
+
+    class Analytic(torch.nn.Module):
+        def forward(self, X):
+            return torch.sin(X[:, 0:1]) * torch.exp(X[:, 1:2])
+
+    a = torch.rand(7, 1, dtype=torch.float64)
+    b = torch.rand(7, 1, dtype=torch.float64)
+    u = torch.sin(a) * torch.exp(b)
+    m = Analytic()
+    uw, rw = pde.wave_operator(m, a.clone(), b.clone())
+    assert torch.allclose(uw, u) and torch.allclose(rw, -u - 4.0 * u)
+    uk, rk = pde.klein_gordon_operator(m, a.clone(), b.clone())
+    assert torch.allclose(rk, -u - u + u ** 3)
+    uh, rh = pde.helmholtz_operator(m, a.clone(), b.clone())
+    assert torch.allclose(rh, -u + u + u)
+
+    class ThreeOut(torch.nn.Module):
+        def forward(self, X):
+            t, x, y = X[:, 0:1], X[:, 1:2], X[:, 2:3]
+            return torch.cat((t * x * y, t + x * x, x * y), 1)
+
+    t, x, y = (torch.rand(5, 1, dtype=torch.float64) for _ in range(3))
+    cont, fu, fv = pde.navier_stokes_2D_operator(ThreeOut(), t.clone(), x.clone(), y.clone())
+    uu, vv = t * x * y, t + x * x
+    assert torch.allclose(cont, t * y + 0 * x)
+    assert torch.allclose(fu, x * y + uu * t * y + vv * t * x + y / 1056.0)
+    assert torch.allclose(fv, 1 + uu * 2 * x + x / 1056.0 - 0.00345 * 2.0)
