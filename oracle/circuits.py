@@ -21,7 +21,7 @@ def params_per_layer(ansatz: str, n: int) -> int:
     """Trainable angles per layer, reference ``nn/DVQuantumLayer.py:25-78``."""
     if ansatz == "layered":
         return 4 * n
-    if ansatz == "alternate":
+    if ansatz in ("alternate", "alternate_flat"):
         return 4 * n - 4
     if ansatz == "cascade":
         return 3 * n
@@ -182,6 +182,13 @@ def ansatz_ops(ansatz: str, n: int):
             tdcnot(i, (i + 1) % n)
         for i in list(range(n))[1::2]:
             tdcnot(i, (i + 1) % n)
+    elif ansatz == "alternate_flat":  # train_hybrid_qpinn.py:273-295: no wrap-around pair
+        for i in list(range(0, n - 1, 2)) + list(range(1, n - 1, 2)):
+            rot("RY", i)
+            rot("RY", i + 1)
+            cnot(i, i + 1)
+            rot("RZ", i)
+            rot("RZ", i + 1)
     elif ansatz == "cascade":  # :287-305
         for q in range(n):
             rot("RX", q)
@@ -249,7 +256,7 @@ def apply_ansatz_layer(state, ansatz, n, row, cdtype):
 def check_param_row(ansatz, n, row):
     """The reference's per-builder length checks (``:247,265,309,327,351``)."""
     want = params_per_layer(ansatz, n)
-    if ansatz in ("layered", "alternate"):
+    if ansatz in ("layered", "alternate", "alternate_flat"):
         assert row is not None and len(row) == want
     elif ansatz in ("farhi", "sim_circ_15", "cross_mesh"):
         if row is None or len(row) != want:

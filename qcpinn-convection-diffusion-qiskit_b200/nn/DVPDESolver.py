@@ -76,7 +76,7 @@ class DVPDESolver(nn.Module):
 
         # The reference leaves quantum_layer on the CPU (PennyLane moves data itself); the fused
         # kernels need every parameter on the model's device.
-        self.quantum_layer = DVQuantumLayer(self.args).to(self.device)
+        self.quantum_layer = self._build_quantum_layer(self.args).to(self.device)
 
         # On a CUDA device Adam is built capturable with a device-resident learning rate, so a
         # whole train step can be replayed as one CUDA graph (trainer.diffusion_train.TrainStep)
@@ -90,12 +90,18 @@ class DVPDESolver(nn.Module):
             self.optimizer = torch.optim.Adam(trainable, lr=self.args["lr"])
         # fused / capturable optimizers update parameters without touching their version counters
         self.optimizer.register_step_post_hook(lambda *_: self.quantum_layer.mark_updated())
-        self.scheduler = _RankConsistentPlateau(
-            self.optimizer, mode="min", factor=0.9, patience=1000)
+        self.scheduler = self._make_scheduler()
         self.loss_fn = torch.nn.MSELoss()
         self.log_path = self.logger.get_output_dir()
         self._initialize_weights()
         self._dp = None
+
+    # construction hooks (the single-file trainer's HybridQPINN overrides them)
+    def _build_quantum_layer(self, args):
+        return DVQuantumLayer(args)
+
+    def _make_scheduler(self):
+        return _RankConsistentPlateau(self.optimizer, mode="min", factor=0.9, patience=1000)
 
     def _initialize_weights(self):
         for layer in self.preprocessor:

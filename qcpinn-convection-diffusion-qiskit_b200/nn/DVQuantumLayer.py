@@ -71,7 +71,8 @@ class DVQuantumLayer(nn.Module):
     def program(self):
         if self._program is None:   # compiled lazily so construction never fails (like the QNode)
             self._program = compile_program(
-                self.q_ansatz, self.num_qubits, self.num_quantum_layers, self.haar_seed1)
+                self.q_ansatz, self.num_qubits, self.num_quantum_layers, self.haar_seed1,
+                getattr(self, "program_variant", "dv"))
         return self._program
 
     def plan(self, device, hidden=1, io_dtype=None) -> F.Plan:

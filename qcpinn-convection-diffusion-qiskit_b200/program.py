@@ -61,8 +61,18 @@ class _Emitter:
         self.ops.append((CNOT, control, target, -1))
 
 
-def _emit_layer(ansatz: str, e: _Emitter) -> None:
+def _emit_layer(ansatz: str, e: _Emitter, variant: str = "dv") -> None:
     n = e.n
+    if ansatz == "alternate" and variant == "single_file":
+        # reference train_hybrid_qpinn.py:273-295: neighbour pairs WITHOUT the wrap-around pair, so
+        # even qubit counts work (4n - 4 angles are exactly enough)
+        for c in list(range(0, n - 1, 2)) + list(range(1, n - 1, 2)):
+            e.rot(RY, c)
+            e.rot(RY, c + 1)
+            e.cnot(c, c + 1)
+            e.rot(RZ, c)
+            e.rot(RZ, c + 1)
+        return
     if ansatz == "layered":          # RZ,RX per wire | CNOT ring | RX,RZ per wire
         for w in range(n):
             e.rot(RZ, w)
@@ -145,7 +155,8 @@ class CircuitProgram:
         return self.n_theta // max(self.n_layers, 1)
 
 
-def compile_program(ansatz: str, n_qubits: int, n_layers: int, haar_seed=None) -> CircuitProgram:
+def compile_program(ansatz: str, n_qubits: int, n_layers: int, haar_seed=None,
+                    variant: str = "dv") -> CircuitProgram:
     """Gate table for: L x ansatz -> [Haar on wires (0,1),(2,3) iff seed given and n >= 4] -> H(n-1).
 
     Raises ``IndexError`` exactly where the reference does when a builder over-indexes its angle
@@ -155,7 +166,7 @@ def compile_program(ansatz: str, n_qubits: int, n_layers: int, haar_seed=None) -
     ops: list[tuple[int, int, int, int]] = []
     for layer in range(n_layers):
         em = _Emitter(n_qubits, layer * per_layer, per_layer)
-        _emit_layer(ansatz, em)
+        _emit_layer(ansatz, em, variant)
         ops.extend(em.ops)
     consts = np.zeros((0, 4, 4), dtype=np.complex128)
     if haar_seed is not None and n_qubits >= 4:

@@ -2,6 +2,7 @@
 diffusion_operator / trainer), the golden fixtures, edge cases and full-size properties."""
 
 import glob
+import math
 import os
 
 import pytest
@@ -394,3 +395,44 @@ def test_navier_stokes_operator_rejects_the_fused_solver(tmp_path):
     t = torch.rand(4, 1, device=DEV)
     with pytest.raises(NotImplementedError):
         pde.navier_stokes_2D_operator(model, t, t.clone(), t.clone())
+
+
+def test_single_file_trainer_entry_point(tmp_path):
+    """reference train_hybrid_qpinn.py on the fused kernels: flags, 1-D angle vector, four boundary
+    faces, pure-diffusion residual against the CPU oracle, checkpoint files."""
+    from qcpinn_b200 import train_hybrid_qpinn as th
+
+    ns = th.parse_args(["--num-qubits", "4", "--ansatz", "alternate", "--epochs", "3",
+                        "--batch-size", "48", "--print-every", "2", "--output-dir", str(tmp_path),
+                        "--device", "cuda"])
+    assert ns.lr == 0.005 and ns.seed == 42 and ns.hidden_dim == 50 and ns.diffusion_coef == 0.01
+    torch.manual_seed(ns.seed)
+    model = th.HybridQPINN(ns, DEV)
+    assert model.quantum_layer.params.shape == (12,)              # 4n - 4, no wrap-around pair
+    assert model.quantum_layer.haar_seed1 == 42 and model.quantum_layer.haar_seed2 == 43
+    assert set(model.state_dict()) >= {"preprocessor.0.weight", "quantum_layer.params",
+                                       "postprocessor.2.bias"}
+    # residual u_t - D (u_xx + u_yy) against nested autograd on the oracle (flat alternate program)
+    from oracle import circuits as oc
+    w = {k: v.detach().cpu() for k, v in _weights_of(model).items()}
+    w["theta"] = w["theta"].reshape(1, -1)
+    oracle = osolver.OracleSolver(4, 1, "alternate_flat", "angle", 42, "f64").set_weights(w)
+    X = points(9, seed=5)
+    uo, ro = osolver.diffusion_operator(oracle, X[:, 0:1].clone(), X[:, 1:2].clone(),
+                                        X[:, 2:3].clone(), D=0.01, v_x=0.0, v_y=0.0)
+    Xd = X.to(DEV, torch.float32)
+    ud, rd = th.diffusion_operator(model, Xd[:, 0:1], Xd[:, 1:2], Xd[:, 2:3], D=0.01)
+    assert rel_err(ud, uo) < 5e-6 and rel_err(rd, ro) < 5e-6
+    # samplers: four faces, zero targets
+    ics, bcs, res, dom = th.create_samplers(DEV, D=0.01)
+    assert len(bcs) == 4 and bcs[1].sample(5)[0][:, 1].eq(1).all() and bcs[3].sample(5)[0][:, 2].eq(1).all()
+    assert res.sample(6)[1].abs().sum() == 0
+    out = tmp_path / "run"
+    out.mkdir()
+    th.train(model, ns, ics, bcs, res, str(out))
+    assert len(model.loss_history) == 4 and all(math.isfinite(v) for v in model.loss_history)
+    ck = torch.load(out / "checkpoint.pth", weights_only=False)
+    assert set(ck) == {"epoch", "model_state_dict", "optimizer_state_dict", "loss", "loss_history"}
+    assert (out / "model.pth").exists()
+    err = th.evaluate(model, ns, dom, str(out))
+    assert math.isfinite(err) and (out / "evaluation.json").exists()

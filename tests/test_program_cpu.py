@@ -99,3 +99,23 @@ def test_generic_pde_operators_on_a_plain_module():
     assert torch.allclose(cont, t * y + 0 * x)
     assert torch.allclose(fu, x * y + uu * t * y + vv * t * x + y / 1056.0)
     assert torch.allclose(fv, 1 + uu * 2 * x + x / 1056.0 - 0.00345 * 2.0)
+
+
+def test_single_file_trainer_cli_defaults_and_flat_alternate():
+    """reference train_hybrid_qpinn.py:50-109 flag defaults; :273-295 the non-wrapping alternate."""
+    import pytest
+
+    from qcpinn_b200 import train_hybrid_qpinn as th
+    from qcpinn_b200.program import CNOT, compile_program
+
+    ns = th.parse_args([])
+    assert (ns.device, ns.num_qubits, ns.ansatz, ns.encoding, ns.shots) == ("auto", 4, "cascade", "angle", 1024)
+    assert (ns.epochs, ns.batch_size, ns.lr, ns.seed, ns.hidden_dim) == (5000, 64, 0.005, 42, 50)
+    assert (ns.print_every, ns.output_dir, ns.diffusion_coef, ns.use_ibm) == (100, "./outputs", 0.01, False)
+    with pytest.raises(NotImplementedError):
+        th.main(["--use-ibm"])
+    flat = compile_program("alternate", 4, 1, None, variant="single_file")
+    pairs = [(a, b) for k, a, b, _ in flat.ops.tolist() if k == CNOT]
+    assert pairs == [(0, 1), (2, 3), (1, 2)] and flat.n_theta == 12
+    with pytest.raises(IndexError):
+        compile_program("alternate", 4, 1, None)            # the DVQuantumLayer variant over-indexes
