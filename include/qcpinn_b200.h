@@ -100,6 +100,11 @@ int qcp_plan_describe(const qcp_plan_t* plan, char* buf, int len);
  * directly, with no cast kernels around the calls. */
 int qcp_plan_set_io_dtype(qcp_plan_t* plan, int io_dtype);
 
+/* Statevector engines (n >= 5): by default the forward of a call with a ``save`` workspace also keeps
+ * the final psi streams there (2^n complex per stream and point, see qcp_solver_workspace_elems) and
+ * the backward starts from them; enabled = 0 trades that memory for a recomputed forward. */
+int qcp_plan_set_state_save(qcp_plan_t* plan, int enabled);
+
 /* Evaluate the batch-shared part of the circuit for the current angles ``theta`` [n_theta]:
  * V(theta) = H_last . Haar . ansatz layers, O_i = V^dag Z_i V, and the real feature matrix C with
  * <Z_i>(z) = sum_s C[i,s] phi_s(z).  Must precede forward calls whenever theta changed. */

@@ -37,6 +37,7 @@ SIGNATURES = {
     "qcp_plan_num_features": (_c_int, [_c_void_p]),
     "qcp_plan_engine": (_c_int, [_c_void_p]),
     "qcp_plan_describe": (_c_int, [_c_void_p, ctypes.c_char_p, _c_int]),
+    "qcp_plan_set_state_save": (_c_int, [_c_void_p, _c_int]),
     "qcp_plan_set_io_dtype": (_c_int, [_c_void_p, _c_int]),
     "qcp_prepare": (_c_int, [_c_void_p, _c_void_p, _c_void_p]),
     "qcp_feature_matrix": (_c_int, [_c_void_p, _dptr, _c_void_p]),

@@ -555,6 +555,7 @@ struct qcp_plan {
   bool engine_l;
   RegPlan* reg;             // engine R context (5 <= n <= 10) or null
   TilePlan* tile;           // engine T context (n up to 16) or null; neither => engine L kernels
+  bool no_state_save;       // engines R / T: recompute the forward in the backward instead of saving psi
   void* d_theta;            // copy of the angles taken by qcp_prepare()
   void* d_ws;               // internal saved-jet workspace (when the caller gives none)
   size_t ws_elems;
@@ -716,6 +717,12 @@ int qcp_plan_describe(const qcp_plan_t* p, char* buf, int len) {
   return 0;
 }
 
+int qcp_plan_set_state_save(qcp_plan_t* p, int enabled) {
+  if (!p) { set_error("qcp_plan_set_state_save: NULL plan"); return 1; }
+  p->no_state_save = !enabled;
+  return 0;
+}
+
 int qcp_plan_set_io_dtype(qcp_plan_t* p, int io_dtype) {
   if (!p || (io_dtype != QCP_F32 && io_dtype != QCP_F64)) { set_error("qcp_plan_set_io_dtype: bad argument"); return 1; }
   if (io_dtype == p->dtype) { p->io_f32 = 0; return 0; }
@@ -836,7 +843,7 @@ static void* internal_ws(qcp_plan* p, long long B, int S) {
 static int circuit_run(qcp_plan* p, int S, bool backward, void* ws, long long B, void* state,
                        void* grad_theta, cudaStream_t s) {
   if (p->reg) return reg_run(p->reg, S, backward, ws, B, state, grad_theta, s);
-  if (p->tile) return tile_run(p->tile, S, backward, ws, B, grad_theta, s);
+  if (p->tile) return tile_run(p->tile, S, backward, ws, B, state, grad_theta, s);
   SvLaunch L{};
   if (sv_configure(p, S, B, L)) return 1;
   L.ws = ws; L.grad_theta = grad_theta;
@@ -844,7 +851,7 @@ static int circuit_run(qcp_plan* p, int S, bool backward, void* ws, long long B,
 }
 
 static void* state_of(const qcp_plan* p, void* save, long long B, int mode) {
-  if (!p->reg || !save) return nullptr;
+  if ((!p->reg && !p->tile) || !save || p->no_state_save) return nullptr;
   return static_cast<char*>(save) + elem_size(p->dtype) * 2 * (size_t)p->n * mode * (size_t)B;
 }
 
@@ -975,7 +982,8 @@ static int check_mode(int mode, const double* coeffs, const char* who) {
 long long qcp_solver_workspace_elems(const qcp_plan_t* p, long long B, int mode) {
   if (!p || B < 0 || (mode != QCP_MODE_VALUE && mode != QCP_MODE_RESIDUAL)) return -1;
   long long e = 2LL * p->n * mode * B;
-  if (p->reg) e += reg_state_elems(p->reg, B, mode);   // engine R also saves the final psi streams
+  if (p->reg && !p->no_state_save) e += reg_state_elems(p->reg, B, mode);   // engines R / T also save
+  if (p->tile && !p->no_state_save) e += tile_state_elems(p->tile, B, mode);  // the final psi streams
   return e;
 }
 

@@ -45,7 +45,9 @@ void tile_destroy(TilePlan* r);
 int tile_prepare(TilePlan* r, const void* d_theta, cudaStream_t s);
 int tile_num_sweeps(const TilePlan* r);
 int tile_describe(const TilePlan* r, char* buf, int len);
-int tile_run(TilePlan* r, int S, bool backward, void* ws, long long B, void* grad_theta, cudaStream_t s);
+long long tile_state_elems(const TilePlan* r, long long B, int S);     // saved final psi, elements of T
+int tile_run(TilePlan* r, int S, bool backward, void* ws, long long B, void* state, void* grad_theta,
+             cudaStream_t s);
 
 // generic-n MLP stages (one thread per point, jets through the workspace)
 struct MlpLaunch {

@@ -287,7 +287,12 @@ static int grow(void** ptr, size_t* have, size_t want) {
   return 0;
 }
 
-int tile_run(TilePlan* r, int S, bool backward, void* ws, long long B, void* grad_theta, cudaStream_t s) {
+long long tile_state_elems(const TilePlan* r, long long B, int S) {
+  return 2LL * S * B << r->n;
+}
+
+int tile_run(TilePlan* r, int S, bool backward, void* ws, long long B, void* state, void* grad_theta,
+             cudaStream_t s) {
   if (S != 1 && S != 6) { set_error("engine T: bad stream count %d", S); return 1; }
   if (!r->theta && r->n_theta > 0) { set_error("engine T: qcp_prepare() has not run"); return 1; }
   const size_t es = es_of(r->dtype);
@@ -306,6 +311,7 @@ int tile_run(TilePlan* r, int S, bool backward, void* ws, long long B, void* gra
   for (int q = 0; q < r->n; ++q) a.final_bit[q] = r->final_bit[q];
   a.rops = r->d_rops; a.sweeps = r->d_sweeps; a.gates = r->d_gates; a.consts = r->d_consts;
   a.theta = r->theta; a.ws = ws; a.B = B; a.slab = r->d_slab; a.slab_stride = stride;
+  a.state = state;
   if (backward) {
     const int nt = r->n_theta > 0 ? r->n_theta : 1;
     if (grow((void**)&r->d_tpart, &r->tpart_bytes, sizeof(double) * (size_t)grid * nt)) return 1;

@@ -60,6 +60,9 @@ struct TlArgs {
   long long B;
   void* slab;                    // per-CTA state storage
   size_t slab_stride;            // complex elements per CTA
+  void* state;                   // optional per-POINT psi storage [B][S][2^n]: the forward works in it
+                                 // (and leaves the final psi there), the backward starts from it
+                                 // instead of recomputing the forward
   double* theta_partials;        // [grid][n_theta]
 };
 
@@ -443,12 +446,13 @@ tl_forward_kernel(const __grid_constant__ TlArgs a) {
   const int n = a.n, NT = 1 << (n - TB), nS = n * S;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = blockDim.x >> 5;
   load_program<T, S>(a);
-  C2A<T>* slab = static_cast<C2A<T>*>(a.slab) + (size_t)blockIdx.x * a.slab_stride;
+  C2A<T>* cta_slab = static_cast<C2A<T>*>(a.slab) + (size_t)blockIdx.x * a.slab_stride;
   T* ws_out = static_cast<T*>(a.ws);
   const size_t M = (size_t)1 << n;
   __syncthreads();
   for (long long p = blockIdx.x; p < a.B; p += gridDim.x) {
     for (int e = threadIdx.x; e < nS; e += blockDim.x) c.qacc()[e] = 0.0;
+    C2A<T>* slab = a.state ? static_cast<C2A<T>*>(a.state) + (size_t)p * S * M : cta_slab;
     forward_point<T, LB, S>(c, a, slab, p);
     // ---- measure pass (canonical mapping over the final layout) --------------------------------
     for (int it = warp; it < S * NT; it += NW) {
@@ -512,16 +516,29 @@ tl_backward_kernel(const __grid_constant__ TlArgs a) {
   const int n = a.n, NT = 1 << (n - TB), nS = n * S, NE = NA + 32 + NT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = blockDim.x >> 5;
   load_program<T, S>(a);
-  C2A<T>* slab = static_cast<C2A<T>*>(a.slab) + (size_t)blockIdx.x * a.slab_stride;
+  C2A<T>* cta_slab = static_cast<C2A<T>*>(a.slab) + (size_t)blockIdx.x * a.slab_stride;
   const T* ws = static_cast<const T*>(a.ws);
   T* ws_out = static_cast<T*>(a.ws);
   double* const gth = a.theta_partials + (size_t)blockIdx.x * (a.n_theta > 0 ? a.n_theta : 1);
   const size_t M = (size_t)1 << n;
-  C2A<T>* lam = slab + (size_t)S * M;
+  C2A<T>* lam = cta_slab + (size_t)S * M;
   __syncthreads();
 
   for (long long p = blockIdx.x; p < a.B; p += gridDim.x) {
-    forward_point<T, LB, S>(c, a, slab, p);
+    C2A<T>* slab = cta_slab;
+    if (a.state) {
+      // final psi saved by the forward (consumed: un-applied in place); the encoding tables are
+      // still needed by the cotangent pass
+      slab = static_cast<C2A<T>*>(a.state) + (size_t)p * S * M;
+      for (int e = threadIdx.x; e < nS; e += blockDim.x) c.zj()[e] = ws[(size_t)e * a.B + p];
+      __syncthreads();
+      encode_qubit_jets<T, S>(c, n, a.enc);
+      __syncthreads();
+      if (a.enc == QCP_ENC_ANGLE) encode_tables<T, LB, S>(c, n);
+      __syncthreads();
+    } else {
+      forward_point<T, LB, S>(c, a, slab, p);
+    }
     for (int e = threadIdx.x; e < nS; e += blockDim.x) c.qj()[e] = ws[(size_t)(nS + e) * a.B + p];
     for (int e = threadIdx.x; e < NE * S; e += blockDim.x) reinterpret_cast<T*>(c.tabbar())[e] = T(0);
     for (int e = threadIdx.x; e < n * 2 * S; e += blockDim.x) reinterpret_cast<T*>(c.rbar())[e] = T(0);

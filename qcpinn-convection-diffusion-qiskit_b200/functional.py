@@ -196,8 +196,21 @@ class Plan:
         _count(3 if b else 1)
         return gz, gtheta
 
+    # fraction of the device memory the saved statevectors of one call may take (engines R / T);
+    # beyond it the backward recomputes the forward instead
+    STATE_SAVE_BUDGET = 0.35
+
     def workspace(self, batch, mode):
         """Uninitialised saved-jet workspace for one (batch, mode) forward/backward pair."""
+        if not self.fused_engine:
+            es = 8 if self.dtype == torch.float64 else 4
+            state_bytes = 2 * es * mode * batch * (1 << self.n)
+            total = torch.cuda.get_device_properties(self.device).total_memory
+            want = state_bytes <= self.STATE_SAVE_BUDGET * total
+            if want != getattr(self, "_state_save", True):
+                _lib.check(self.lib.qcp_plan_set_state_save(self._handle, int(want)),
+                           "qcp_plan_set_state_save")
+                self._state_save = want
         n = self.lib.qcp_solver_workspace_elems(self._handle, batch, mode)
         return torch.empty(max(int(n), 1), dtype=self.dtype, device=self.device)
 
