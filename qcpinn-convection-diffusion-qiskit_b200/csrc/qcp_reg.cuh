@@ -746,8 +746,6 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
       c.zj()[(size_t)sl * nS + rem] = ok ? ws[(size_t)rem * a.B + p] : T(0);
       c.qj()[(size_t)sl * nS + rem] = ok ? ws[(size_t)(nS + rem) * a.B + p] : T(0);
     }
-    for (int e = threadIdx.x; e < NPT * NE * S; e += blockDim.x) reinterpret_cast<T*>(c.tabbar())[e] = T(0);
-    for (int e = threadIdx.x; e < NPT * n * 2 * S; e += blockDim.x) reinterpret_cast<T*>(c.rbar())[e] = T(0);
     __syncthreads();
     // ---- B2/B3: encoding tables, local part of the sign sums -----------------------------------
     encode_qubit_jets<T, S>(c, n, a.enc, NPT);
@@ -922,63 +920,83 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
         rb[(size_t)row * 32 * NA + i * 32 + lane] = fma(lx[i], fx, ly[i] * fy);
       }
       __syncthreads();
-      // items (slot, L/R, index, stream): partial cotangent jets of the table entries
-      for (int e = threadIdx.x; e < NPT * NE * S; e += blockDim.x) {
-        const int k = e % S, ent = (e / S) % NE, sl = e / (S * NE);
-        const int rw = S == 6 ? k : sl / PP, sb = S == 6 ? sl : sl % PP;
-        const T* rr = rb + (size_t)rw * 32 * NA + sb * G;
-        const Jet<T, S>* tab = c.tab() + (size_t)sl * NE;
-        T a0 = T(0), as = T(0), ap = T(0);
-        if (ent >= NA) {          // lane entry: sum over the local index
-          const int l = ent - NA;
-          for (int i = 0; i < NA; ++i) {
-            const T rho = rr[i * 32 + l];
-            const Jet<T, S>& R = tab[i];
-            a0 = fma(rho, R.c[k], a0);
-            if (k > 0) as = fma(rho, R.c[0], as);
-            if (k >= 4) ap = fma(T(2) * rho, R.c[k - 2], ap);
+      // cotangent jets of the table entries.  Items (slot, entry, stream k) sit on 8 consecutive
+      // lanes: stream k owns component k of the entry, component 0 is the sum over the streams and
+      // the second-order streams (k = 4, 5) also feed components 2, 3 -- combined with shuffles, so
+      // every entry is written once with plain stores (no shared-memory atomics).
+      {
+        const int total = NPT * NE * 8;
+        for (int e0 = 0; e0 < total; e0 += blockDim.x) {
+          const int e = e0 + threadIdx.x;
+          const bool live = e < total;
+          const int k = e & 7, ent = live ? (e >> 3) % NE : 0, sl = live ? (e >> 3) / NE : 0;
+          T a0 = T(0), as = T(0), ap = T(0);
+          if (live && k < S) {
+            const int rw = S == 6 ? k : sl / PP, sb = S == 6 ? sl : sl % PP;
+            const T* rr = rb + (size_t)rw * 32 * NA + sb * G;
+            const Jet<T, S>* tab = c.tab() + (size_t)sl * NE;
+            if (ent >= NA) {          // lane entry: sum over the local index
+              const int l = ent - NA;
+              for (int i = 0; i < NA; ++i) {
+                const T rho = rr[i * 32 + l];
+                const Jet<T, S>& R = tab[i];
+                a0 = fma(rho, R.c[k], a0);
+                if (k > 0) as = fma(rho, R.c[0], as);
+                if (k >= 4) ap = fma(T(2) * rho, R.c[k - 2], ap);
+              }
+            } else {                  // local entry: sum over the lanes of the group
+              for (int l = 0; l < G; ++l) {
+                const T rho = rr[ent * 32 + l];
+                const Jet<T, S>& Lj = tab[NA + l];
+                a0 = fma(rho, Lj.c[k], a0);
+                if (k > 0) as = fma(rho, Lj.c[0], as);
+                if (k >= 4) ap = fma(T(2) * rho, Lj.c[k - 2], ap);
+              }
+            }
           }
-        } else {                  // local entry: sum over the lanes of the group
-          for (int l = 0; l < G; ++l) {
-            const T rho = rr[ent * 32 + l];
-            const Jet<T, S>& Lj = tab[NA + l];
-            a0 = fma(rho, Lj.c[k], a0);
-            if (k > 0) as = fma(rho, Lj.c[0], as);
-            if (k >= 4) ap = fma(T(2) * rho, Lj.c[k - 2], ap);
+          a0 += shx(a0, 1); a0 += shx(a0, 2); a0 += shx(a0, 4);
+          const T ap2 = __shfl_down_sync(0xffffffffu, ap, 2);      // stream k + 2 -> component k
+          if (live && k < S) {
+            Jet<T, S>& tb = c.tabbar()[(size_t)sl * NE + ent];
+            if (k == 0) tb.c[0] = a0;
+            else tb.c[k] = as + ((S == 6 && (k == 2 || k == 3)) ? ap2 : T(0));
           }
         }
-        Jet<T, S>& tb = c.tabbar()[(size_t)sl * NE + ent];
-        atomicAdd(&tb.c[0], a0);
-        if (k > 0) atomicAdd(&tb.c[k], as);
-        if (k >= 4) atomicAdd(&tb.c[k - 2], ap);
       }
       __syncthreads();
-      // table entries -> one-qubit jets (leave-one-out products)
-      for (int e = threadIdx.x; e < NPT * NE; e += blockDim.x) {
-        const int sl = e / NE, ent = e % NE;
-        const bool lane_part = ent >= NA;
-        const int idx = lane_part ? ent - NA : ent;
-        const int K = lane_part ? n - LB : LB;
-        const int q0 = lane_part ? n - 1 - LB : n - 1;
-        const Jet<T, S> eb = c.tabbar()[(size_t)sl * NE + ent];
-        Jet<T, S> suf[6];
-        jzero(suf[K]);
-        suf[K].c[0] = T(1);
-        for (int k = K - 1; k >= 0; --k)
-          suf[k] = jmul(c.rj()[((size_t)sl * n + (q0 - k)) * 2 + ((idx >> k) & 1)], suf[k + 1]);
-        Jet<T, S> pre;
-        jzero(pre);
-        pre.c[0] = T(1);
-        for (int k = 0; k < K; ++k) {
-          const int jq = q0 - k, bit = (idx >> k) & 1;
-          const Jet<T, S> other = jmul(pre, suf[k + 1]);
-          Jet<T, S> fb;
-          jzero(fb);
-          jmul_pull_acc(fb, eb, other);
-          Jet<T, S>& dst = c.rbar()[((size_t)sl * n + jq) * 2 + bit];
+      // table entries -> one-qubit jets: item (slot, qubit, bit, quarter) sums the leave-one-out
+      // pullbacks of a quarter of the entries whose index has that bit; four lanes, two shuffles
+      {
+        const int total = NPT * n * 8;
+        for (int e0 = 0; e0 < total; e0 += blockDim.x) {
+          const int e = e0 + threadIdx.x;
+          const bool live = e < total;
+          const int part = e & 3, bit = (e >> 2) & 1, qq = live ? (e >> 3) % n : 0, sl = live ? (e >> 3) / n : 0;
+          const bool lane_part = qq >= LB;
+          const int kq = lane_part ? qq - LB : qq;
+          const int K = lane_part ? n - LB : LB;
+          const int q0 = lane_part ? n - 1 - LB : n - 1;
+          const int half = (lane_part ? G : NA) >> 1;
+          const int ebase = lane_part ? NA : 0;
+          Jet<T, S> acc;
+          jzero(acc);
+          if (live) {
+            for (int j = part; j < half; j += 4) {
+              const int idx = (((j >> kq) << (kq + 1)) | (j & ((1 << kq) - 1))) | (bit << kq);
+              Jet<T, S> other;
+              jzero(other);
+              other.c[0] = T(1);
+              for (int k2 = 0; k2 < K; ++k2)
+                if (k2 != kq) other = jmul(other, c.rj()[((size_t)sl * n + (q0 - k2)) * 2 + ((idx >> k2) & 1)]);
+              jmul_pull_acc(acc, c.tabbar()[(size_t)sl * NE + ebase + idx], other);
+            }
+          }
 #pragma unroll
-          for (int m = 0; m < S; ++m) atomicAdd(&dst.c[m], fb.c[m]);
-          pre = jmul(pre, c.rj()[((size_t)sl * n + jq) * 2 + bit]);
+          for (int m = 0; m < S; ++m) {
+            acc.c[m] += shx(acc.c[m], 1);
+            acc.c[m] += shx(acc.c[m], 2);
+          }
+          if (live && part == 0) c.rbar()[((size_t)sl * n + (n - 1 - qq)) * 2 + bit] = acc;
         }
       }
       __syncthreads();
