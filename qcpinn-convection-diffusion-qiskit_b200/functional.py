@@ -200,19 +200,36 @@ class Plan:
     # beyond it the backward recomputes the forward instead
     STATE_SAVE_BUDGET = 0.35
 
+    def _state_save_wanted(self, batch, mode) -> bool:
+        if self.fused_engine:
+            return False
+        es = 8 if self.dtype == torch.float64 else 4
+        state_bytes = 2 * es * mode * batch * (1 << self.n)
+        total = torch.cuda.get_device_properties(self.device).total_memory
+        return state_bytes <= self.STATE_SAVE_BUDGET * total
+
+    def _set_state_save(self, want: bool) -> None:
+        if want != getattr(self, "_state_save", True):
+            _lib.check(self.lib.qcp_plan_set_state_save(self._handle, int(want)),
+                       "qcp_plan_set_state_save")
+            self._state_save = want
+
+    def _sync_state_flag(self, save) -> None:
+        """The library sizes / interprets a workspace by the plan's state-save flag: put the flag in
+        the state the workspace was allocated with before every call that receives it."""
+        if save is not None and not self.fused_engine:
+            self._set_state_save(bool(getattr(save, "_qcp_has_state", True)))
+
     def workspace(self, batch, mode):
-        """Uninitialised saved-jet workspace for one (batch, mode) forward/backward pair."""
+        """Uninitialised saved-jet workspace for one (batch, mode) forward/backward pair (engines
+        R / T: plus the final psi streams when they fit the memory budget)."""
+        want = self._state_save_wanted(batch, mode)
         if not self.fused_engine:
-            es = 8 if self.dtype == torch.float64 else 4
-            state_bytes = 2 * es * mode * batch * (1 << self.n)
-            total = torch.cuda.get_device_properties(self.device).total_memory
-            want = state_bytes <= self.STATE_SAVE_BUDGET * total
-            if want != getattr(self, "_state_save", True):
-                _lib.check(self.lib.qcp_plan_set_state_save(self._handle, int(want)),
-                           "qcp_plan_set_state_save")
-                self._state_save = want
+            self._set_state_save(want)
         n = self.lib.qcp_solver_workspace_elems(self._handle, batch, mode)
-        return torch.empty(max(int(n), 1), dtype=self.dtype, device=self.device)
+        ws = torch.empty(max(int(n), 1), dtype=self.dtype, device=self.device)
+        ws._qcp_has_state = want
+        return ws
 
     def solver_forward(self, X, mlp, mode, coeffs=None, want_streams=False, save=None):
         b = X.shape[0]
@@ -222,6 +239,7 @@ class Plan:
                    if (want_streams and mode == MODE_RESIDUAL) else None)
         c = (ctypes.c_double * 5)(*coeffs) if coeffs is not None else None
         m = self._mlp(mlp)
+        self._sync_state_flag(save)
         with torch.cuda.device(self.device):
             rc = self.lib.qcp_solver_forward(
                 self._handle, ctypes.byref(m), ctypes.c_void_p(X.data_ptr()), b, mode, c,
@@ -247,6 +265,7 @@ class Plan:
         c = (ctypes.c_double * 5)(*coeffs) if coeffs is not None else None
         m = self._mlp(mlp)
         g = self._mlp(views[:8])
+        self._sync_state_flag(save)
         with torch.cuda.device(self.device):
             rc = self.lib.qcp_solver_backward(
                 self._handle, ctypes.byref(m), ctypes.c_void_p(theta.data_ptr()),

@@ -169,3 +169,28 @@ def test_solver_module_runs_a_train_step_at_6_qubits(tmp_path):
     l0 = step()
     l1 = step()
     assert l0 == l0 and l1 == l1 and len(model.loss_history) == 2
+
+
+@pytest.mark.parametrize("case", [("cross_mesh", 6, 1, "angle", None), ("sim_circ_15", 11, 1, "angle", None)],
+                         ids=_ids)
+def test_backward_without_saved_state_recomputes_the_forward(case, monkeypatch):
+    """Engines R / T keep the final psi streams in the workspace only while they fit the memory
+    budget; with the budget at zero the backward recomputes the forward -- same gradients, and the
+    flag follows the workspace object when calls with and without state interleave."""
+    ansatz, n, layers, enc, seed = case
+    w, oracle, prog = make_case(ansatz, n, layers, enc, seed)
+    X = points(6, seed=3)
+    coeffs = (1.0, 1.0, 1.0, -0.01, -0.01)
+    uo, ro = osolver.diffusion_operator(
+        oracle, X[:, 0:1].clone(), X[:, 1:2].clone(), X[:, 2:3].clone())
+    (uo.sum() + ro.sum()).backward()
+    plan = F.Plan(prog, 0, torch.float64, 50, DEV)
+    dw = device_weights(w, torch.float64, requires_grad=True)
+    monkeypatch.setattr(F.Plan, "STATE_SAVE_BUDGET", 0.0)
+    ud, rd = F.solver_residual(plan, X.to(DEV), dw["theta"], mlp_list(dw), coeffs)   # no state
+    monkeypatch.setattr(F.Plan, "STATE_SAVE_BUDGET", 0.35)
+    ud2, rd2 = F.solver_residual(plan, X.to(DEV), dw["theta"], mlp_list(dw), coeffs)  # with state
+    (ud.sum() + rd.sum()).backward()          # backward of the FIRST call after the flag flipped
+    assert rel_err(rd, ro) < 1e-10 and rel_err(rd2, ro) < 1e-10
+    for k in osolver.WEIGHT_NAMES:
+        assert rel_err(dw[k].grad, oracle.w[k].grad) < 1e-10, k
