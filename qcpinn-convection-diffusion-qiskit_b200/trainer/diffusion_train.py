@@ -68,6 +68,8 @@ class TrainStep:
         self._eager_calls = 0
         self._graphs = {}          # "device" / "host" -> (graph, static outputs, static batch)
         self.last_terms = None     # (loss, loss_r, loss_bc, loss_ic) tensors of the last step
+        self._stages = []          # two device staging slots for prefetched host batches
+        self._copy_stream = None
 
     def sample(self):
         n = self.batch_size
@@ -139,6 +141,44 @@ class TrainStep:
         model.optimizer.step()
         return flat[numel].clone(), local_terms[0], local_terms[1], local_terms[2]
 
+    # -- host-fed batches ----------------------------------------------------------------------------
+    def prefetch(self, batch):
+        """Start the host->device copy of a FUTURE step's batch on a side stream, so that it overlaps
+        the step running now (data-loader style double buffering; two staging slots).  ``batch`` =
+        the six pinned host tensors of :meth:`sample`; pass the same object to ``step(batch)``
+        later."""
+        dev = self.model.device
+        if not self._stages or any(d.shape != s.shape for d, s in zip(self._stages[0]["buf"], batch)):
+            self._stages = [{"buf": tuple(torch.empty(t.shape, dtype=t.dtype, device=dev) for t in batch),
+                             "src": None, "ready": None, "free": None} for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        slot = next((s for s in self._stages if s["src"] is None), None)
+        if slot is None:
+            raise RuntimeError("TrainStep.prefetch: both staging slots hold batches that were never used")
+        if slot["free"] is not None:                     # its previous consumer is done reading
+            self._copy_stream.wait_event(slot["free"])
+        with torch.cuda.stream(self._copy_stream):
+            for dst, src in zip(slot["buf"], batch):
+                dst.copy_(src, non_blocking=True)
+            slot["ready"] = torch.cuda.Event()
+            slot["ready"].record(self._copy_stream)
+        slot["src"] = batch
+
+    def _take_prefetched(self, batch):
+        """The staging slot holding ``batch`` if it was prefetched (made stream-ordered), else None."""
+        if batch is None:
+            return None
+        for slot in self._stages:
+            if slot["src"] is batch:
+                torch.cuda.current_stream(self.model.device).wait_event(slot["ready"])
+                return slot
+        return None
+
+    def _release_stage(self, slot):
+        slot["src"] = None
+        slot["free"] = torch.cuda.Event()
+        slot["free"].record(torch.cuda.current_stream(self.model.device))
+
     def _host_update(self, loss):
         """plateau scheduler -> loss.item() -> history (needs the host value)."""
         model = self.model
@@ -187,9 +227,12 @@ class TrainStep:
 
         graph, outs, static_batch, launches = self._graphs[kind]
         if static_batch is not None:
+            staged = self._take_prefetched(batch)
             with torch.no_grad():                       # X_ics is a leaf that requires grad
-                for dst, src in zip(static_batch, batch):   # device or pinned-host sources
-                    dst.copy_(src, non_blocking=True)
+                for dst, src in zip(static_batch, staged["buf"] if staged is not None else batch):
+                    dst.copy_(src, non_blocking=True)   # device (staged) or pinned-host sources
+            if staged is not None:
+                self._release_stage(staged)
         graph.replay()
         F.launch_counter += launches
         self.last_terms = outs
@@ -200,7 +243,12 @@ class TrainStep:
             return self._graph_step(batch)
         self._eager_calls += 1
         if batch is not None:
-            batch = tuple(t.to(self.model.device, non_blocking=True) for t in batch)
+            staged = self._take_prefetched(batch)
+            if staged is not None:
+                batch = tuple(t.clone() for t in staged["buf"])
+                self._release_stage(staged)
+            else:
+                batch = tuple(t.to(self.model.device, non_blocking=True) for t in batch)
         if self.fuse_step:
             reduced, loss_r, loss_bc, loss_ic = self._fused_device_step(batch)
         else:

@@ -436,3 +436,29 @@ def test_single_file_trainer_entry_point(tmp_path):
     assert (out / "model.pth").exists()
     err = th.evaluate(model, ns, dom, str(out))
     assert math.isfinite(err) and (out / "evaluation.json").exists()
+
+
+def test_prefetched_host_batches_give_the_same_steps(tmp_path):
+    """TrainStep.prefetch (side-stream H2D into staging slots) vs feeding the host batch directly:
+    identical loss trajectory, in eager and in graph-replay steps."""
+    from qcpinn_b200.trainer.diffusion_train import TrainStep
+
+    def run(prefetch):
+        model = _model(tmp_path / ("p" if prefetch else "d"))
+        step = TrainStep(model, 48)
+        batches = []
+        for i in range(6):
+            b = osolver.make_batches(48, seed=300 + i)
+            batches.append(tuple(b[k].float().contiguous().pin_memory()
+                                 for k in ("X_ic", "u_ic", "X_bc", "u_bc", "X_res", "r_res")))
+        out = []
+        if prefetch:
+            step.prefetch(batches[0])
+        for i, hb in enumerate(batches):
+            if prefetch and i + 1 < len(batches):
+                step.prefetch(batches[i + 1])
+            out.append(step(hb))
+        return out
+
+    a, b = run(False), run(True)
+    assert len(a) == 6 and all(abs(x - y) <= 1e-6 * abs(x) for x, y in zip(a, b)), (a, b)
