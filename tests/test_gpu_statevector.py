@@ -35,6 +35,10 @@ CASES = [
     ("cascade", 12, 1, "angle", 1),
     ("layered", 11, 1, "amplitude", None),
     ("sim_circ_15", 13, 1, "angle", None),
+    ("farhi", 11, 1, "angle", 1),
+    ("alternate", 11, 1, "angle", None),
+    ("layered", 10, 1, "angle", 1),
+    ("cascade", 10, 1, "amplitude", 1),
 ]
 DTYPES = [torch.float64, torch.float32]
 
