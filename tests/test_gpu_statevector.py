@@ -198,3 +198,30 @@ def test_backward_without_saved_state_recomputes_the_forward(case, monkeypatch):
     assert rel_err(rd, ro) < 1e-10 and rel_err(rd2, ro) < 1e-10
     for k in osolver.WEIGHT_NAMES:
         assert rel_err(dw[k].grad, oracle.w[k].grad) < 1e-10, k
+
+
+@pytest.mark.parametrize("n,ansatz", [(6, "layered"), (11, "sim_circ_15")])
+def test_train_step_graph_replay_on_statevector_engines(tmp_path, n, ansatz):
+    """Default TrainStep (CUDA-graph replay after three eager steps) on engines R and T: the
+    captured step allocates nothing, and replays keep training (loss history grows, stays finite,
+    parameters move) exactly like eager steps on the same batches."""
+    from qcpinn_b200.trainer.diffusion_train import TrainStep
+
+    def run(graph):
+        torch.manual_seed(0)
+        args = {"batch_size": 16, "epochs": 2, "lr": 0.005, "seed": 1, "print_every": 10,
+                "num_qubits": n, "num_quantum_layers": 1, "classic_network": [3, 50, 1],
+                "q_ansatz": ansatz, "problem": "diffusion", "solver": "DV", "cuda_graph": graph,
+                "dtype": "float32"}
+        model = qb.DVPDESolver(args, qb.Logging(str(tmp_path / str(graph))), device=DEV)
+        step = TrainStep(model, 24)
+        out = []
+        for i in range(6):
+            b = osolver.make_batches(24, seed=400 + i)
+            out.append(step(tuple(b[k].float().to(DEV) for k in
+                                  ("X_ic", "u_ic", "X_bc", "u_bc", "X_res", "r_res"))))
+        return out
+
+    eager, graph = run(False), run(True)
+    assert all(v == v for v in graph)
+    assert all(abs(a - b) <= 1e-4 * abs(a) for a, b in zip(eager, graph)), (eager, graph)
