@@ -225,3 +225,43 @@ def test_train_step_graph_replay_on_statevector_engines(tmp_path, n, ansatz):
     eager, graph = run(False), run(True)
     assert all(v == v for v in graph)
     assert all(abs(a - b) <= 1e-4 * abs(a) for a, b in zip(eager, graph)), (eager, graph)
+
+
+@pytest.mark.parametrize("ansatz,n,layers,n_pts,n_check", [
+    ("cross_mesh", 10, 2, 262_144, 6),      # BASELINE config 3 at full size (engine R, float32)
+    ("sim_circ_15", 16, 2, 16_384, 2),      # BASELINE config 4 at full size (engine T, float32)
+])
+def test_full_size_properties_configs_3_and_4(ansatz, n, layers, n_pts, n_check):
+    """Size-independent properties at the full BASELINE sizes: (a) deterministic and finite;
+    (b) gradients are additive over a partition of the batch (persistent grids, padding and the
+    saved-state workspace do not depend on where a point sits); (c) a strided sample of points
+    agrees with the CPU oracle."""
+    w, oracle, prog = make_case(ansatz, n, layers, "angle", None)
+    plan = F.Plan(prog, 0, torch.float32, 50, DEV)
+    dw = device_weights(w, torch.float32, DEV)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    X = torch.rand(n_pts, 3, device=DEV, dtype=torch.float32, generator=g)
+    gr = torch.rand(n_pts, device=DEV, dtype=torch.float32, generator=g) / n_pts
+    coeffs = (1.0, 1.0, 1.0, -0.01, -0.01)
+    theta = dw["theta"].reshape(-1)
+    mlp = mlp_list(dw)
+    plan.prepare(theta)
+
+    def fwd_bwd(Xb, gb):
+        ws = plan.workspace(Xb.shape[0], F.MODE_RESIDUAL)
+        u, r, _ = plan.solver_forward(Xb, mlp, F.MODE_RESIDUAL, coeffs, save=ws)
+        grads, _ = plan.solver_backward(Xb, mlp, theta, None, gb, F.MODE_RESIDUAL, coeffs, save=ws)
+        return u.clone(), r.clone(), [v.clone() for v in grads]
+
+    u1, r1, full = fwd_bwd(X, gr)
+    u2, r2, again = fwd_bwd(X, gr)
+    assert torch.equal(r1, r2) and torch.equal(u1, u2) and bool(torch.isfinite(r1).all())
+    half = n_pts // 2 + 7                       # ragged split
+    _, _, a = fwd_bwd(X[:half].contiguous(), gr[:half].contiguous())
+    _, _, b = fwd_bwd(X[half:].contiguous(), gr[half:].contiguous())
+    for f_, a_, b_ in zip(full, a, b):
+        assert rel_err(a_ + b_, f_) < 2e-4          # float32 sums in a different order
+    idx = torch.arange(0, n_pts, n_pts // n_check, device=DEV)[:n_check]
+    Xs = X[idx].cpu().double()
+    uo, ro = osolver.diffusion_operator(oracle, Xs[:, 0:1].clone(), Xs[:, 1:2].clone(), Xs[:, 2:3].clone())
+    assert rel_err(u1[idx], uo[:, 0]) < 1e-5 and rel_err(r1[idx], ro[:, 0]) < 1e-5
