@@ -175,6 +175,14 @@ int qcp_mse_seed(const float* pred, const float* target, long long n, double wei
 int qcp_clip_grads(float* flat, int n_grad, int n_extra, double pre_scale, double max_norm,
                    void* stream);
 
+/* Host-only self check of the statevector-engine planners (no CUDA device needed; used by the CPU
+ * tests): plans the gate list like qcp_plan_create() would for (n_qubits >= 5, dtype), runs the
+ * logical circuit and the planned physical program on the CPU over a random statevector and
+ * returns the largest amplitude difference.  consts = 4x4 complex128 matrices, theta = HOST doubles. */
+int qcp_debug_check_plan(int n_qubits, int dtype, const int32_t* ops, int n_ops, const double* consts,
+                         int n_consts, const double* theta, int n_theta, double* max_err,
+                         int* n_phys_ops, int* n_sweeps);
+
 /* FMA-pipe micro-benchmark used as the roofline denominator: runs
  * ``iters`` dependent-chain FMA rounds on every SM and returns achieved FLOP/s. */
 int qcp_bench_fma(int dtype, int iters, double* flops_per_s, void* stream);

@@ -63,6 +63,9 @@ SIGNATURES = {
                               _c_void_p]),
     "qcp_clip_grads": (_c_int, [_c_void_p, _c_int, _c_int, ctypes.c_double, ctypes.c_double,
                                 _c_void_p]),
+    "qcp_debug_check_plan": (_c_int, [_c_int, _c_int, ctypes.POINTER(ctypes.c_int32), _c_int, _dptr,
+                                      _c_int, _dptr, _c_int, _dptr, ctypes.POINTER(_c_int),
+                                      ctypes.POINTER(_c_int)]),
     "qcp_bench_fma": (_c_int, [_c_int, _c_int, _dptr, _c_void_p]),
 }
 

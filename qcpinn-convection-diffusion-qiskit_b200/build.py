@@ -21,7 +21,7 @@ BUILD_DIR = PKG_DIR / "csrc" / "build"
 LIB_PATH = PKG_DIR / "libqcpinn_b200.so"
 SOURCES = ["qcp_plan.cu", "qcp_point_f32.cu", "qcp_point_f64.cu", "qcp_data.cu", "qcp_state.cu",
            "qcp_reg.cu", "qcp_reg_f32.cu", "qcp_reg_f64.cu", "qcp_tile.cu", "qcp_tile_f32.cu",
-           "qcp_tile_f64.cu",
+           "qcp_tile_f64.cu", "qcp_plancheck.cu",
            "qcp_mlp.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH_FLAGS + [

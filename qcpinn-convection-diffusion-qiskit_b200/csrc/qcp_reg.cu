@@ -203,6 +203,14 @@ static void compile_physical(const GateOp* ops, int n_ops, int n, int LB, std::v
   for (int q = 0; q < n; ++q) meas_pos[q] = pos[q];
 }
 
+// host-only entry for qcp_plancheck.cu
+void reg_compile_host(const GateOp* ops, int n_ops, int n, int LB, std::vector<ROp>& rops,
+                      std::vector<std::vector<int>>& blk_pos, std::vector<DiagGate>& dgs, int* meas_pos) {
+  std::vector<BlkPos> bpos;
+  compile_physical(ops, n_ops, n, LB, rops, bpos, dgs, meas_pos);
+  for (const BlkPos& b : bpos) blk_pos.emplace_back(b.pos, b.pos + n);
+}
+
 RegPlan* reg_create(int n, int enc, int dtype, const GateOp* host_ops, int n_ops, int n_theta,
                     int n_consts, const GateOp* d_ops, const double2* d_consts, int num_sms) {
   if (!reg_supported(n, dtype)) return nullptr;

@@ -227,6 +227,12 @@ static void plan_sweeps(const GateOp* ops, int n_ops, int n, int LB, std::vector
   for (int q = 0; q < n; ++q) final_bit[q] = mbit[q];
 }
 
+// host-only entry for qcp_plancheck.cu
+void tile_plan_host(const GateOp* ops, int n_ops, int n, int LB, std::vector<ROp>& rops,
+                    std::vector<Sweep>& sweeps, int* final_bit) {
+  plan_sweeps(ops, n_ops, n, LB, rops, sweeps, final_bit);
+}
+
 TilePlan* tile_create(int n, int enc, int dtype, const GateOp* host_ops, int n_ops, int n_theta,
                       int n_consts, const GateOp* d_ops, const double2* d_consts, int num_sms) {
   if (!tile_supported(n, dtype)) return nullptr;

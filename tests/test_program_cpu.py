@@ -119,3 +119,48 @@ def test_single_file_trainer_cli_defaults_and_flat_alternate():
     assert pairs == [(0, 1), (2, 3), (1, 2)] and flat.n_theta == 12
     with pytest.raises(IndexError):
         compile_program("alternate", 4, 1, None)            # the DVQuantumLayer variant over-indexes
+
+
+def _check_plan(ansatz, n, layers, seed, dtype_code):
+    import ctypes
+
+    import numpy as np
+
+    import qcpinn_b200 as qb
+    from qcpinn_b200.program import compile_program
+
+    lib = qb._lib.load()
+    prog = compile_program(ansatz, n, layers, seed)
+    ops = np.ascontiguousarray(prog.ops, dtype=np.int32)
+    consts = np.ascontiguousarray(prog.consts, dtype=np.complex128).view(np.float64)
+    theta = np.random.default_rng(7).normal(size=max(prog.n_theta, 1))
+    err, nphys, nsw = ctypes.c_double(), ctypes.c_int(), ctypes.c_int()
+    rc = lib.qcp_debug_check_plan(
+        n, dtype_code, ops.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ops.shape[0],
+        consts.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), prog.consts.shape[0],
+        theta.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), prog.n_theta,
+        ctypes.byref(err), ctypes.byref(nphys), ctypes.byref(nsw))
+    assert rc == 0, lib.qcp_last_error()
+    return err.value, nphys.value, nsw.value
+
+
+def test_statevector_planners_reproduce_the_logical_circuit():
+    """Engine R (register layouts, SWAP / PERM, phase tables) and engine T (sweeps, evolving memory
+    bit map, tile-bit controls) planners, checked on the CPU: the planned physical program applied
+    to a random statevector equals the logical gate list, for every ansatz, both dtypes' layouts
+    and qubit counts across both engines.  No CUDA device involved."""
+    cases = []
+    for ansatz in ("cascade", "layered", "farhi", "sim_circ_15", "cross_mesh"):
+        for n, layers, seed in ((5, 1, None), (6, 2, 1), (8, 1, 1), (10, 2, None), (11, 1, 1), (13, 1, None)):
+            cases.append((ansatz, n, layers, seed))
+    for n in (5, 7, 9, 11, 13):
+        cases.append(("alternate", n, 1, 1))
+    cases.append(("sim_circ_15", 16, 2, None))          # BASELINE config 4
+    cases.append(("cascade", 16, 1, 1))
+    for ansatz, n, layers, seed in cases:
+        for dtype_code in (0, 1):                          # QCP_F32 (LB = 5) / QCP_F64 (LB = 4)
+            err, nphys, nsw = _check_plan(ansatz, n, layers, seed, dtype_code)
+            assert err < 1e-12, (ansatz, n, layers, seed, dtype_code, err)
+            assert nphys > 0
+            tiled = n > (10 if dtype_code == 0 else 9)
+            assert (nsw > 0) == tiled
