@@ -22,7 +22,8 @@ using rg::ROp;
 void reg_compile_host(const GateOp* ops, int n_ops, int n, int LB, std::vector<ROp>& rops,
                       std::vector<std::vector<int>>& blk_pos, std::vector<rg::DiagGate>& dgs, int* meas_pos);
 void tile_plan_host(const GateOp* ops, int n_ops, int n, int LB, std::vector<ROp>& rops,
-                    std::vector<tl::Sweep>& sweeps, int* final_bit);
+                    std::vector<tl::Sweep>& sweeps, int* final_bit, std::vector<rg::DiagGate>& dgs,
+                    std::vector<tl::DiagOff>& doffs);
 
 namespace {
 
@@ -190,7 +191,9 @@ extern "C" int qcp_debug_check_plan(int n_qubits, int dtype, const int32_t* ops_
   } else if (tile_supported(n, dtype)) {
     const int LB = dtype == QCP_F64 ? 4 : 5, TB = LB + 5;
     std::vector<tl::Sweep> sweeps;
-    tile_plan_host(ops, n_ops, n, LB, rops, sweeps, where.data());
+    std::vector<rg::DiagGate> dgs;
+    std::vector<tl::DiagOff> doffs;
+    tile_plan_host(ops, n_ops, n, LB, rops, sweeps, where.data(), dgs, doffs);
     sweeps_out = (int)sweeps.size();
     std::vector<cd> tile((size_t)1 << TB);
     for (const tl::Sweep& sw : sweeps) {
@@ -200,7 +203,26 @@ extern "C" int qcp_debug_check_plan(int n_qubits, int dtype, const int32_t* ops_
         for (int lane = 0; lane < 32; ++lane)
           for (int i = 0; i < (1 << LB); ++i)
             tile[(size_t)i | ((size_t)lane << LB)] = phys[base + sw.ld_loc[i] + sw.ld_lane[lane]];
-        for (int r = sw.r0; r < sw.r1; ++r) apply_rop(tile, rops[r], LB, TB, t, ops, theta, consts);
+        for (int r = sw.r0; r < sw.r1; ++r) {
+          const rg::ROp& op = rops[r];
+          if (op.kind != rg::R_DIAG) { apply_rop(tile, op, LB, TB, t, ops, theta, consts); continue; }
+          // phase table lookup by the LOGICAL index of every tile amplitude
+          const tl::DiagOff& d = doffs[op.m];
+          int toff = 0;
+          for (int k = 0; k < sw.n_other; ++k) toff |= ((t >> k) & 1) ? d.other[k] : 0;
+          for (int lane = 0; lane < 32; ++lane)
+            for (int i = 0; i < (1 << LB); ++i) {
+              const int kl = toff + d.lane[lane] + d.loc[i];
+              double ang = 0.0;
+              for (const rg::DiagGate& dg : dgs) {
+                if (dg.blk != op.g) continue;
+                const double half = 0.5 * theta[dg.p];
+                if (dg.kind == QCP_GATE_RZ) ang += ((kl >> (n - 1 - dg.a)) & 1) ? half : -half;
+                else if ((kl >> (n - 1 - dg.a)) & 1) ang += ((kl >> (n - 1 - dg.b)) & 1) ? half : -half;
+              }
+              tile[(size_t)i | ((size_t)lane << LB)] *= cd(std::cos(ang), std::sin(ang));
+            }
+        }
         for (int lane = 0; lane < 32; ++lane)
           for (int i = 0; i < (1 << LB); ++i)
             phys[base + sw.st_loc[i] + sw.st_lane[lane]] = tile[(size_t)i | ((size_t)lane << LB)];

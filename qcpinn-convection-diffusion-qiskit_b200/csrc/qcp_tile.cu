@@ -29,12 +29,74 @@ __global__ void tl_reduce_theta_kernel(const double* __restrict__ partials, int 
   gtheta[p] = (T)s;
 }
 
+// phase tables of the diagonal blocks in LOGICAL index order: D[(blk << n) + k] = exp(i sum_g angle_g(k)),
+// RZ(t) = diag(e^{-it/2}, e^{+it/2}) on bit n-1-wire of k, CRZ likewise on the control = 1 half
+template <typename T>
+__global__ void tl_diag_build_kernel(int n, int n_blk, const rg::DiagGate* __restrict__ dg, int n_dg,
+                                     const T* __restrict__ theta, C2A<T>* __restrict__ out) {
+  const long long total = (long long)n_blk << n;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int blk = (int)(idx >> n), k = (int)(idx & (((long long)1 << n) - 1));
+    double ang = 0.0;
+    for (int g = 0; g < n_dg; ++g) {
+      const rg::DiagGate d = dg[g];
+      if (d.blk != blk) continue;
+      const double half = 0.5 * (double)theta[d.p];
+      if (d.kind == QCP_GATE_RZ) ang += ((k >> (n - 1 - d.a)) & 1) ? half : -half;
+      else if ((k >> (n - 1 - d.a)) & 1) ang += ((k >> (n - 1 - d.b)) & 1) ? half : -half;
+    }
+    double s, c;
+    sincos(ang, &s, &c);
+    out[idx] = {(T)c, (T)s};
+  }
+}
+
+template <typename T>
+__global__ void tl_wsum_kernel(const T* __restrict__ wpart, int grid, long long total, double* __restrict__ wsum) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= total) return;
+  double s = 0.0;
+  for (int g = 0; g < grid; ++g) s += (double)wpart[(size_t)g * total + j];
+  wsum[j] = s;
+}
+
+// dL/dtheta_g = 1/2 sum_k z_g(k) W_blk[k], z_g = eigenvalue of the generator (Z, or |1><1| (x) Z)
+template <typename T>
+__global__ void tl_diag_grad_kernel(int n, const rg::DiagGate* __restrict__ dg, const double* __restrict__ wsum,
+                                    T* __restrict__ gtheta) {
+  __shared__ double red[8];
+  const rg::DiagGate d = dg[blockIdx.x];
+  double acc = 0.0;
+  for (int k = threadIdx.x; k < (1 << n); k += blockDim.x) {
+    double z;
+    if (d.kind == QCP_GATE_RZ) z = ((k >> (n - 1 - d.a)) & 1) ? -1.0 : 1.0;
+    else z = ((k >> (n - 1 - d.a)) & 1) ? (((k >> (n - 1 - d.b)) & 1) ? -1.0 : 1.0) : 0.0;
+    acc += z * wsum[((size_t)d.blk << n) + k];
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    gtheta[d.p] = (T)(0.5 * s);
+  }
+}
+
 struct TilePlan {
   int n, enc, dtype, LB, TB, n_gates, n_theta, n_consts, n_rops, n_sweeps, num_sms;
   int kind_count[8];
   int final_bit[kMaxQubitsSv];
   ROp* d_rops;
   Sweep* d_sweeps;
+  int n_blk, n_dg, n_doff;    // diagonal blocks, their gates, DIAG op occurrences
+  rg::DiagGate* d_dg;
+  DiagOff* d_doff;
+  void* d_diag;               // C2A<T>[n_blk << n]
+  void* d_wpart;
+  size_t wpart_bytes;
+  double* d_wsum;
   const GateOp* d_gates;      // borrowed from the owning plan
   const double2* d_consts;    // borrowed
   void* d_slab;
@@ -53,10 +115,13 @@ int tile_supported(int n, int dtype) {
   return n > tb && n <= kMaxQubitsSv && n - tb < kMaxOther;
 }
 
+constexpr int kDiagMarker = 100;     // virtual op: "multiply by the phase table of block a"
+
 // qubits a gate needs INSIDE the tile (its dense / diagonal target; both wires of a Haar block)
 static void gate_targets(const GateOp& g, int* t, int* nt) {
   *nt = 0;
   switch (g.kind) {
+    case kDiagMarker: break;          // a table lookup by the full logical index: no residency needed
     case QCP_GATE_RX: case QCP_GATE_RY: case QCP_GATE_RZ: case QCP_GATE_H: t[(*nt)++] = g.a; break;
     case QCP_GATE_CRX: case QCP_GATE_CRZ: case QCP_GATE_CNOT: t[(*nt)++] = g.b; break;
     default: t[(*nt)++] = g.a; t[(*nt)++] = g.b; break;
@@ -82,9 +147,50 @@ static int grow_tile(const GateOp* ops, int n_ops, int g0, int cap, const std::v
   return g;
 }
 
-static void plan_sweeps(const GateOp* ops, int n_ops, int n, int LB, std::vector<ROp>& rops,
-                        std::vector<Sweep>& sweeps, int* final_bit) {
+static bool tile_diag_tables() {
+  const char* env = std::getenv("QCP_TILE_DIAG");
+  return !(env && env[0] == '0');
+}
+
+// Replace every run of commuting diagonal gates (RZ / CRZ) by ONE marker op (same rule as engine R:
+// a diagonal gate joins the open block when no non-diagonal gate since the block opened touches its
+// qubits).  vops = virtual op list, orig[g] = index in the original list (-1 for markers).
+static void fold_diagonals(const GateOp* ops, int n_ops, std::vector<GateOp>& vops, std::vector<int>& orig,
+                           std::vector<rg::DiagGate>& dgs, int* n_blk) {
+  int open = -1, blocks = 0;
+  unsigned dirty = 0;
+  const bool fold = tile_diag_tables();
+  for (int g = 0; g < n_ops; ++g) {
+    const GateOp op = ops[g];
+    if (fold && (op.kind == QCP_GATE_RZ || op.kind == QCP_GATE_CRZ)) {
+      unsigned qs = 1u << op.a;
+      if (op.kind == QCP_GATE_CRZ) qs |= 1u << op.b;
+      if (open < 0 || (qs & dirty)) {
+        open = blocks++;
+        dirty = 0;
+        vops.push_back({kDiagMarker, open, -1, -1});
+        orig.push_back(-1);
+      }
+      dgs.push_back({open, op.kind, op.a, op.b, op.p});
+      continue;
+    }
+    dirty |= 1u << op.a;
+    if (op.b >= 0) dirty |= 1u << op.b;
+    vops.push_back(op);
+    orig.push_back(g);
+  }
+  *n_blk = blocks;
+}
+
+static void plan_sweeps(const GateOp* ops_in, int n_ops_in, int n, int LB, std::vector<ROp>& rops,
+                        std::vector<Sweep>& sweeps, int* final_bit, std::vector<rg::DiagGate>& dgs,
+                        std::vector<DiagOff>& doffs, int* n_blk) {
   const int TB = LB + 5, NA = 1 << LB;
+  std::vector<GateOp> vops;
+  std::vector<int> orig;
+  fold_diagonals(ops_in, n_ops_in, vops, orig, dgs, n_blk);
+  const GateOp* ops = vops.data();
+  const int n_ops = (int)vops.size();
   std::vector<int> mbit(n), qatm(n);               // memory bit of qubit q / qubit at memory bit b
   for (int q = 0; q < n; ++q) { mbit[q] = n - 1 - q; qatm[n - 1 - q] = q; }
   int g = 0;
@@ -164,23 +270,39 @@ static void plan_sweeps(const GateOp* ops, int n_ops, int n, int LB, std::vector
     for (int gg = g; gg < g_end; ++gg) {
       const GateOp op = ops[gg];
       switch (op.kind) {
+        case kDiagMarker: {
+          // logical-index offsets of the current register layout (logical bit of qubit q = n-1-q)
+          DiagOff d{};
+          for (int i = 0; i < 32; ++i) {
+            int lo = 0, la = 0;
+            for (int x = 0; x < LB; ++x)
+              if ((i >> x) & 1) lo |= 1 << (n - 1 - qat[x]);
+            for (int y = 0; y < 5; ++y)
+              if ((i >> y) & 1) la |= 1 << (n - 1 - qat[LB + y]);
+            d.loc[i] = lo; d.lane[i] = la;
+          }
+          for (int k = 0; k < (int)other.size(); ++k) d.other[k] = 1 << (n - 1 - qatm[other[k]]);
+          rops.push_back({rg::R_DIAG, 0, -1, 0, op.a, -1, (int)doffs.size(), 0});
+          doffs.push_back(d);
+          break;
+        }
         case QCP_GATE_RX: case QCP_GATE_RY: case QCP_GATE_RZ: case QCP_GATE_H: {
           make_local(op.a, gg);
           const int type = op.kind == QCP_GATE_RX ? T_X : (op.kind == QCP_GATE_RZ ? T_Z : T_R);
-          rops.push_back({R_L1, pos[op.a], -1, type, gg, op.kind == QCP_GATE_H ? -1 : op.p, 0, 0});
+          rops.push_back({R_L1, pos[op.a], -1, type, orig[gg], op.kind == QCP_GATE_H ? -1 : op.p, 0, 0});
           break;
         }
         case QCP_GATE_CRX: case QCP_GATE_CRZ: {
           make_local(op.b, gg);
           const int pc = ctl_pos(op.a);
-          rops.push_back({R_L1, pos[op.b], pc, op.kind == QCP_GATE_CRX ? T_X : T_Z, gg, op.p,
+          rops.push_back({R_L1, pos[op.b], pc, op.kind == QCP_GATE_CRX ? T_X : T_Z, orig[gg], op.p,
                           pair_mask(pos[op.b], pc), 0});
           break;
         }
         case QCP_GATE_CNOT: {
           make_local(op.b, gg);
           const int pc = ctl_pos(op.a);
-          rops.push_back({R_CX, pos[op.b], pc, 0, gg, -1, pair_mask(pos[op.b], pc), 0});
+          rops.push_back({R_CX, pos[op.b], pc, 0, orig[gg], -1, pair_mask(pos[op.b], pc), 0});
           break;
         }
         default:
@@ -229,8 +351,10 @@ static void plan_sweeps(const GateOp* ops, int n_ops, int n, int LB, std::vector
 
 // host-only entry for qcp_plancheck.cu
 void tile_plan_host(const GateOp* ops, int n_ops, int n, int LB, std::vector<ROp>& rops,
-                    std::vector<Sweep>& sweeps, int* final_bit) {
-  plan_sweeps(ops, n_ops, n, LB, rops, sweeps, final_bit);
+                    std::vector<Sweep>& sweeps, int* final_bit, std::vector<rg::DiagGate>& dgs,
+                    std::vector<DiagOff>& doffs) {
+  int n_blk = 0;
+  plan_sweeps(ops, n_ops, n, LB, rops, sweeps, final_bit, dgs, doffs, &n_blk);
 }
 
 TilePlan* tile_create(int n, int enc, int dtype, const GateOp* host_ops, int n_ops, int n_theta,
@@ -245,13 +369,24 @@ TilePlan* tile_create(int n, int enc, int dtype, const GateOp* host_ops, int n_o
   r->d_gates = d_ops; r->d_consts = d_consts;
   std::vector<ROp> rops;
   std::vector<Sweep> sweeps;
-  plan_sweeps(host_ops, n_ops, n, r->LB, rops, sweeps, r->final_bit);
+  std::vector<rg::DiagGate> dgs;
+  std::vector<DiagOff> doffs;
+  plan_sweeps(host_ops, n_ops, n, r->LB, rops, sweeps, r->final_bit, dgs, doffs, &r->n_blk);
   r->n_rops = (int)rops.size(); r->n_sweeps = (int)sweeps.size();
+  r->n_dg = (int)dgs.size(); r->n_doff = (int)doffs.size();
   for (const ROp& o : rops) r->kind_count[o.kind & 7]++;
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes ? bytes : 16); };
   alloc((void**)&r->d_rops, sizeof(ROp) * rops.size());
   alloc((void**)&r->d_sweeps, sizeof(Sweep) * sweeps.size());
+  alloc((void**)&r->d_dg, sizeof(rg::DiagGate) * dgs.size());
+  alloc((void**)&r->d_doff, sizeof(DiagOff) * doffs.size());
+  alloc(&r->d_diag, 2 * es_of(dtype) * ((size_t)r->n_blk << n));
+  alloc((void**)&r->d_wsum, sizeof(double) * ((size_t)r->n_blk << n));
+  if (e == cudaSuccess && !dgs.empty())
+    e = cudaMemcpy(r->d_dg, dgs.data(), sizeof(rg::DiagGate) * dgs.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && !doffs.empty())
+    e = cudaMemcpy(r->d_doff, doffs.data(), sizeof(DiagOff) * doffs.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess && !rops.empty())
     e = cudaMemcpy(r->d_rops, rops.data(), sizeof(ROp) * rops.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess && !sweeps.empty())
@@ -267,20 +402,33 @@ TilePlan* tile_create(int n, int enc, int dtype, const GateOp* host_ops, int n_o
 void tile_destroy(TilePlan* r) {
   if (!r) return;
   cudaFree(r->d_rops); cudaFree(r->d_sweeps); cudaFree(r->d_slab); cudaFree(r->d_tpart);
+  cudaFree(r->d_dg); cudaFree(r->d_doff); cudaFree(r->d_diag); cudaFree(r->d_wpart); cudaFree(r->d_wsum);
   delete r;
 }
 
-int tile_prepare(TilePlan* r, const void* d_theta, cudaStream_t) {
+int tile_prepare(TilePlan* r, const void* d_theta, cudaStream_t s) {
   r->theta = d_theta;
+  if (r->n_blk == 0) return 0;
+  const long long total = (long long)r->n_blk << r->n;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+  if (r->dtype == QCP_F64)
+    tl_diag_build_kernel<double><<<blocks, 256, 0, s>>>(r->n, r->n_blk, r->d_dg, r->n_dg,
+        static_cast<const double*>(d_theta), static_cast<C2A<double>*>(r->d_diag));
+  else
+    tl_diag_build_kernel<float><<<blocks, 256, 0, s>>>(r->n, r->n_blk, r->d_dg, r->n_dg,
+        static_cast<const float*>(d_theta), static_cast<C2A<float>*>(r->d_diag));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("engine T: table build launch failed: %s", cudaGetErrorString(e)); return 1; }
   return 0;
 }
 
 int tile_num_sweeps(const TilePlan* r) { return r ? r->n_sweeps : 0; }
 
 int tile_describe(const TilePlan* r, char* buf, int len) {
-  return snprintf(buf, len, "engine=tiled n=%d LB=%d tile_bits=%d sweeps=%d ops=%d (dense=%d cnot=%d swap=%d haar=%d)",
+  return snprintf(buf, len, "engine=tiled n=%d LB=%d tile_bits=%d sweeps=%d ops=%d (dense=%d cnot=%d swap=%d "
+                  "diag_blocks=%d covering %d diagonal gates, haar=%d)",
                   r->n, r->LB, r->TB, r->n_sweeps, r->n_rops, r->kind_count[R_L1], r->kind_count[R_CX],
-                  r->kind_count[R_SWAP], r->kind_count[R_U4]);
+                  r->kind_count[R_SWAP], r->n_blk, r->n_dg, r->kind_count[R_U4]);
 }
 
 static int grow(void** ptr, size_t* have, size_t want) {
@@ -318,10 +466,17 @@ int tile_run(TilePlan* r, int S, bool backward, void* ws, long long B, void* sta
   a.rops = r->d_rops; a.sweeps = r->d_sweeps; a.gates = r->d_gates; a.consts = r->d_consts;
   a.theta = r->theta; a.ws = ws; a.B = B; a.slab = r->d_slab; a.slab_stride = stride;
   a.state = state;
+  a.n_blk = r->n_blk; a.doff = r->d_doff; a.diag = r->d_diag;
   if (backward) {
     const int nt = r->n_theta > 0 ? r->n_theta : 1;
     if (grow((void**)&r->d_tpart, &r->tpart_bytes, sizeof(double) * (size_t)grid * nt)) return 1;
     a.theta_partials = r->d_tpart;
+    const size_t wbytes = es * ((size_t)grid * (r->n_blk > 0 ? r->n_blk : 1) << r->n);
+    if (grow(&r->d_wpart, &r->wpart_bytes, wbytes)) return 1;
+    a.w_partials = r->d_wpart;
+    if (r->n_blk > 0 && cudaMemsetAsync(r->d_wpart, 0, wbytes, s) != cudaSuccess) {
+      set_error("engine T: cudaMemsetAsync failed"); return 1;
+    }
     cudaError_t ez = cudaMemsetAsync(r->d_tpart, 0, sizeof(double) * (size_t)grid * nt, s);
     if (ez != cudaSuccess) { set_error("engine T: cudaMemsetAsync failed: %s", cudaGetErrorString(ez)); return 1; }
   }
@@ -337,6 +492,19 @@ int tile_run(TilePlan* r, int S, bool backward, void* ws, long long B, void* sta
       tl_reduce_theta_kernel<float><<<tb, 128, 0, s>>>(r->d_tpart, grid, r->n_theta, static_cast<float*>(grad_theta));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("engine T: reduction launch failed: %s", cudaGetErrorString(e)); return 1; }
+  }
+  if (r->n_blk > 0) {
+    const long long total = (long long)r->n_blk << r->n;
+    const int wb = (int)((total + 127) / 128);
+    if (r->dtype == QCP_F64) {
+      tl_wsum_kernel<double><<<wb, 128, 0, s>>>(static_cast<const double*>(r->d_wpart), grid, total, r->d_wsum);
+      tl_diag_grad_kernel<double><<<r->n_dg, 256, 0, s>>>(r->n, r->d_dg, r->d_wsum, static_cast<double*>(grad_theta));
+    } else {
+      tl_wsum_kernel<float><<<wb, 128, 0, s>>>(static_cast<const float*>(r->d_wpart), grid, total, r->d_wsum);
+      tl_diag_grad_kernel<float><<<r->n_dg, 256, 0, s>>>(r->n, r->d_dg, r->d_wsum, static_cast<float*>(grad_theta));
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("engine T: diagonal gradient launch failed: %s", cudaGetErrorString(e)); return 1; }
   }
   return 0;
 }

@@ -43,6 +43,12 @@ struct Sweep {
   int32_t other[kMaxOther];          // memory bits enumerated by the tile index
 };
 
+// logical-index offsets of one DIAG op occurrence (the register layout at that point of the sweep):
+// amplitude (tile t, local i, lane) has logical index  sum_k bit_k(t) other[k] + lane[lane] + loc[i]
+struct DiagOff {
+  int32_t loc[32], lane[32], other[kMaxOther];
+};
+
 struct TlLayout {
   int rops, cs, u4, zj, qj, rj, tab, qacc, scr, warp_bytes, tabbar, rbar, total;
 };
@@ -60,6 +66,10 @@ struct TlArgs {
   long long B;
   void* slab;                    // per-CTA state storage
   size_t slab_stride;            // complex elements per CTA
+  int n_blk;                     // diagonal blocks (phase tables, LOGICAL index order)
+  const DiagOff* doff;           // one per DIAG op occurrence (ROp.m)
+  const void* diag;              // C2A<T>[n_blk << n]
+  void* w_partials;              // T[grid][n_blk << n]: sum Im(conj(lambda) psi) per block (backward)
   void* state;                   // optional per-POINT psi storage [B][S][2^n]: the forward works in it
                                  // (and leaves the final psi there), the backward starts from it
                                  // instead of recomputing the forward
@@ -158,12 +168,32 @@ __device__ __forceinline__ int ctl_mode(const ROp& op, int lane, int t) {
   return (t >> (op.pc - TB)) & 1;
 }
 
+__device__ __forceinline__ int diag_tile_offset(const DiagOff& d, int n_other, int t) {
+  int o = 0;
+  for (int k = 0; k < n_other; ++k) o |= ((t >> k) & 1) ? d.other[k] : 0;
+  return o;
+}
+
 template <typename T, int LB, int S>
 __device__ __forceinline__ void run_ops_forward(T (&ax)[1 << LB], T (&ay)[1 << LB], const Ctx<T, S>& c,
-                                                int r0, int r1, int lane, int t) {
+                                                int r0, int r1, int lane, int t, int n_other) {
+  constexpr int NA = 1 << LB;
   for (int r = r0; r < r1; ++r) {
     const ROp op = c.rops()[r];
     switch (op.kind) {
+      case rg::R_DIAG: {
+        const DiagOff& d = c.a.doff[op.m];
+        const C2A<T>* tab = static_cast<const C2A<T>*>(c.a.diag) + ((size_t)op.g << c.a.n) +
+                            diag_tile_offset(d, n_other, t) + d.lane[lane];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+          const C2A<T> e = tab[d.loc[i]];
+          const T x = ax[i], y = ay[i];
+          ax[i] = fma(x, e.x, -y * e.y);
+          ay[i] = fma(x, e.y, y * e.x);
+        }
+        break;
+      }
       case rg::R_L1: {
         const T m0 = c.cs()[4 * op.g], m1 = c.cs()[4 * op.g + 1], m2 = c.cs()[4 * op.g + 2], m3 = c.cs()[4 * op.g + 3];
         const int mode = ctl_mode<LB>(op, lane, t);
@@ -196,10 +226,27 @@ __device__ __forceinline__ void run_ops_forward(T (&ax)[1 << LB], T (&ay)[1 << L
 template <typename T, int LB, int S>
 __device__ __forceinline__ void run_ops_backward(T (&ax)[1 << LB], T (&ay)[1 << LB], T (&lx)[1 << LB],
                                                  T (&ly)[1 << LB], const Ctx<T, S>& c, int r0, int r1,
-                                                 int lane, int t, double* gth) {
+                                                 int lane, int t, double* gth, int n_other, T* wacc) {
+  constexpr int NA = 1 << LB;
   for (int r = r1 - 1; r >= r0; --r) {
     const ROp op = c.rops()[r];
     switch (op.kind) {
+      case rg::R_DIAG: {
+        const DiagOff& d = c.a.doff[op.m];
+        const size_t off = ((size_t)op.g << c.a.n) + diag_tile_offset(d, n_other, t) + d.lane[lane];
+        const C2A<T>* tab = static_cast<const C2A<T>*>(c.a.diag) + off;
+        T* wa = wacc + off;
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+          const int li = d.loc[i];
+          atomicAdd(wa + li, fma(lx[i], ay[i], -ly[i] * ax[i]));     // W += Im(conj(lambda) psi)
+          const C2A<T> e = tab[li];
+          const T x = ax[i], y = ay[i], u = lx[i], v = ly[i];
+          ax[i] = fma(x, e.x, y * e.y);  ay[i] = fma(y, e.x, -x * e.y);   // times conj(D)
+          lx[i] = fma(u, e.x, v * e.y);  ly[i] = fma(v, e.x, -u * e.y);
+        }
+        break;
+      }
       case rg::R_L1: {
         const T m0 = c.cs()[4 * op.g], m1 = c.cs()[4 * op.g + 1], m2 = c.cs()[4 * op.g + 2], m3 = c.cs()[4 * op.g + 3];
         const T d1 = op.type == rg::T_R ? m2 : -m1, d2 = op.type == rg::T_R ? m1 : m2;
@@ -431,7 +478,7 @@ __device__ void forward_point(const Ctx<T, S>& c, const TlArgs& a, C2A<T>* slab,
       C2A<T>* vec = slab + (size_t)s * M + tile_base(sw, t);
       T ax[NA], ay[NA];
       tile_load<T, LB>(ax, ay, vec, sw.ld_loc, ld_lane);
-      run_ops_forward<T, LB, S>(ax, ay, c, sw.r0, sw.r1, lane, t);
+      run_ops_forward<T, LB, S>(ax, ay, c, sw.r0, sw.r1, lane, t, sw.n_other);
       tile_store<T, LB>(ax, ay, vec, sw.st_loc, st_lane);
     }
     __syncthreads();
@@ -520,6 +567,7 @@ tl_backward_kernel(const __grid_constant__ TlArgs a) {
   const T* ws = static_cast<const T*>(a.ws);
   T* ws_out = static_cast<T*>(a.ws);
   double* const gth = a.theta_partials + (size_t)blockIdx.x * (a.n_theta > 0 ? a.n_theta : 1);
+  T* const wacc = static_cast<T*>(a.w_partials) + ((size_t)blockIdx.x * a.n_blk << n);
   const size_t M = (size_t)1 << n;
   C2A<T>* lam = cta_slab + (size_t)S * M;
   __syncthreads();
@@ -628,7 +676,7 @@ tl_backward_kernel(const __grid_constant__ TlArgs a) {
         T ax[NA], ay[NA], lx[NA], ly[NA];
         tile_load<T, LB>(ax, ay, vp, sw.st_loc, st_lane);
         tile_load<T, LB>(lx, ly, vl, sw.st_loc, st_lane);
-        run_ops_backward<T, LB, S>(ax, ay, lx, ly, c, sw.r0, sw.r1, lane, t, gth);
+        run_ops_backward<T, LB, S>(ax, ay, lx, ly, c, sw.r0, sw.r1, lane, t, gth, sw.n_other, wacc);
         tile_store<T, LB>(ax, ay, vp, sw.ld_loc, ld_lane);
         tile_store<T, LB>(lx, ly, vl, sw.ld_loc, ld_lane);
       }
