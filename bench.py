@@ -133,6 +133,7 @@ OTHER_CONFIGS = [
     # key, ansatz, qubits, layers, residual points, plan dtype, timed steps
     ("cfg2", "layered", 4, 1, 65_536, "f64", 10),
     ("cfg3", "cross_mesh", 10, 2, 262_144, "f32", 3),
+    ("cfg3_f64", "cross_mesh", 10, 2, 262_144, "f64", 1),
     ("cfg4", "sim_circ_15", 16, 2, 16_384, "f32", 1),
 ]
 

@@ -174,14 +174,17 @@ __device__ __forceinline__ int diag_tile_offset(const DiagOff& d, int n_other, i
   return o;
 }
 
-template <typename T, int LB, int S>
+// DG: the program has diagonal blocks.  The gate interpreter is sensitive to the size of its switch
+// (instruction fetch), so programs without them (sim_circ_15: BASELINE config 4) run a variant that
+// does not contain the table code at all.
+template <typename T, int LB, int S, bool DG>
 __device__ __forceinline__ void run_ops_forward(T (&ax)[1 << LB], T (&ay)[1 << LB], const Ctx<T, S>& c,
                                                 int r0, int r1, int lane, int t, int n_other) {
   constexpr int NA = 1 << LB;
   for (int r = r0; r < r1; ++r) {
     const ROp op = c.rops()[r];
     switch (op.kind) {
-      case rg::R_DIAG: {
+      case rg::R_DIAG: if constexpr (DG) {
         const DiagOff& d = c.a.doff[op.m];
         const C2A<T>* tab = static_cast<const C2A<T>*>(c.a.diag) + ((size_t)op.g << c.a.n) +
                             diag_tile_offset(d, n_other, t) + d.lane[lane];
@@ -192,8 +195,7 @@ __device__ __forceinline__ void run_ops_forward(T (&ax)[1 << LB], T (&ay)[1 << L
           ax[i] = fma(x, e.x, -y * e.y);
           ay[i] = fma(x, e.y, y * e.x);
         }
-        break;
-      }
+      } break;
       case rg::R_L1: {
         const T m0 = c.cs()[4 * op.g], m1 = c.cs()[4 * op.g + 1], m2 = c.cs()[4 * op.g + 2], m3 = c.cs()[4 * op.g + 3];
         const int mode = ctl_mode<LB>(op, lane, t);
@@ -223,7 +225,7 @@ __device__ __forceinline__ void run_ops_forward(T (&ax)[1 << LB], T (&ay)[1 << L
   }
 }
 
-template <typename T, int LB, int S>
+template <typename T, int LB, int S, bool DG>
 __device__ __forceinline__ void run_ops_backward(T (&ax)[1 << LB], T (&ay)[1 << LB], T (&lx)[1 << LB],
                                                  T (&ly)[1 << LB], const Ctx<T, S>& c, int r0, int r1,
                                                  int lane, int t, double* gth, int n_other, T* wacc) {
@@ -231,7 +233,7 @@ __device__ __forceinline__ void run_ops_backward(T (&ax)[1 << LB], T (&ay)[1 << 
   for (int r = r1 - 1; r >= r0; --r) {
     const ROp op = c.rops()[r];
     switch (op.kind) {
-      case rg::R_DIAG: {
+      case rg::R_DIAG: if constexpr (DG) {
         const DiagOff& d = c.a.doff[op.m];
         const size_t off = ((size_t)op.g << c.a.n) + diag_tile_offset(d, n_other, t) + d.lane[lane];
         const C2A<T>* tab = static_cast<const C2A<T>*>(c.a.diag) + off;
@@ -245,8 +247,7 @@ __device__ __forceinline__ void run_ops_backward(T (&ax)[1 << LB], T (&ay)[1 << 
           ax[i] = fma(x, e.x, y * e.y);  ay[i] = fma(y, e.x, -x * e.y);   // times conj(D)
           lx[i] = fma(u, e.x, v * e.y);  ly[i] = fma(v, e.x, -u * e.y);
         }
-        break;
-      }
+      } break;
       case rg::R_L1: {
         const T m0 = c.cs()[4 * op.g], m1 = c.cs()[4 * op.g + 1], m2 = c.cs()[4 * op.g + 2], m3 = c.cs()[4 * op.g + 3];
         const T d1 = op.type == rg::T_R ? m2 : -m1, d2 = op.type == rg::T_R ? m1 : m2;
@@ -450,7 +451,7 @@ __device__ __forceinline__ bool canon_bit(int fb, int t, int i, int lane) {
 // ---------------------------------------------------------------------------------------------
 // forward of one point into the slab (shared by both kernels): generate pass + sweeps
 // ---------------------------------------------------------------------------------------------
-template <typename T, int LB, int S>
+template <typename T, int LB, int S, bool DG>
 __device__ void forward_point(const Ctx<T, S>& c, const TlArgs& a, C2A<T>* slab, long long p) {
   constexpr int NA = 1 << LB, TB = LB + 5;
   const int n = a.n, NT = 1 << (n - TB), nS = n * S;
@@ -478,14 +479,14 @@ __device__ void forward_point(const Ctx<T, S>& c, const TlArgs& a, C2A<T>* slab,
       C2A<T>* vec = slab + (size_t)s * M + tile_base(sw, t);
       T ax[NA], ay[NA];
       tile_load<T, LB>(ax, ay, vec, sw.ld_loc, ld_lane);
-      run_ops_forward<T, LB, S>(ax, ay, c, sw.r0, sw.r1, lane, t, sw.n_other);
+      run_ops_forward<T, LB, S, DG>(ax, ay, c, sw.r0, sw.r1, lane, t, sw.n_other);
       tile_store<T, LB>(ax, ay, vec, sw.st_loc, st_lane);
     }
     __syncthreads();
   }
 }
 
-template <typename T, int LB, int S>
+template <typename T, int LB, int S, bool DG>
 __global__ void __launch_bounds__(tl_warps(false) * 32, 1)
 tl_forward_kernel(const __grid_constant__ TlArgs a) {
   constexpr int NA = 1 << LB, TB = LB + 5;
@@ -500,7 +501,7 @@ tl_forward_kernel(const __grid_constant__ TlArgs a) {
   for (long long p = blockIdx.x; p < a.B; p += gridDim.x) {
     for (int e = threadIdx.x; e < nS; e += blockDim.x) c.qacc()[e] = 0.0;
     C2A<T>* slab = a.state ? static_cast<C2A<T>*>(a.state) + (size_t)p * S * M : cta_slab;
-    forward_point<T, LB, S>(c, a, slab, p);
+    forward_point<T, LB, S, DG>(c, a, slab, p);
     // ---- measure pass (canonical mapping over the final layout) --------------------------------
     for (int it = warp; it < S * NT; it += NW) {
       const int s = it / NT, t = it % NT;
@@ -555,7 +556,7 @@ tl_forward_kernel(const __grid_constant__ TlArgs a) {
 // ---------------------------------------------------------------------------------------------
 // backward kernel
 // ---------------------------------------------------------------------------------------------
-template <typename T, int LB, int S>
+template <typename T, int LB, int S, bool DG>
 __global__ void __launch_bounds__(tl_warps(true) * 32, 1)
 tl_backward_kernel(const __grid_constant__ TlArgs a) {
   constexpr int NA = 1 << LB, TB = LB + 5;
@@ -585,7 +586,7 @@ tl_backward_kernel(const __grid_constant__ TlArgs a) {
       if (a.enc == QCP_ENC_ANGLE) encode_tables<T, LB, S>(c, n);
       __syncthreads();
     } else {
-      forward_point<T, LB, S>(c, a, slab, p);
+      forward_point<T, LB, S, DG>(c, a, slab, p);
     }
     for (int e = threadIdx.x; e < nS; e += blockDim.x) c.qj()[e] = ws[(size_t)(nS + e) * a.B + p];
     for (int e = threadIdx.x; e < NE * S; e += blockDim.x) reinterpret_cast<T*>(c.tabbar())[e] = T(0);
@@ -676,7 +677,7 @@ tl_backward_kernel(const __grid_constant__ TlArgs a) {
         T ax[NA], ay[NA], lx[NA], ly[NA];
         tile_load<T, LB>(ax, ay, vp, sw.st_loc, st_lane);
         tile_load<T, LB>(lx, ly, vl, sw.st_loc, st_lane);
-        run_ops_backward<T, LB, S>(ax, ay, lx, ly, c, sw.r0, sw.r1, lane, t, gth, sw.n_other, wacc);
+        run_ops_backward<T, LB, S, DG>(ax, ay, lx, ly, c, sw.r0, sw.r1, lane, t, gth, sw.n_other, wacc);
         tile_store<T, LB>(ax, ay, vp, sw.ld_loc, ld_lane);
         tile_store<T, LB>(lx, ly, vl, sw.ld_loc, ld_lane);
       }
@@ -849,11 +850,13 @@ inline int tl_launch_one(K kernel, const TlArgs& a, int grid, int threads, size_
   return 0;
 }
 
-#define TL_INSTANTIATE(T, LBV)                                                                         \
-  if (LB == LBV) {                                                                                     \
+#define TL_INSTANTIATE(T, LBV, DGV)                                                                    \
+  if (LB == LBV && (a.n_blk > 0) == DGV) {                                                             \
     if (S == 6)                                                                                        \
-      return backward ? TL_CALL(tl_backward_kernel, T, LBV, 6, true) : TL_CALL(tl_forward_kernel, T, LBV, 6, false); \
-    return backward ? TL_CALL(tl_backward_kernel, T, LBV, 1, true) : TL_CALL(tl_forward_kernel, T, LBV, 1, false);   \
+      return backward ? TL_CALL(tl_backward_kernel, T, LBV, 6, DGV, true)                              \
+                      : TL_CALL(tl_forward_kernel, T, LBV, 6, DGV, false);                             \
+    return backward ? TL_CALL(tl_backward_kernel, T, LBV, 1, DGV, true)                                \
+                    : TL_CALL(tl_forward_kernel, T, LBV, 1, DGV, false);                               \
   }
 
 }  // namespace tl

@@ -6,8 +6,9 @@ namespace tl {
 
 template <>
 int tl_launch<float>(int LB, int S, bool backward, const TlArgs& a, int grid, size_t smem, cudaStream_t s) {
-#define TL_CALL(K, T, LBV, SV, BW) tl_launch_one(&K<T, LBV, SV>, a, grid, tl_warps(BW) * 32, smem, s, #K)
-  TL_INSTANTIATE(float, 5)
+#define TL_CALL(K, T, LBV, SV, DGV, BW) tl_launch_one(&K<T, LBV, SV, DGV>, a, grid, tl_warps(BW) * 32, smem, s, #K)
+  TL_INSTANTIATE(float, 5, false)
+  TL_INSTANTIATE(float, 5, true)
 #undef TL_CALL
   set_error("engine T: no float32 kernel for %d local bits", LB);
   return 1;

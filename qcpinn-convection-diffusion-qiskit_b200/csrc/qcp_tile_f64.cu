@@ -6,8 +6,9 @@ namespace tl {
 
 template <>
 int tl_launch<double>(int LB, int S, bool backward, const TlArgs& a, int grid, size_t smem, cudaStream_t s) {
-#define TL_CALL(K, T, LBV, SV, BW) tl_launch_one(&K<T, LBV, SV>, a, grid, tl_warps(BW) * 32, smem, s, #K)
-  TL_INSTANTIATE(double, 4)
+#define TL_CALL(K, T, LBV, SV, DGV, BW) tl_launch_one(&K<T, LBV, SV, DGV>, a, grid, tl_warps(BW) * 32, smem, s, #K)
+  TL_INSTANTIATE(double, 4, false)
+  TL_INSTANTIATE(double, 4, true)
 #undef TL_CALL
   set_error("engine T: no float64 kernel for %d local bits", LB);
   return 1;
