@@ -14,6 +14,49 @@
 
 namespace qcp {
 
+constexpr int kDiagMarker = 100;     // virtual op: "multiply by the phase table of block a"
+
+// Replace runs of commuting diagonal gates (RZ / CRZ) by ONE marker op per block.
+//   * a diagonal gate JOINS the last emitted block E when no non-diagonal gate emitted since E
+//     touches its qubits (it commutes back to E);
+//   * otherwise it waits in a PENDING block P, which is only emitted when a non-diagonal gate
+//     touches one of P's qubits (gates on other qubits commute past P and are emitted before it).
+// So "RZ RX per wire" layers, "RX RZ per wire" layers and the RZ layers on both sides of a layer
+// boundary all collapse into single blocks.  vops = virtual op list, orig[g] = index in the original
+// list (-1 for markers), dgs = the diagonal gates tagged with their block.
+inline void fold_diagonals(const GateOp* ops, int n_ops, bool enable, std::vector<GateOp>& vops,
+                           std::vector<int>& orig, std::vector<rg::DiagGate>& dgs, int* n_blk) {
+  int blocks = 0, E = -1;
+  unsigned dirtyE = 0, qubitsP = 0;
+  std::vector<rg::DiagGate> P;
+  auto flush = [&]() {
+    if (P.empty()) return;
+    E = blocks++;
+    for (rg::DiagGate d : P) { d.blk = E; dgs.push_back(d); }
+    P.clear();
+    qubitsP = 0;
+    dirtyE = 0;
+    vops.push_back({kDiagMarker, E, -1, -1});
+    orig.push_back(-1);
+  };
+  for (int g = 0; g < n_ops; ++g) {
+    const GateOp op = ops[g];
+    unsigned qs = 1u << op.a;
+    if (op.b >= 0) qs |= 1u << op.b;
+    if (enable && (op.kind == QCP_GATE_RZ || op.kind == QCP_GATE_CRZ)) {
+      if (E >= 0 && !(qs & dirtyE)) dgs.push_back({E, op.kind, op.a, op.b, op.p});
+      else { P.push_back({-1, op.kind, op.a, op.b, op.p}); qubitsP |= qs; }
+      continue;
+    }
+    if (qs & qubitsP) flush();
+    dirtyE |= qs;
+    vops.push_back(op);
+    orig.push_back(g);
+  }
+  flush();
+  *n_blk = blocks;
+}
+
 struct LayoutTracker {
   int LB = 0;
   int perm_min = 4;        // exchanges from which one PERM beats a chain of SWAPs (measured)

@@ -128,8 +128,14 @@ int reg_supported(int n, int dtype) {
 }
 
 // Translate the logical gate list into physical ops (see the header comment of qcp_reg.cuh).
-static void compile_physical(const GateOp* ops, int n_ops, int n, int LB, std::vector<ROp>& rops,
+static void compile_physical(const GateOp* ops_in, int n_ops_in, int n, int LB, std::vector<ROp>& rops,
                              std::vector<BlkPos>& bpos, std::vector<DiagGate>& dgs, int* meas_pos) {
+  std::vector<GateOp> vops;
+  std::vector<int> orig;
+  int n_blk = 0;
+  fold_diagonals(ops_in, n_ops_in, true, vops, orig, dgs, &n_blk);
+  const GateOp* ops = vops.data();
+  const int n_ops = (int)vops.size();
   LayoutTracker lt;
   lt.LB = LB;
   lt.pos.assign(n, -1);
@@ -159,35 +165,25 @@ static void compile_physical(const GateOp* ops, int n_ops, int n, int LB, std::v
     }
     return m;
   };
-  int open = -1;
-  unsigned dirty = 0;
   for (int g = 0; g < n_ops; ++g) {
     const GateOp op = ops[g];
-    if (is_diag(op.kind)) {
-      unsigned qs = 1u << op.a;
-      if (op.kind == QCP_GATE_CRZ) qs |= 1u << op.b;
-      if (open < 0 || (qs & dirty)) {
-        open = (int)bpos.size();
-        BlkPos bp{};
-        for (int q = 0; q < n; ++q) bp.pos[q] = pos[q];
-        bpos.push_back(bp);
-        dirty = 0;
-        rops.push_back({R_DIAG, 0, -1, 0, open, -1, 0, 0});
-      }
-      dgs.push_back({open, op.kind, op.a, op.b, op.p});
+    if (op.kind == kDiagMarker) {          // phase table of block op.a, in the layout of this point
+      BlkPos bp{};
+      for (int q = 0; q < n; ++q) bp.pos[q] = pos[q];
+      if ((int)bpos.size() <= op.a) bpos.resize(op.a + 1);
+      bpos[op.a] = bp;
+      rops.push_back({R_DIAG, 0, -1, 0, op.a, -1, 0, 0});
       continue;
     }
-    dirty |= 1u << op.a;
-    if (op.b >= 0) dirty |= 1u << op.b;
     switch (op.kind) {
       case QCP_GATE_RX: case QCP_GATE_RY: case QCP_GATE_H:
         make_local(op.a, g);
-        rops.push_back({R_L1, pos[op.a], -1, op.kind == QCP_GATE_RX ? T_X : T_R, g,
+        rops.push_back({R_L1, pos[op.a], -1, op.kind == QCP_GATE_RX ? T_X : T_R, orig[g],
                         op.kind == QCP_GATE_H ? -1 : op.p, 0, 0});
         break;
       case QCP_GATE_CRX:
         make_local(op.b, g);
-        rops.push_back({R_L1, pos[op.b], pos[op.a], T_X, g, op.p, pair_mask(pos[op.b], pos[op.a]), 0});
+        rops.push_back({R_L1, pos[op.b], pos[op.a], T_X, orig[g], op.p, pair_mask(pos[op.b], pos[op.a]), 0});
         break;
       case QCP_GATE_CNOT:
         make_local(op.b, g);

@@ -115,8 +115,6 @@ int tile_supported(int n, int dtype) {
   return n > tb && n <= kMaxQubitsSv && n - tb < kMaxOther;
 }
 
-constexpr int kDiagMarker = 100;     // virtual op: "multiply by the phase table of block a"
-
 // qubits a gate needs INSIDE the tile (its dense / diagonal target; both wires of a Haar block)
 static void gate_targets(const GateOp& g, int* t, int* nt) {
   *nt = 0;
@@ -152,43 +150,13 @@ static bool tile_diag_tables() {
   return !(env && env[0] == '0');
 }
 
-// Replace every run of commuting diagonal gates (RZ / CRZ) by ONE marker op (same rule as engine R:
-// a diagonal gate joins the open block when no non-diagonal gate since the block opened touches its
-// qubits).  vops = virtual op list, orig[g] = index in the original list (-1 for markers).
-static void fold_diagonals(const GateOp* ops, int n_ops, std::vector<GateOp>& vops, std::vector<int>& orig,
-                           std::vector<rg::DiagGate>& dgs, int* n_blk) {
-  int open = -1, blocks = 0;
-  unsigned dirty = 0;
-  const bool fold = tile_diag_tables();
-  for (int g = 0; g < n_ops; ++g) {
-    const GateOp op = ops[g];
-    if (fold && (op.kind == QCP_GATE_RZ || op.kind == QCP_GATE_CRZ)) {
-      unsigned qs = 1u << op.a;
-      if (op.kind == QCP_GATE_CRZ) qs |= 1u << op.b;
-      if (open < 0 || (qs & dirty)) {
-        open = blocks++;
-        dirty = 0;
-        vops.push_back({kDiagMarker, open, -1, -1});
-        orig.push_back(-1);
-      }
-      dgs.push_back({open, op.kind, op.a, op.b, op.p});
-      continue;
-    }
-    dirty |= 1u << op.a;
-    if (op.b >= 0) dirty |= 1u << op.b;
-    vops.push_back(op);
-    orig.push_back(g);
-  }
-  *n_blk = blocks;
-}
-
 static void plan_sweeps(const GateOp* ops_in, int n_ops_in, int n, int LB, std::vector<ROp>& rops,
                         std::vector<Sweep>& sweeps, int* final_bit, std::vector<rg::DiagGate>& dgs,
                         std::vector<DiagOff>& doffs, int* n_blk) {
   const int TB = LB + 5, NA = 1 << LB;
   std::vector<GateOp> vops;
   std::vector<int> orig;
-  fold_diagonals(ops_in, n_ops_in, vops, orig, dgs, n_blk);
+  fold_diagonals(ops_in, n_ops_in, tile_diag_tables(), vops, orig, dgs, n_blk);
   const GateOp* ops = vops.data();
   const int n_ops = (int)vops.size();
   std::vector<int> mbit(n), qatm(n);               // memory bit of qubit q / qubit at memory bit b
