@@ -441,7 +441,17 @@ def cpu_baseline(points, steps):
     for i in range(steps):
         trainer.step(osolver.make_batches(points, seed=2 + i))
     dt = time.perf_counter() - t0
+    # also the reference's own batch sizes (README quick-start 64, trainer default 128)
+    # and a mid size, so the CPU path is not judged on one batch size only
+    small = {}
+    for n_small, reps in ((64, 5), (128, 5), (4096, 3)):
+        trainer.step(osolver.make_batches(n_small, seed=50))
+        ts = time.perf_counter()
+        for i in range(reps):
+            trainer.step(osolver.make_batches(n_small, seed=60 + i))
+        small[str(n_small)] = n_small * reps / (time.perf_counter() - ts)
     return {"value": points * steps / dt, "unit": "points/s", "cores": torch.get_num_threads(),
+            "points_per_s_at_batch": small,
             "kind": "port", "sample": f"{steps} full train steps of {points} residual points "
             f"(+2x{points // 3} IC/BC) of the same 4q-cascade workload, complex128 state",
             "note": "oracle restatement stand-in, not PennyLane (not installable here)",
