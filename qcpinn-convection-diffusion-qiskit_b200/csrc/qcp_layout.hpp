@@ -59,6 +59,7 @@ inline void fold_diagonals(const GateOp* ops, int n_ops, bool enable, std::vecto
 
 struct LayoutTracker {
   int LB = 0;
+  int lane_bits = 5;       // 6 when a vector spans two warps (every relayout is then a PERM)
   int perm_min = 4;        // exchanges from which one PERM beats a chain of SWAPs (measured)
   std::vector<int> pos;    // position of qubit q inside the tile, or -1
   std::vector<int> qat;    // qubit at tile position j
@@ -105,14 +106,14 @@ struct LayoutTracker {
     auto masks = [&](const int* src, rg::ROp& op) {
       // bank swizzle: a local source bit x that becomes lane bit y toggles column bit y
       unsigned col[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int y = 0; y < 5; ++y)
+      for (int y = 0; y < lane_bits; ++y)
         if (src[LB + y] < LB) col[src[LB + y]] = 1u << y;
       auto slot_mask = [&](int sp) {          // slot bits toggled by the bit of source position sp
-        return sp < LB ? ((32u << sp) | col[sp]) : (1u << (sp - LB));
+        return sp < LB ? (((1u << lane_bits) << sp) | col[sp]) : (1u << (sp - LB));
       };
       uint32_t w[6] = {0, 0, 0, 0, 0, 0};
       for (int x = 0; x < LB; ++x) w[x / 3] |= slot_mask(x) << (10 * (x % 3));
-      for (int j = 0; j < LB + 5; ++j) w[2 + j / 3] |= slot_mask(src[j]) << (10 * (j % 3));
+      for (int j = 0; j < LB + lane_bits; ++j) w[2 + j / 3] |= slot_mask(src[j]) << (10 * (j % 3));
       op.pc = (int32_t)w[0]; op.type = (int32_t)w[1]; op.g = (int32_t)w[2]; op.p = (int32_t)w[3];
       op.m = (int32_t)w[4]; op.pad = (int32_t)w[5];
     };

@@ -81,10 +81,10 @@ void logical_circuit(std::vector<cd>& v, const GateOp* ops, int n_ops, int n, co
 }
 
 // source position of destination position j, decoded from the PermMasks read masks
-int perm_source(const ROp& op, int LB, int j) {
+int perm_source(const ROp& op, int LB, int lane_bits, int j) {
   const uint32_t w[6] = {(uint32_t)op.pc, (uint32_t)op.type, (uint32_t)op.g, (uint32_t)op.p, (uint32_t)op.m, (uint32_t)op.pad};
   const uint32_t mask = (w[2 + j / 3] >> (10 * (j % 3))) & 1023u;
-  if (mask >> 5) { int sp = 0; while (!((mask >> (5 + sp)) & 1)) ++sp; return sp; }
+  if (mask >> lane_bits) { int sp = 0; while (!((mask >> (lane_bits + sp)) & 1)) ++sp; return sp; }
   int y = 0; while (!((mask >> y) & 1)) ++y;
   return LB + y;
 }
@@ -120,8 +120,9 @@ void apply_rop(std::vector<cd>& v, const ROp& op, int LB, int tile_bits, int til
       std::vector<cd> out(v.size());
       for (size_t d = 0; d < v.size(); ++d) {
         size_t src = 0;
-        for (int j = 0; j < LB + 5; ++j)
-          if ((d >> j) & 1) src |= (size_t)1 << perm_source(op, LB, j);
+        const int lane_bits = tile_bits - LB > 5 ? 6 : 5;
+        for (int j = 0; j < LB + lane_bits; ++j)
+          if ((d >> j) & 1) src |= (size_t)1 << perm_source(op, LB, lane_bits, j);
         out[d] = src < v.size() ? v[src] : cd(0);
       }
       v.swap(out);

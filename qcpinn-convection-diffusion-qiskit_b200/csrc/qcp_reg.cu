@@ -98,6 +98,7 @@ __global__ void rg_diag_grad_kernel(int n, int LB, const BlkPos* __restrict__ bp
 // plan
 // ---------------------------------------------------------------------------------------------
 struct RegPlan {
+  int WV;                     // warps per stream vector (2 when n - LB = 6)
   int n, enc, dtype, LB, G, n_gates, n_theta, n_consts, n_rops, n_blk, n_dg, num_sms;
   int kind_count[8];
   int meas_pos[kMaxQubitsReg];
@@ -118,13 +119,11 @@ struct RegPlan {
 
 static size_t es_of(int dtype) { return dtype == QCP_F64 ? 8 : 4; }
 
-static bool is_diag(int kind) { return kind == QCP_GATE_RZ || kind == QCP_GATE_CRZ; }
-
 int reg_supported(int n, int dtype) {
   const char* env = std::getenv("QCP_ENGINE");
   if (env && (env[0] == 'L' || env[0] == 'l')) return 0;
   if (n < 5) return 0;
-  return dtype == QCP_F64 ? n <= 9 : n <= kMaxQubitsReg;
+  return n <= kMaxQubitsReg;     // float64 at n = 10: two warps per vector
 }
 
 // Translate the logical gate list into physical ops (see the header comment of qcp_reg.cuh).
@@ -138,6 +137,7 @@ static void compile_physical(const GateOp* ops_in, int n_ops_in, int n, int LB, 
   const int n_ops = (int)vops.size();
   LayoutTracker lt;
   lt.LB = LB;
+  if (n - LB > 5) { lt.lane_bits = 6; lt.perm_min = 1; }   // warp-pair vectors: relayout = PERM only
   lt.pos.assign(n, -1);
   lt.qat.assign(16, -1);
   lt.rops = &rops;
@@ -217,6 +217,7 @@ RegPlan* reg_create(int n, int enc, int dtype, const GateOp* host_ops, int n_ops
   const int lbmax = dtype == QCP_F64 ? 4 : 5;
   r->LB = n - 1 < lbmax ? n - 1 : lbmax;
   r->G = 1 << (n - r->LB);
+  r->WV = r->G > 32 ? 2 : 1;
   r->d_gates = d_ops; r->d_consts = d_consts;
   std::vector<ROp> rops;
   std::vector<BlkPos> bpos;
@@ -307,11 +308,11 @@ int reg_run(RegPlan* r, int S, bool backward, void* ws, long long B, void* state
   }
   int& occ = r->occ[S == 6][backward];
   if (occ == 0) {
-    const int rc = r->dtype == QCP_F64 ? rg_occupancy<double>(r->LB, S, backward, L.total, &occ)
-                                       : rg_occupancy<float>(r->LB, S, backward, L.total, &occ);
+    const int rc = r->dtype == QCP_F64 ? rg_occupancy<double>(r->LB, r->WV, S, backward, L.total, &occ)
+                                       : rg_occupancy<float>(r->LB, r->WV, S, backward, L.total, &occ);
     if (rc || occ < 1) { set_error("engine R: kernel does not fit on an SM (smem %d)", L.total); occ = 0; return 1; }
   }
-  const int PP = 32 / r->G, NPT = S == 6 ? PP : rg_warps(S) * PP;
+  const int PP = r->WV == 2 ? 1 : 32 / r->G, NPT = S == 6 ? PP : (rg_warps(S, r->WV) / r->WV) * PP;
   long long want = (B + NPT - 1) / NPT;
   int grid = r->num_sms * occ;
   if ((long long)grid > want) grid = (int)want;
@@ -335,8 +336,8 @@ int reg_run(RegPlan* r, int S, bool backward, void* ws, long long B, void* state
       ez = cudaMemsetAsync(r->d_wpart, 0, es * ((size_t)grid * r->n_blk << r->n), s);
     if (ez != cudaSuccess) { set_error("engine R: cudaMemsetAsync failed: %s", cudaGetErrorString(ez)); return 1; }
   }
-  const int rc = r->dtype == QCP_F64 ? rg_launch<double>(r->LB, S, backward, a, grid, L.total, s)
-                                     : rg_launch<float>(r->LB, S, backward, a, grid, L.total, s);
+  const int rc = r->dtype == QCP_F64 ? rg_launch<double>(r->LB, r->WV, S, backward, a, grid, L.total, s)
+                                     : rg_launch<float>(r->LB, r->WV, S, backward, a, grid, L.total, s);
   if (rc) return rc;
   if (!backward) return 0;
 

@@ -58,7 +58,7 @@ struct DiagGate {   // one diagonal gate of a block (table builder + gradient pr
 
 // shared-memory carve-up (byte offsets; computed on the host, read from the constant bank)
 struct SmemLayout {
-  int rops, cs, u4, zj, qj, rj, tab, exch, atab, tabbar, rbar, gth, wacc, total;
+  int rops, cs, u4, zj, qj, rj, tab, exch, xred, atab, tabbar, rbar, gth, wacc, total;
 };
 
 struct RgArgs {
@@ -89,7 +89,9 @@ struct alignas(2 * sizeof(T)) C2A {
 template <typename T>
 __device__ __forceinline__ T shx(T v, int mask) { return __shfl_xor_sync(0xffffffffu, v, mask); }
 
-__host__ __device__ constexpr int rg_warps(int S) { return S == 6 ? 6 : 4; }
+// WV = warps per stream vector: 1 (n - LB <= 5 lane bits) or 2 (six lane bits: float64 at n = 10; the
+// sixth lane bit is the warp parity, relayouts go through a pair-wide shared-memory PERM)
+__host__ __device__ constexpr int rg_warps(int S, int WV = 1) { return S == 6 ? 6 * WV : 4; }
 
 // ---------------------------------------------------------------------------------------------
 // shared-memory carve-up (identical on host and device)
@@ -98,8 +100,9 @@ __host__ __device__ inline int rg_align(size_t v) { return (int)((v + 15) & ~siz
 
 __host__ __device__ inline SmemLayout rg_layout(size_t es, int LB, int S, int n, int n_rops, int n_gates,
                                                 int n_consts, int n_theta, int n_blk, bool backward) {
-  const int NA = 1 << LB, G = 1 << (n - LB), PP = 32 / G, NW = rg_warps(S);
-  const int NPT = S == 6 ? PP : NW * PP;
+  const int NA = 1 << LB, G = 1 << (n - LB), WV = G > 32 ? 2 : 1, PP = G > 32 ? 1 : 32 / G;
+  const int NW = rg_warps(S, WV);
+  const int NPT = S == 6 ? PP : (NW / WV) * PP;
   SmemLayout L{};
   int o = 0;
   L.rops = o; o = rg_align(o + sizeof(ROp) * (size_t)n_rops);
@@ -110,6 +113,7 @@ __host__ __device__ inline SmemLayout rg_layout(size_t es, int LB, int S, int n,
   L.rj = o; o = rg_align(o + es * (size_t)NPT * n * 2 * S);
   L.tab = o; o = rg_align(o + es * (size_t)NPT * (NA + G) * S);
   L.exch = o; o = rg_align(o + es * 2 * (size_t)NW * 32 * NA);
+  L.xred = o; o = rg_align(o + es * (size_t)NW * kMaxQubitsReg);
   L.atab = o; L.tabbar = o; L.rbar = o; L.gth = o; L.wacc = o;
   if (backward) {
     L.atab = o; o = rg_align(o + es * (size_t)NPT * S * NA);
@@ -304,9 +308,16 @@ __device__ __forceinline__ unsigned perm_field(const PermMasks& pm, int base, in
   return (pm.w[base + j / 3] >> (10 * (j % 3))) & 1023u;
 }
 
-template <typename T, int LB>
+// the WV warps of one stream vector meet at a named barrier (ids 1..15; id 0 is __syncthreads)
+template <int WV>
+__device__ __forceinline__ void vec_sync(int vec) {
+  if constexpr (WV == 1) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(1 + vec), "n"(32 * WV) : "memory");
+}
+
+template <typename T, int LB, int WV = 1>
 __device__ __forceinline__ void perm_apply(T (&ax)[1 << LB], T (&ay)[1 << LB], C2<T>* buf,
-                                           const PermMasks& pm, int lane) {
+                                           const PermMasks& pm, int lane, int vec = 0) {
   constexpr int NA = 1 << LB;
   unsigned wl[LB], rl[LB];
 #pragma unroll
@@ -314,10 +325,10 @@ __device__ __forceinline__ void perm_apply(T (&ax)[1 << LB], T (&ay)[1 << LB], C
     wl[x] = perm_field(pm, 0, x);
     rl[x] = perm_field(pm, 2, x);
   }
-  unsigned rn = 0;
+  unsigned rn = 0;       // `lane` = lane index inside the vector (5 bits, or 6 with WV = 2)
 #pragma unroll
-  for (int y = 0; y < 5; ++y) rn ^= ((lane >> y) & 1) ? perm_field(pm, 2, LB + y) : 0u;
-  __syncwarp();
+  for (int y = 0; y < (WV == 2 ? 6 : 5); ++y) rn ^= ((lane >> y) & 1) ? perm_field(pm, 2, LB + y) : 0u;
+  vec_sync<WV>(vec);
 #pragma unroll
   for (int i = 0; i < NA; ++i) {
     unsigned sl = lane;
@@ -326,7 +337,7 @@ __device__ __forceinline__ void perm_apply(T (&ax)[1 << LB], T (&ay)[1 << LB], C
       if ((i >> x) & 1) sl ^= wl[x];
     buf[sl] = {ax[i], ay[i]};
   }
-  __syncwarp();
+  vec_sync<WV>(vec);
 #pragma unroll
   for (int i = 0; i < NA; ++i) {
     unsigned sl = rn;
@@ -407,6 +418,7 @@ struct Ctx {
   __device__ __forceinline__ Jet<T, S>* rj() const { return at<Jet<T, S>>(a.lay.rj); }          // [NPT][n][2]
   __device__ __forceinline__ Jet<T, S>* tab() const { return at<Jet<T, S>>(a.lay.tab); }        // [NPT][NA+G]
   __device__ __forceinline__ C2<T>* exch() const { return at<C2<T>>(a.lay.exch); }              // [NW][32*NA]
+  __device__ __forceinline__ T* xred() const { return at<T>(a.lay.xred); }                      // [NW][kMaxQubitsReg]
   __device__ __forceinline__ T* atab() const { return at<T>(a.lay.atab); }                      // [NPT][S][NA]
   __device__ __forceinline__ Jet<T, S>* tabbar() const { return at<Jet<T, S>>(a.lay.tabbar); }  // [NPT][NA+G]
   __device__ __forceinline__ Jet<T, S>* rbar() const { return at<Jet<T, S>>(a.lay.rbar); }      // [NPT][n][2]
@@ -446,7 +458,7 @@ __device__ void load_program(const RgArgs& a) {
 // ---------------------------------------------------------------------------------------------
 // gate program, forward direction, on one register vector
 // ---------------------------------------------------------------------------------------------
-template <typename T, int LB, int S>
+template <typename T, int LB, int S, int WV>
 __device__ __forceinline__ void run_forward(T (&ax)[1 << LB], T (&ay)[1 << LB], const Ctx<T, S>& c,
                                             const RgArgs& a, int lig, int G) {
   const C2A<T>* diag = static_cast<const C2A<T>*>(a.diag);
@@ -482,8 +494,12 @@ __device__ __forceinline__ void run_forward(T (&ax)[1 << LB], T (&ay)[1 << LB], 
         diag_apply<T, LB>(ax, ay, diag + ((size_t)op.g << a.n) + lig, G, false);
         break;
       case R_PERM:
-        perm_apply<T, LB>(ax, ay, c.exch() + (size_t)(threadIdx.x >> 5) * 32 * (1 << LB),
-                          perm_masks_of(op), threadIdx.x & 31);
+        if constexpr (WV == 1)
+          perm_apply<T, LB>(ax, ay, c.exch() + (size_t)(threadIdx.x >> 5) * 32 * (1 << LB),
+                            perm_masks_of(op), threadIdx.x & 31);
+        else       // the two rows of the warp pair are one 64 x NA buffer
+          perm_apply<T, LB, 2>(ax, ay, c.exch() + (size_t)(threadIdx.x >> 6) * 64 * (1 << LB),
+                               perm_masks_of(op), lig, threadIdx.x >> 6);
         break;
       case R_PERMB:
         break;
@@ -609,9 +625,10 @@ __device__ __forceinline__ void encode_stream(T (&ax)[1 << LB], T (&ay)[1 << LB]
 // measurement helpers
 // ---------------------------------------------------------------------------------------------
 // signed sums of a per-amplitude real density over the group -> q[qubit] (valid in every lane)
-template <typename T, int LB>
+template <typename T, int LB, int WV = 1>
 __device__ __forceinline__ void signed_sums(const T (&w)[1 << LB], const RgArgs& a, int lig, int G,
-                                            T* out /* [n] registers via static loop bound kMaxQubitsReg */) {
+                                            T* out /* [n] registers via static loop bound kMaxQubitsReg */,
+                                            T* xred = nullptr /* [NW][kMaxQubitsReg] when WV == 2 */) {
   constexpr int NA = 1 << LB;
   T t = T(0), sx[LB];
 #pragma unroll
@@ -634,26 +651,40 @@ __device__ __forceinline__ void signed_sums(const T (&w)[1 << LB], const RgArgs&
 #pragma unroll
         for (int x = 1; x < LB; ++x) v = pos == x ? sx[x] : v;
       }
-      for (int m = 1; m < G; m <<= 1) v += shx(v, m);
+      for (int m = 1; m < (G < 32 ? G : 32); m <<= 1) v += shx(v, m);
       out[q] = v;
     }
+  }
+  if constexpr (WV == 2) {       // the other half of the vector lives in the partner warp
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int q = 0; q < kMaxQubitsReg; ++q)
+        if (q < a.n) xred[warp * kMaxQubitsReg + q] = out[q];
+    }
+    vec_sync<2>(warp >> 1);
+#pragma unroll
+    for (int q = 0; q < kMaxQubitsReg; ++q)
+      if (q < a.n) out[q] += xred[(warp ^ 1) * kMaxQubitsReg + q];
+    vec_sync<2>(warp >> 1);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // forward kernel
 // ---------------------------------------------------------------------------------------------
-template <typename T, int LB, int S>
-__global__ void __launch_bounds__(rg_warps(S) * 32, rg_min_blocks(S, false))
+template <typename T, int LB, int S, int WV>
+__global__ void __launch_bounds__(rg_warps(S, WV) * 32, WV == 2 ? 1 : rg_min_blocks(S, false))
 rg_forward_kernel(const __grid_constant__ RgArgs a) {
-  constexpr int NA = 1 << LB, NW = rg_warps(S);
-  const int n = a.n, G = 1 << (n - LB), PP = 32 / G, NPT = S == 6 ? PP : NW * PP;
+  constexpr int NA = 1 << LB, NW = rg_warps(S, WV);
+  const int n = a.n, G = 1 << (n - LB), PP = WV == 2 ? 1 : 32 / G, NPT = S == 6 ? PP : (NW / WV) * PP;
   const Ctx<T, S> c{a};
   load_program<T, S>(a);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int lig = lane & (G - 1), sub = lane / G;
-  const int slot = S == 6 ? sub : warp * PP + sub;
-  const int s = S == 6 ? warp : 0;
+  const int wv = WV == 2 ? warp & 1 : 0, vec = warp / WV;          // half of / index of this warp's vector
+  const int lig = WV == 2 ? (wv << 5) | lane : lane & (G - 1), sub = WV == 2 ? 0 : lane / G;
+  const int slot = S == 6 ? sub : vec * PP + sub;
+  const int s = S == 6 ? vec : 0;
   const T* ws = static_cast<const T*>(a.ws);
   T* ws_out = static_cast<T*>(a.ws);
   const int nS = n * S;
@@ -673,7 +704,7 @@ rg_forward_kernel(const __grid_constant__ RgArgs a) {
 
     T ax[NA], ay[NA];
     encode_stream<T, LB, S>(ax, ay, c, n, a.enc, slot, lig, s);
-    run_forward<T, LB, S>(ax, ay, c, a, lig, G);
+    run_forward<T, LB, S, WV>(ax, ay, c, a, lig, G);
 
     const long long p = base + slot;
     const bool valid = p < a.B;
@@ -682,11 +713,12 @@ rg_forward_kernel(const __grid_constant__ RgArgs a) {
 #pragma unroll
       for (int i = 0; i < NA; ++i) st[i * G] = {ax[i], ay[i]};
     }
-    C2<T>* ex = c.exch();
+    C2<T>* ex = c.exch();          // row of (stream k, half wv) = k * WV + wv
     if constexpr (S == 6) {
+      if constexpr (WV == 2) __syncthreads();   // the rows were PERM staging buffers until now
       if (s < 4) {
 #pragma unroll
-        for (int i = 0; i < NA; ++i) ex[(size_t)s * 32 * NA + i * 32 + lane] = {ax[i], ay[i]};
+        for (int i = 0; i < NA; ++i) ex[(size_t)(s * WV + wv) * 32 * NA + i * 32 + lane] = {ax[i], ay[i]};
       }
       __syncthreads();
     }
@@ -697,17 +729,17 @@ rg_forward_kernel(const __grid_constant__ RgArgs a) {
     } else {
 #pragma unroll
       for (int i = 0; i < NA; ++i) {
-        const C2<T> p0 = ex[i * 32 + lane];
+        const C2<T> p0 = ex[(size_t)wv * 32 * NA + i * 32 + lane];
         T v = T(2) * fma(ax[i], p0.x, ay[i] * p0.y);
         if (s >= 4) {
-          const C2<T> pd = ex[(size_t)(s - 2) * 32 * NA + i * 32 + lane];
+          const C2<T> pd = ex[(size_t)((s - 2) * WV + wv) * 32 * NA + i * 32 + lane];
           v = fma(T(2), fma(pd.x, pd.x, pd.y * pd.y), v);
         }
         w[i] = v;
       }
     }
     T q[kMaxQubitsReg];
-    signed_sums<T, LB>(w, a, lig, G, q);
+    signed_sums<T, LB, WV>(w, a, lig, G, q, c.xred());
     if (lig == 0 && valid) {
 #pragma unroll
       for (int j = 0; j < kMaxQubitsReg; ++j)
@@ -720,11 +752,11 @@ rg_forward_kernel(const __grid_constant__ RgArgs a) {
 // ---------------------------------------------------------------------------------------------
 // backward kernel
 // ---------------------------------------------------------------------------------------------
-template <typename T, int LB, int S>
-__global__ void __launch_bounds__(rg_warps(S) * 32, rg_min_blocks(S, true))
+template <typename T, int LB, int S, int WV>
+__global__ void __launch_bounds__(rg_warps(S, WV) * 32, WV == 2 ? 1 : rg_min_blocks(S, true))
 rg_backward_kernel(const __grid_constant__ RgArgs a) {
-  constexpr int NA = 1 << LB, NW = rg_warps(S);
-  const int n = a.n, G = 1 << (n - LB), PP = 32 / G, NPT = S == 6 ? PP : NW * PP, NE = NA + G;
+  constexpr int NA = 1 << LB, NW = rg_warps(S, WV);
+  const int n = a.n, G = 1 << (n - LB), PP = WV == 2 ? 1 : 32 / G, NPT = S == 6 ? PP : (NW / WV) * PP, NE = NA + G;
   const Ctx<T, S> c{a};
   load_program<T, S>(a);
   // per-CTA accumulator rows in global memory (zeroed by the host): fire-and-forget RED.ADD, which
@@ -732,10 +764,11 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
   double* const gth = a.theta_partials + (size_t)blockIdx.x * (a.n_theta > 0 ? a.n_theta : 1);
   T* const wacc = static_cast<T*>(a.w_partials) + ((size_t)blockIdx.x * a.n_blk << n);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int lig = lane & (G - 1), sub = lane / G;
-  const int slot = S == 6 ? sub : warp * PP + sub;
-  const int s = S == 6 ? warp : 0;
-  const int row = S == 6 ? s : warp;               // exchange-buffer row of this warp
+  const int wv = WV == 2 ? warp & 1 : 0, vec = warp / WV;          // half of / index of this warp's vector
+  const int lig = WV == 2 ? (wv << 5) | lane : lane & (G - 1), sub = WV == 2 ? 0 : lane / G;
+  const int slot = S == 6 ? sub : vec * PP + sub;
+  const int s = S == 6 ? vec : 0;
+  const int row = warp;                            // exchange-buffer row of this warp (= s * WV + wv)
   const T* ws = static_cast<const T*>(a.ws);
   T* ws_out = static_cast<T*>(a.ws);
   const C2A<T>* diag = static_cast<const C2A<T>*>(a.diag);
@@ -784,12 +817,13 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
       }
     } else {
       encode_stream<T, LB, S>(ax, ay, c, n, a.enc, slot, lig, s);
-      run_forward<T, LB, S>(ax, ay, c, a, lig, G);
+      run_forward<T, LB, S, WV>(ax, ay, c, a, lig, G);
     }
-    C2<T>* ex = c.exch();
+    C2<T>* ex = c.exch();          // row of (stream k, half wv) = k * WV + wv
     if constexpr (S == 6) {
+      if constexpr (WV == 2) __syncthreads();   // (recompute path) rows were PERM staging buffers
 #pragma unroll
-      for (int i = 0; i < NA; ++i) ex[(size_t)s * 32 * NA + i * 32 + lane] = {ax[i], ay[i]};
+      for (int i = 0; i < NA; ++i) ex[(size_t)row * 32 * NA + i * 32 + lane] = {ax[i], ay[i]};
       __syncthreads();
     }
     // ---- B5: lambda streams from the q cotangents -----------------------------------------------
@@ -819,7 +853,7 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
 #pragma unroll
             for (int k = 1; k < 6; ++k) {
               const T zk = T(2) * (at[k * NA + i] + bl[k]);
-              const C2<T> pk = ex[(size_t)k * 32 * NA + i * 32 + lane];
+              const C2<T> pk = ex[(size_t)(k * WV + wv) * 32 * NA + i * 32 + lane];
               vx = fma(zk, pk.x, vx);
               vy = fma(zk, pk.y, vy);
             }
@@ -829,7 +863,7 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
       } else if constexpr (S == 6) {
 #pragma unroll
         for (int i = 0; i < NA; ++i) {
-          const C2<T> p0 = ex[i * 32 + lane];
+          const C2<T> p0 = ex[(size_t)wv * 32 * NA + i * 32 + lane];
           const T zs = T(2) * (at[s * NA + i] + bl[s]);
           T vx = zs * p0.x, vy = zs * p0.y;
           if (s == 2 || s == 3) {
@@ -898,10 +932,16 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
           break;
         }
         case R_PERMB: {
-          C2<T>* pb = c.exch() + (size_t)warp * 32 * NA;
           const PermMasks pm = perm_masks_of(op);
-          perm_apply<T, LB>(ax, ay, pb, pm, lane);
-          perm_apply<T, LB>(lx, ly, pb, pm, lane);
+          if constexpr (WV == 1) {
+            C2<T>* pb = c.exch() + (size_t)warp * 32 * NA;
+            perm_apply<T, LB>(ax, ay, pb, pm, lane);
+            perm_apply<T, LB>(lx, ly, pb, pm, lane);
+          } else {
+            C2<T>* pb = c.exch() + (size_t)vec * 64 * NA;
+            perm_apply<T, LB, 2>(ax, ay, pb, pm, lig, vec);
+            perm_apply<T, LB, 2>(lx, ly, pb, pm, lig, vec);
+          }
           break;
         }
         case R_PERM:
@@ -938,13 +978,17 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
           const int k = e & 7, ent = live ? (e >> 3) % NE : 0, sl = live ? (e >> 3) / NE : 0;
           T a0 = T(0), as = T(0), ap = T(0);
           if (live && k < S) {
-            const int rw = S == 6 ? k : sl / PP, sb = S == 6 ? sl : sl % PP;
-            const T* rr = rb + (size_t)rw * 32 * NA + sb * G;
+            // row of (stream / vector, half) and the lane inside it that holds rho(i, l)
+            const int vrow = (S == 6 ? k : sl / PP) * WV, sb = S == 6 ? sl : sl % PP;
+            auto rho_at = [&](int i, int l) -> T {
+              if constexpr (WV == 2) return rb[(size_t)(vrow + (l >> 5)) * 32 * NA + i * 32 + (l & 31)];
+              else return rb[(size_t)vrow * 32 * NA + i * 32 + sb * G + l];
+            };
             const Jet<T, S>* tab = c.tab() + (size_t)sl * NE;
             if (ent >= NA) {          // lane entry: sum over the local index
               const int l = ent - NA;
               for (int i = 0; i < NA; ++i) {
-                const T rho = rr[i * 32 + l];
+                const T rho = rho_at(i, l);
                 const Jet<T, S>& R = tab[i];
                 a0 = fma(rho, R.c[k], a0);
                 if (k > 0) as = fma(rho, R.c[0], as);
@@ -952,7 +996,7 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
               }
             } else {                  // local entry: sum over the lanes of the group
               for (int l = 0; l < G; ++l) {
-                const T rho = rr[ent * 32 + l];
+                const T rho = rho_at(ent, l);
                 const Jet<T, S>& Lj = tab[NA + l];
                 a0 = fma(rho, Lj.c[k], a0);
                 if (k > 0) as = fma(rho, Lj.c[0], as);
@@ -1071,9 +1115,9 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
 
 // per-dtype launchers (qcp_reg_f32.cu / qcp_reg_f64.cu)
 template <typename T>
-int rg_launch(int LB, int S, bool backward, const RgArgs& a, int grid, size_t smem, cudaStream_t s);
+int rg_launch(int LB, int WV, int S, bool backward, const RgArgs& a, int grid, size_t smem, cudaStream_t s);
 template <typename T>
-int rg_occupancy(int LB, int S, bool backward, size_t smem, int* blocks_per_sm);
+int rg_occupancy(int LB, int WV, int S, bool backward, size_t smem, int* blocks_per_sm);
 
 template <typename K>
 inline int rg_launch_one(K kernel, const RgArgs& a, int grid, int threads, size_t smem, cudaStream_t s,
@@ -1108,11 +1152,11 @@ inline int rg_occ_one(K kernel, int threads, size_t smem, int* out) {
 }
 
 // dispatch over (LB, S, direction); RG_CALL(kernel-template, T, LB, S) is defined by the includer
-#define RG_INSTANTIATE(T, LBV)                                                              \
-  if (LB == LBV) {                                                                          \
+#define RG_INSTANTIATE(T, LBV, WVV)                                                         \
+  if (LB == LBV && WV == WVV) {                                                             \
     if (S == 6)                                                                             \
-      return backward ? RG_CALL(rg_backward_kernel, T, LBV, 6) : RG_CALL(rg_forward_kernel, T, LBV, 6); \
-    return backward ? RG_CALL(rg_backward_kernel, T, LBV, 1) : RG_CALL(rg_forward_kernel, T, LBV, 1);   \
+      return backward ? RG_CALL(rg_backward_kernel, T, LBV, 6, WVV) : RG_CALL(rg_forward_kernel, T, LBV, 6, WVV); \
+    return backward ? RG_CALL(rg_backward_kernel, T, LBV, 1, WVV) : RG_CALL(rg_forward_kernel, T, LBV, 1, WVV);   \
   }
 
 }  // namespace rg

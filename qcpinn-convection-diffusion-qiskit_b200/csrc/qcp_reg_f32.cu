@@ -5,20 +5,20 @@ namespace qcp {
 namespace rg {
 
 template <>
-int rg_launch<float>(int LB, int S, bool backward, const RgArgs& a, int grid, size_t smem, cudaStream_t s) {
-#define RG_CALL(K, T, LBV, SV) rg_launch_one(&K<T, LBV, SV>, a, grid, rg_warps(SV) * 32, smem, s, #K)
-  RG_INSTANTIATE(float, 5)
-  RG_INSTANTIATE(float, 4)
+int rg_launch<float>(int LB, int WV, int S, bool backward, const RgArgs& a, int grid, size_t smem, cudaStream_t s) {
+#define RG_CALL(K, T, LBV, SV, WVV) rg_launch_one(&K<T, LBV, SV, WVV>, a, grid, rg_warps(SV, WVV) * 32, smem, s, #K)
+  RG_INSTANTIATE(float, 5, 1)
+  RG_INSTANTIATE(float, 4, 1)
 #undef RG_CALL
-  set_error("engine R: no float32 kernel for %d local bits", LB);
+  set_error("engine R: no float32 kernel for %d local bits / %d warps per vector", LB, WV);
   return 1;
 }
 
 template <>
-int rg_occupancy<float>(int LB, int S, bool backward, size_t smem, int* blocks_per_sm) {
-#define RG_CALL(K, T, LBV, SV) rg_occ_one(&K<T, LBV, SV>, rg_warps(SV) * 32, smem, blocks_per_sm)
-  RG_INSTANTIATE(float, 5)
-  RG_INSTANTIATE(float, 4)
+int rg_occupancy<float>(int LB, int WV, int S, bool backward, size_t smem, int* blocks_per_sm) {
+#define RG_CALL(K, T, LBV, SV, WVV) rg_occ_one(&K<T, LBV, SV, WVV>, rg_warps(SV, WVV) * 32, smem, blocks_per_sm)
+  RG_INSTANTIATE(float, 5, 1)
+  RG_INSTANTIATE(float, 4, 1)
 #undef RG_CALL
   *blocks_per_sm = 0;
   return 1;

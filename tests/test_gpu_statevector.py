@@ -23,7 +23,7 @@ CASES = [
     ("cascade", 6, 1, "amplitude", 1),
     ("cross_mesh", 5, 2, "amplitude", None),
     # larger registers-resident shapes (engine R: lane/local swaps, diagonal blocks, Haar hops);
-    # float64 n = 10 runs on the tiled engine
+    # float64 n = 10 runs with two warps per stream vector
     ("cross_mesh", 10, 2, "angle", None),
     ("sim_circ_15", 8, 1, "angle", 1),
     ("layered", 9, 1, "angle", None),
@@ -60,8 +60,7 @@ def test_layer_forward_backward(case, dtype):
     (qo * cot).sum().backward()
 
     plan = F.Plan(prog, F.encoding_code(enc), dtype, 50, DEV)
-    reg_max = 10 if dtype == torch.float32 else 9
-    assert plan.engine == ("register" if n <= reg_max else "tiled")
+    assert plan.engine == ("register" if n <= 10 else "tiled")    # float64 at n = 10: warp pairs
     zd = z.to(DEV, dtype).requires_grad_(True)
     th = w["theta"].to(DEV, dtype).requires_grad_(True)
     qd = F.layer_apply(plan, zd, th)

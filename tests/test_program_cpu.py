@@ -162,5 +162,5 @@ def test_statevector_planners_reproduce_the_logical_circuit():
             err, nphys, nsw = _check_plan(ansatz, n, layers, seed, dtype_code)
             assert err < 1e-12, (ansatz, n, layers, seed, dtype_code, err)
             assert nphys > 0
-            tiled = n > (10 if dtype_code == 0 else 9)
+            tiled = n > 10
             assert (nsw > 0) == tiled
