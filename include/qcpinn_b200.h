@@ -82,7 +82,7 @@ int qcp_plan_destroy(qcp_plan_t* plan);
 int qcp_plan_num_features(const qcp_plan_t* plan);
 
 /* Which kernels a plan runs on: QCP_ENGINE_FEATURE (n <= 4: observables pre-multiplied into a real
- * feature matrix), QCP_ENGINE_REGISTER (5 <= n <= 10, float64: <= 9: per-sample statevectors in
+ * feature matrix), QCP_ENGINE_REGISTER (5 <= n <= 10: per-sample statevectors in
  * registers, one warp per Taylor stream), QCP_ENGINE_TILED (up to 16 qubits: per-sample statevectors
  * in an HBM/L2-resident slab, swept tile by tile through registers) or QCP_ENGINE_GLOBAL (the
  * gate-by-gate fallback, selected with QCP_ENGINE=L in the environment). */

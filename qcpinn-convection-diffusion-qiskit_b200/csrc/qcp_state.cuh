@@ -24,7 +24,7 @@ size_t sv_state_bytes_rt(int dtype, int n, int S);
 size_t sv_fixed_smem_rt(int dtype, int n, int S, int n_ops, int n_theta);
 int sv_run(int dtype, int S, bool backward, const SvLaunch& L, cudaStream_t s);
 
-// engine R (qcp_reg.cu): register-resident statevectors for 5 <= n <= 10 (float64: <= 9)
+// engine R (qcp_reg.cu): register-resident statevectors for 5 <= n <= 10 (float64 at n = 10: two warps per vector)
 struct RegPlan;
 int reg_supported(int n, int dtype);
 RegPlan* reg_create(int n, int enc, int dtype, const GateOp* host_ops, int n_ops, int n_theta,
@@ -36,7 +36,7 @@ long long reg_state_elems(const RegPlan* r, long long B, int S);       // saved 
 int reg_run(RegPlan* r, int S, bool backward, void* ws, long long B, void* state, void* grad_theta,
             cudaStream_t s);
 
-// engine T (qcp_tile.cu): tiled statevector sweeps for 11 <= n <= 16 (float64: 10 <= n <= 16)
+// engine T (qcp_tile.cu): tiled statevector sweeps for 11 <= n <= 16
 struct TilePlan;
 int tile_supported(int n, int dtype);
 TilePlan* tile_create(int n, int enc, int dtype, const GateOp* host_ops, int n_ops, int n_theta,

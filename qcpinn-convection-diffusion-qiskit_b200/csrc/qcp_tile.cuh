@@ -1,5 +1,5 @@
 // qcpinn_b200 -- "engine T": tiled per-sample statevector path for 11 <= n <= 16 qubits
-// (float64: 10 <= n <= 16).  BASELINE config 4 (sim_circ_15, 16 qubits) runs here.
+// (both precisions).  BASELINE config 4 (sim_circ_15, 16 qubits) runs here.
 //
 // A 2^n statevector no longer fits a warp's registers, so each stream vector lives in an
 // HBM/L2-resident slab owned by the CTA (one collocation point per CTA at a time) and is processed
