@@ -10,6 +10,7 @@
 // Both run in complex128 whatever the plan dtype; they cost microseconds.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -175,6 +176,68 @@ __device__ void simulate_columns(double2* V, int n, const GateOp* ops, int n_ops
     apply_op(V, M, n, ops[g], theta, consts, false, table ? table + g : nullptr);
 }
 
+// ---------------------------------------------------------------------------------------------
+// warp-synchronous variant of the column sweeps (n <= 4): thread t owns entry (column t / M, row
+// t % M) of the M x M matrix in a register.  M <= 16 rows of a column sit in consecutive lanes of
+// one warp, so a gate's partner row is one __shfl_xor away: no shared memory and no block barrier
+// per gate.  Threads t >= M*M carry zeros (their partners are zeros too).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 shfl_xor2(double2 v, int mask) {
+  return make_double2(__shfl_xor_sync(0xffffffffu, v.x, mask), __shfl_xor_sync(0xffffffffu, v.y, mask));
+}
+
+struct WarpOp {   // a program op decoded once into bit positions
+  int kind, pt, pc, pa, pb, p;
+};
+
+__device__ __forceinline__ WarpOp decode_op(const GateOp op, int n) {
+  WarpOp w;
+  w.kind = op.kind; w.p = op.p;
+  const bool ctl = op.kind == QCP_GATE_CRX || op.kind == QCP_GATE_CRZ || op.kind == QCP_GATE_CNOT;
+  w.pt = n - 1 - (ctl ? op.b : op.a);
+  w.pc = ctl ? n - 1 - op.a : -1;
+  w.pa = n - 1 - op.a; w.pb = n - 1 - op.b;
+  return w;
+}
+
+// v <- U v (or U^dagger v) for the row k this thread owns; `o` = partner row of a one-qubit block
+__device__ __forceinline__ double2 warp_apply_1q(double2 v, double2 o, int k, const WarpOp& w, Mat2 u,
+                                                 bool dag) {
+  if (dag) u = dagger(u);
+  const int bit = (k >> w.pt) & 1;
+  const double2 nv = bit ? cadd(cmul(u.m[2], o), cmul(u.m[3], v)) : cadd(cmul(u.m[0], v), cmul(u.m[1], o));
+  return (w.pc < 0 || ((k >> w.pc) & 1)) ? nv : v;
+}
+
+__device__ __forceinline__ double2 warp_apply_u4(double2 v, int k, const WarpOp& w, const double2* consts,
+                                                 bool dag) {
+  const double2* U = consts + 16 * w.p;
+  const int idx = (((k >> w.pa) & 1) << 1) | ((k >> w.pb) & 1);
+  double2 acc = make_double2(0, 0);
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    const double2 x = d == 0 ? v : shfl_xor2(v, ((d >> 1) << w.pa) | ((d & 1) << w.pb));
+    const int j = idx ^ d;
+    acc = cadd(acc, cmul(dag ? cconj(U[j * 4 + idx]) : U[idx * 4 + j], x));
+  }
+  return acc;
+}
+
+__device__ __forceinline__ double2 warp_apply(double2 v, int k, const WarpOp& w, const Mat2& u,
+                                              const double2* consts, bool dag) {
+  if (w.kind == QCP_GATE_U4) return warp_apply_u4(v, k, w, consts, dag);
+  return warp_apply_1q(v, shfl_xor2(v, 1 << w.pt), k, w, u, dag);
+}
+
+// columns of the circuit unitary, one entry per thread (see above); ops / table in shared memory
+__device__ double2 warp_simulate(int n, const GateOp* ops, int n_ops, const double2* consts,
+                                 const Mat2* table) {
+  const int M = 1 << n, t = threadIdx.x, k = t % M;
+  double2 v = make_double2((t < M * M && t / M == k) ? 1.0 : 0.0, 0.0);
+  for (int g = 0; g < n_ops; ++g) v = warp_apply(v, k, decode_op(ops[g], n), table[g], consts, false);
+  return v;
+}
+
 __device__ __forceinline__ int trit_of(int s, int j, int n) {
   int d = 1;
   for (int t = 0; t < n - 1 - j; ++t) d *= 3;
@@ -188,18 +251,28 @@ __device__ __forceinline__ int trit_of(int s, int j, int n) {
 // (n <= 5), which removes the global-memory round trip of every one of the ~100 tiny phases.
 extern __shared__ __align__(16) unsigned char setup_smem[];
 
-template <typename T>
+// WARP: register / shuffle column sweep (host guarantees n <= 4, n_ops <= kMaxTableOps, use_smem)
+template <typename T, bool WARP>
 __global__ void __launch_bounds__(kSetupThreads)
 prepare_kernel(int n, int enc, const GateOp* ops, int n_ops, const T* theta, const double2* consts,
                double2* V, double2* O, double* C64, T* CT, int use_smem) {
   const int M = 1 << n;
   __shared__ Mat2 table_mem[kMaxTableOps];
+  __shared__ GateOp ops_s[WARP ? kMaxTableOps : 1];
   if (use_smem) {
     V = reinterpret_cast<double2*>(setup_smem);
     O = V + M * M;
   }
-  const Mat2* table = build_gate_table(table_mem, ops, n_ops, theta);
-  simulate_columns(V, n, ops, n_ops, theta, consts, table);
+  if constexpr (WARP) {
+    for (int g = threadIdx.x; g < n_ops; g += blockDim.x) ops_s[g] = ops[g];
+    const Mat2* table = build_gate_table(table_mem, ops, n_ops, theta);   // ends with a barrier
+    const double2 v = warp_simulate(n, ops_s, n_ops, consts, table);
+    if (threadIdx.x < M * M) V[threadIdx.x] = v;
+    __syncthreads();
+  } else {
+    const Mat2* table = build_gate_table(table_mem, ops, n_ops, theta);
+    simulate_columns(V, n, ops, n_ops, theta, consts, table);
+  }
 
   // O_i[b,a] = sum_k conj(V[k,b]) z_i(k) V[k,a]
   for (int it = threadIdx.x; it < n * M * M; it += blockDim.x) {
@@ -362,12 +435,15 @@ constexpr int kMaxThetaSmem = 256;   // circuit angles accumulated in shared mem
 __device__ __forceinline__ void atomicAdd_T(double* p, double v) { atomicAdd(p, v); }
 __device__ __forceinline__ void atomicAdd_T(float* p, double v) { atomicAdd(p, (float)v); }
 
-template <typename T>
+// WARP: as in prepare_kernel; additionally n_theta <= kMaxThetaSmem.  V and Lambda then stay in
+// registers through the reverse sweep (V is staged once in shared memory for the Lambda product).
+template <typename T, bool WARP>
 __global__ void __launch_bounds__(kSetupThreads)
 theta_grad_kernel(int n, int enc, const GateOp* ops, int n_ops, const T* theta, int n_theta,
                   const double2* consts, const double* Cbar, double2* V, double2* R, double2* Lam,
                   T* gtheta, int use_smem) {
   __shared__ Mat2 table_mem[kMaxTableOps];
+  __shared__ GateOp ops_s[WARP ? kMaxTableOps : 1];
   __shared__ double gacc[kSetupThreads / 32][kMaxThetaSmem];   // one row per warp: no atomics
   const int M = 1 << n;
   if (use_smem) {
@@ -383,8 +459,18 @@ theta_grad_kernel(int n, int enc, const GateOp* ops, int n_ops, const T* theta, 
       gtheta[p] = (T)0;
     }
   }
-  const Mat2* table = build_gate_table(table_mem, ops, n_ops, theta);
-  simulate_columns(V, n, ops, n_ops, theta, consts, table);
+  double2 v = make_double2(0, 0), lam = make_double2(0, 0);   // WARP: this thread's entries
+  const Mat2* table;
+  if constexpr (WARP) {
+    for (int g = threadIdx.x; g < n_ops; g += blockDim.x) ops_s[g] = ops[g];
+    table = build_gate_table(table_mem, ops, n_ops, theta);   // ends with a barrier
+    v = warp_simulate(n, ops_s, n_ops, consts, table);
+    if (threadIdx.x < M * M) V[threadIdx.x] = v;
+    __syncthreads();
+  } else {
+    table = build_gate_table(table_mem, ops, n_ops, theta);
+    simulate_columns(V, n, ops, n_ops, theta, consts, table);
+  }
   // stage C-bar in shared memory: the R loop below reads it with data-dependent indices
   __shared__ double cbar_s[kMaxCbarSmem];
   const int n_cbar = num_features(n, enc) * n;
@@ -441,7 +527,40 @@ theta_grad_kernel(int n, int enc, const GateOp* ops, int n_ops, const T* theta, 
       for (int b = 0; b < M; ++b) t = cadd(t, cmul(V[b * M + k], Ri[b * M + a]));
       acc.x += sgn * t.x; acc.y += sgn * t.y;
     }
-    Lam[it] = acc;
+    if constexpr (WARP) lam = acc;   // it == threadIdx.x: exactly the entry this thread owns
+    else Lam[it] = acc;
+  }
+  if constexpr (WARP) {
+    const int k = threadIdx.x % M, warp = threadIdx.x >> 5;
+    for (int g = n_ops - 1; g >= 0; --g) {
+      const WarpOp w = decode_op(ops_s[g], n);
+      if (w.kind == QCP_GATE_U4) {
+        v = warp_apply_u4(v, k, w, consts, true);
+        lam = warp_apply_u4(lam, k, w, consts, true);
+        continue;
+      }
+      const double2 ov = shfl_xor2(v, 1 << w.pt);
+      if (w.p >= 0) {
+        // dL/dtheta = Im sum_cols <lambda| H |psi>, both taken AFTER the gate
+        const int bit = (k >> w.pt) & 1;
+        double2 hpsi;
+        if (w.kind == QCP_GATE_RX || w.kind == QCP_GATE_CRX) hpsi = ov;
+        else if (w.kind == QCP_GATE_RY) hpsi = bit ? make_double2(-ov.y, ov.x) : make_double2(ov.y, -ov.x);
+        else hpsi = bit ? make_double2(-v.x, -v.y) : v;
+        double part = (w.pc < 0 || ((k >> w.pc) & 1)) ? lam.x * hpsi.y - lam.y * hpsi.x : 0.0;
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if ((threadIdx.x & 31) == 0) gacc[warp][w.p] += part;   // this warp's own row
+      }
+      v = warp_apply_1q(v, ov, k, w, table[g], true);
+      lam = warp_apply_1q(lam, shfl_xor2(lam, 1 << w.pt), k, w, table[g], true);
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < n_theta; p += blockDim.x) {
+      double s = 0.0;
+      for (int w = 0; w < kSetupThreads / 32; ++w) s += gacc[w][p];   // fixed order: deterministic
+      gtheta[p] = (T)s;
+    }
+    return;
   }
   __syncthreads();
 
@@ -586,6 +705,42 @@ static int opt_in_smem(K kernel, size_t bytes) {
   }
   return 0;
 }
+
+// the register / shuffle setup kernels need the whole M x M matrix in one CTA's threads
+static bool warp_setup_ok(const qcp_plan* p, size_t smem_bytes) {
+  static const bool legacy = [] {
+    const char* e = getenv("QCP_SETUP");
+    return e && !strcmp(e, "legacy");
+  }();
+  return !legacy && smem_bytes > 0 && p->M * p->M <= kSetupThreads && p->n_ops <= kMaxTableOps;
+}
+
+template <typename T, bool WARP>
+static int launch_prepare(qcp_plan* p, const void* theta, size_t sm, cudaStream_t s) {
+  if (opt_in_smem(&prepare_kernel<T, WARP>, sm)) {
+    if (WARP) return launch_prepare<T, false>(p, theta, sm, s);
+    sm = 0;
+  }
+  prepare_kernel<T, WARP><<<1, kSetupThreads, sm, s>>>(p->n, p->enc, p->d_ops, p->n_ops,
+      static_cast<const T*>(theta), p->d_consts, p->d_V, p->d_O, p->d_C64, static_cast<T*>(p->d_C),
+      sm != 0);
+  QCP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T, bool WARP>
+static int launch_theta_grad(qcp_plan* p, const void* theta, void* gtheta, size_t sm, cudaStream_t s) {
+  if (opt_in_smem(&theta_grad_kernel<T, WARP>, sm)) {
+    if (WARP) return launch_theta_grad<T, false>(p, theta, gtheta, sm, s);
+    sm = 0;
+  }
+  theta_grad_kernel<T, WARP><<<1, kSetupThreads, sm, s>>>(p->n, p->enc, p->d_ops, p->n_ops,
+      static_cast<const T*>(theta), p->n_theta, p->d_consts, p->d_Cbar, p->d_V, p->d_O, p->d_Lam,
+      static_cast<T*>(gtheta), sm != 0);
+  QCP_CUDA(cudaGetLastError());
+  return 0;
+}
+
 
 static int ensure_partials(qcp_plan* p, size_t elems) {
   if (elems <= p->partials_elems) return 0;
@@ -747,19 +902,12 @@ int qcp_prepare(qcp_plan_t* p, const void* theta, void* stream) {
     p->prepared = true;
     return 0;
   }
-  size_t sm = setup_smem_bytes(p, false);
-  if (p->dtype == QCP_F64) {
-    if (opt_in_smem(&prepare_kernel<double>, sm)) sm = 0;
-    prepare_kernel<double><<<1, kSetupThreads, sm, s>>>(p->n, p->enc, p->d_ops, p->n_ops,
-        static_cast<const double*>(theta), p->d_consts, p->d_V, p->d_O, p->d_C64,
-        static_cast<double*>(p->d_C), sm != 0);
-  } else {
-    if (opt_in_smem(&prepare_kernel<float>, sm)) sm = 0;
-    prepare_kernel<float><<<1, kSetupThreads, sm, s>>>(p->n, p->enc, p->d_ops, p->n_ops,
-        static_cast<const float*>(theta), p->d_consts, p->d_V, p->d_O, p->d_C64,
-        static_cast<float*>(p->d_C), sm != 0);
-  }
-  QCP_CUDA(cudaGetLastError());
+  const size_t sm = setup_smem_bytes(p, false);
+  const bool warp = warp_setup_ok(p, sm);
+  const int rc = p->dtype == QCP_F64
+      ? (warp ? launch_prepare<double, true>(p, theta, sm, s) : launch_prepare<double, false>(p, theta, sm, s))
+      : (warp ? launch_prepare<float, true>(p, theta, sm, s) : launch_prepare<float, false>(p, theta, sm, s));
+  if (rc) return 1;
   p->prepared = true;
   return 0;
 }
@@ -906,20 +1054,13 @@ int qcp_layer_forward(qcp_plan_t* p, const void* z, long long B, void* q, void* 
 }
 
 static int run_theta_grad(qcp_plan* p, const void* theta, void* gtheta, cudaStream_t s) {
-  size_t sm = setup_smem_bytes(p, true);
-  if (p->dtype == QCP_F64) {
-    if (opt_in_smem(&theta_grad_kernel<double>, sm)) sm = 0;
-    theta_grad_kernel<double><<<1, kSetupThreads, sm, s>>>(p->n, p->enc, p->d_ops, p->n_ops,
-        static_cast<const double*>(theta), p->n_theta, p->d_consts, p->d_Cbar, p->d_V, p->d_O,
-        p->d_Lam, static_cast<double*>(gtheta), sm != 0);
-  } else {
-    if (opt_in_smem(&theta_grad_kernel<float>, sm)) sm = 0;
-    theta_grad_kernel<float><<<1, kSetupThreads, sm, s>>>(p->n, p->enc, p->d_ops, p->n_ops,
-        static_cast<const float*>(theta), p->n_theta, p->d_consts, p->d_Cbar, p->d_V, p->d_O,
-        p->d_Lam, static_cast<float*>(gtheta), sm != 0);
-  }
-  QCP_CUDA(cudaGetLastError());
-  return 0;
+  const size_t sm = setup_smem_bytes(p, true);
+  const bool warp = warp_setup_ok(p, sm) && p->n_theta <= kMaxThetaSmem;
+  return p->dtype == QCP_F64
+      ? (warp ? launch_theta_grad<double, true>(p, theta, gtheta, sm, s)
+              : launch_theta_grad<double, false>(p, theta, gtheta, sm, s))
+      : (warp ? launch_theta_grad<float, true>(p, theta, gtheta, sm, s)
+              : launch_theta_grad<float, false>(p, theta, gtheta, sm, s));
 }
 
 int qcp_layer_backward(qcp_plan_t* p, const void* theta, const void* z, const void* grad_q,
