@@ -238,6 +238,11 @@ class TrainStep:
         self.last_terms = outs
         return self._host_update(outs[0])
 
+    def steady(self, host_batches=False):
+        """True once a call does only steady-state work: no eager start-up steps and no CUDA-graph
+        capture left for this kind of batch (device-sampled or host-fed)."""
+        return not self.use_graph or ("host" if host_batches else "device") in self._graphs
+
     def __call__(self, batch=None):
         if self.use_graph and self._eager_calls >= self.EAGER_STEPS_BEFORE_CAPTURE:
             return self._graph_step(batch)
