@@ -292,7 +292,9 @@ def _flat_grad_views(plan: Plan, mlp, theta):
 
 def solver_backward_many(plan: Plan, items, mlp, theta):
     """Adjoint kernels of several model calls, ONE partial reduction and ONE theta-gradient kernel.
-    ``items`` = [(X, grad_u, grad_r, mode, coeffs, save, need_gx), ...].  Returns (views, [gx])."""
+    ``items`` = [(X, grad_u, grad_r, mode, coeffs, save, need_gx[, stream]), ...]; an item's adjoint
+    kernels run on its ``stream`` (a torch stream already ordered after the producers of its
+    inputs) and the reduction waits for it.  Returns (views, [gx])."""
     lib = plan.lib
     flat, views = _flat_grad_views(plan, mlp, theta)
     m = plan._mlp(mlp)
@@ -301,7 +303,11 @@ def solver_backward_many(plan: Plan, items, mlp, theta):
     with torch.cuda.device(plan.device):
         stream = plan._stream()
         _lib.check(lib.qcp_solver_backward_begin(plan._handle), "qcp_solver_backward_begin")
-        for X, gu, gr, mode, coeffs, save, need_gx in items:
+        main = torch.cuda.current_stream(plan.device)
+        joins = []
+        for X, gu, gr, mode, coeffs, save, need_gx, *rest in items:
+            side = rest[0] if rest and rest[0] is not None and rest[0] != main else None
+            item_stream = ctypes.c_void_p(side.cuda_stream) if side is not None else stream
             gx = torch.empty_like(X) if need_gx else None
             gxs.append(gx)
             c = (ctypes.c_double * 5)(*coeffs) if coeffs is not None else None
@@ -310,10 +316,14 @@ def solver_backward_many(plan: Plan, items, mlp, theta):
                 ctypes.c_void_p(gu.data_ptr() if gu is not None else None),
                 ctypes.c_void_p(gr.data_ptr() if gr is not None else None),
                 X.shape[0], mode, c, ctypes.c_void_p(save.data_ptr() if save is not None else None),
-                ctypes.c_void_p(gx.data_ptr() if gx is not None else None), stream)
+                ctypes.c_void_p(gx.data_ptr() if gx is not None else None), item_stream)
             _lib.check(rc, "qcp_solver_backward_add")
+            if side is not None:
+                joins.append(side)
             if X.shape[0]:
                 _count(3 if save is not None else 1)
+        for side in joins:
+            main.wait_stream(side)
         rc = lib.qcp_solver_backward_finish(
             plan._handle, ctypes.c_void_p(theta.data_ptr()), ctypes.byref(g),
             ctypes.c_void_p(views[8].data_ptr()), stream)

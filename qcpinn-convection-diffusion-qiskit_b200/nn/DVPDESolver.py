@@ -261,17 +261,25 @@ class DVPDESolver(nn.Module):
         X_r = X_res.detach().to(plan.io_dtype).contiguous()
         ws_v = plan.workspace(nb + ni, F.MODE_VALUE)
         ws_r = plan.workspace(nr, F.MODE_RESIDUAL)
-        u_v, _, _ = plan.solver_forward(X_val, mt, F.MODE_VALUE, save=ws_v)
-        _, r_r, _ = plan.solver_forward(X_r, mt, F.MODE_RESIDUAL, coeffs, save=ws_r)
         terms = torch.zeros(3, dtype=torch.float64, device=dev)            # r, bc, ic
-        gu_v = torch.empty_like(u_v)
+        t_bc, t_ic = u_bcs.detach().reshape(-1).contiguous(), u_ics.detach().reshape(-1).contiguous()
+        t_r = r_res.detach().reshape(-1).contiguous()
+        # the IC/BC chain and the residual chain are independent until the partial reduction: run
+        # the (small) IC/BC kernels on a side stream so they fill the tails of the residual kernels
+        main = torch.cuda.current_stream(dev)
+        side = self._value_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            u_v, _, _ = plan.solver_forward(X_val, mt, F.MODE_VALUE, save=ws_v)
+            gu_v = torch.empty_like(u_v)
+            F.mse_seed(plan, u_v[:nb], t_bc, w_bc, gu_v[:nb], terms[1:2])
+            F.mse_seed(plan, u_v[nb:], t_ic, w_ic, gu_v[nb:], terms[2:3])
+        _, r_r, _ = plan.solver_forward(X_r, mt, F.MODE_RESIDUAL, coeffs, save=ws_r)
         gr = torch.empty_like(r_r)
-        F.mse_seed(plan, u_v[:nb], u_bcs.detach().reshape(-1).contiguous(), w_bc, gu_v[:nb], terms[1:2])
-        F.mse_seed(plan, u_v[nb:], u_ics.detach().reshape(-1).contiguous(), w_ic, gu_v[nb:], terms[2:3])
-        F.mse_seed(plan, r_r, r_res.detach().reshape(-1).contiguous(), w_r, gr, terms[0:1])
+        F.mse_seed(plan, r_r, t_r, w_r, gr, terms[0:1])
         views, _ = F.solver_backward_many(
-            plan, [(X_val, gu_v, None, F.MODE_VALUE, None, ws_v, False),
-                   (X_r, None, gr, F.MODE_RESIDUAL, coeffs, ws_r, False)], mt, tt)
+            plan, [(X_val, gu_v, None, F.MODE_VALUE, None, ws_v, False, side),
+                   (X_r, None, gr, F.MODE_RESIDUAL, coeffs, ws_r, False, None)], mt, tt)
         flat, numel = self.flat_grad_buffer()
         flat[:numel].copy_(views[0]._base)                                   # one cast kernel
         wvec = getattr(self, "_loss_weights", None)
@@ -281,6 +289,16 @@ class DVPDESolver(nn.Module):
         flat[numel + 1:numel + 4].copy_(terms)
         flat[numel:numel + 1].copy_((terms * wvec).sum().reshape(1))
         return flat, numel
+
+    def _value_stream(self, dev):
+        """Side stream of the IC/BC chain in :meth:`train_step_grads` (the current stream itself when
+        ``QCP_OVERLAP=0``)."""
+        if os.environ.get("QCP_OVERLAP", "1") == "0":
+            return torch.cuda.current_stream(dev)
+        streams = self.__dict__.setdefault("_value_streams", {})
+        if dev not in streams:
+            streams[dev] = torch.cuda.Stream(device=dev)
+        return streams[dev]
 
     def taylor_streams(self, X: torch.Tensor):
         """No-grad evaluation helper: (B,6) = u, u_t, u_x, u_y, u_xx, u_yy."""
