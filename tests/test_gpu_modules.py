@@ -346,6 +346,26 @@ def test_fused_step_equals_autograd_route(tmp_path, dtype):
         assert rel_err(pf, pa) < 1e-4
 
 
+def test_side_stream_overlap_is_bit_identical(tmp_path, monkeypatch):
+    """train_step_grads runs the IC/BC chain on a side stream (joined before the partial reduction):
+    same bits as the serialised order (QCP_OVERLAP=0), eagerly and under repeated calls."""
+    from qcpinn_b200.trainer.diffusion_train import DIFFUSION_COEFFS
+
+    batches = osolver.make_batches(3000, seed=5)
+    batch = tuple(batches[k].to(DEV) for k in ("X_ic", "u_ic", "X_bc", "u_bc", "X_res", "r_res"))
+    model = _model(tmp_path)
+    outs = {}
+    for mode in ("0", "1", "1", "0"):
+        monkeypatch.setenv("QCP_OVERLAP", mode)
+        flat, numel = model.train_step_grads(batch, DIFFUSION_COEFFS)
+        torch.cuda.synchronize()
+        outs.setdefault(mode, []).append(flat[:numel + 4].clone())
+    ref = outs["0"][0]
+    assert torch.isfinite(ref).all() and ref.abs().sum() > 0
+    for got in outs["0"][1:] + outs["1"]:
+        assert torch.equal(got, ref)
+
+
 def _two_input_model(tmp_path, dtype):
     torch.manual_seed(3)
     args = dict(ARGS, classic_network=[2, 50, 1], dtype=dtype)
