@@ -92,3 +92,32 @@ def features_amplitude(f):
     nrm = (f ** 2).sum(axis=1)
     cols = [f[:, a] * f[:, b] / nrm for a in range(n) for b in range(a, n)]
     return np.stack(cols, axis=1)
+
+
+def feature_tensor_angle_fast(O, n):
+    """Same C as :func:`feature_matrix_angle`, by n axis contractions instead of 3^n Kronecker
+    products: view O_i as a (row bits, column bits) tensor and contract every qubit's (row, column)
+    pair with K[t, r, c] = P_t[c, r] / 2 (so that sum_{r,c} K[t,r,c] O[r,c] = tr(P_t O) / 2).
+    O(n 4^n) work per observable -- the transform a device prepare step would run for n = 10
+    (DESIGN.md "what comes next", item 1).  Returns (n, 3, ..., 3) with one axis per qubit."""
+    K = np.stack([_PAULI[t].T / 2.0 for t in range(3)])            # [t, r, c]
+    out = []
+    for i in range(n):
+        T = np.asarray(O[i]).reshape((2,) * (2 * n))               # axes: r_0..r_{n-1}, c_0..c_{n-1}
+        for j in range(n):
+            # qubit j's row axis is always the first remaining one, its column axis n - j later
+            T = np.tensordot(K, np.moveaxis(T, [0, n - j], [0, 1]), axes=([1, 2], [0, 1]))
+            T = np.moveaxis(T, 0, -1)                               # finished trit axes go last
+        out.append(np.real(T))
+    return np.stack(out)
+
+
+def factored_contraction(C, z, n_a):
+    """<Z_i>(z) = phiA(z_A)^T C_i phiB(z_B) with the features split after the first ``n_a`` qubits:
+    C (n, 3, ..., 3) -> (n, 3^n_a, 3^(n-n_a)); the (B x 3^nB) x (3^nB x n 3^nA) product is the GEMM
+    of the planned tensor-core engine, the phiA dot its epilogue."""
+    n = C.shape[0]
+    Cm = C.reshape(n, 3 ** n_a, 3 ** (n - n_a))
+    pa, pb = features_angle(z[:, :n_a]), features_angle(z[:, n_a:])
+    T = np.einsum("pb,iab->pia", pb, Cm)                           # the GEMM
+    return np.einsum("pa,pia->ip", pa, T)                          # the epilogue

@@ -38,6 +38,27 @@ def test_program_matches_oracle_for_both_encodings(ansatz, n):
             assert np.abs(got - want).max() < 1e-12
 
 
+@pytest.mark.parametrize("ansatz,n,layers,n_a", [("cross_mesh", 6, 1, 3), ("layered", 5, 2, 3),
+                                                  ("sim_circ_15", 7, 1, 4), ("cascade", 6, 1, 3)])
+def test_factored_feature_contraction_matches_oracle(ansatz, n, layers, n_a):
+    """Specification of the planned n > 4 feature engine: the Pauli
+    coefficients from n axis contractions equal the Kronecker definition, and
+    <Z_i>(z) = phiA^T C_i phiB (one GEMM over the B-half features + a dot with the A-half) equals
+    the gate-by-gate statevector oracle."""
+    g = torch.Generator().manual_seed(10 * n + layers)
+    prog = P.compile_program(ansatz, n, layers, 1)
+    th = torch.randn(layers, prog.params_per_layer, generator=g, dtype=torch.float64)
+    O = fm.observables(fm.program_unitary(prog, th), n)
+    C = fm.feature_tensor_angle_fast(O, n)
+    assert C.shape == (n,) + (3,) * n
+    if n <= 5:
+        assert np.abs(C.reshape(n, -1) - fm.feature_matrix_angle(O, n)).max() < 1e-13
+    z = torch.randn(7, n, generator=g, dtype=torch.float64)
+    want = oc.quantum_layer(z, th, ansatz, n, "angle", oc.haar_for(1, n)).numpy()
+    got = fm.factored_contraction(C, z.numpy(), n_a)
+    assert np.abs(got - want).max() < 1e-12
+
+
 def test_gate_table_layout():
     prog = P.compile_program("cascade", 4, 1, 1)
     ops = prog.ops.tolist()
