@@ -150,9 +150,61 @@ static bool tile_diag_tables() {
   return !(env && env[0] == '0');
 }
 
-static void plan_sweeps(const GateOp* ops_in, int n_ops_in, int n, int LB, std::vector<ROp>& rops,
-                        std::vector<Sweep>& sweeps, int* final_bit, std::vector<rg::DiagGate>& dgs,
-                        std::vector<DiagOff>& doffs, int* n_blk) {
+// Dependency DAG of a gate list.  Two gates must keep their order iff they share a qubit on which at
+// least one of them is not diagonal: controls, RZ / CRZ targets and diagonal-block tables are
+// "Z-type" uses of a qubit and commute with each other.  prio[g] = earliest dependent gate.
+struct GateDag {
+  std::vector<std::vector<int>> succ;
+  std::vector<int> npred, prio;
+};
+
+static GateDag build_dag(const GateOp* ops, int n_ops, int n) {
+  GateDag d;
+  d.succ.resize(n_ops);
+  d.npred.assign(n_ops, 0);
+  d.prio.assign(n_ops, 1 << 30);
+  std::vector<int> last_x(n, -1);
+  std::vector<std::vector<int>> z_since(n);
+  for (int j = 0; j < n_ops; ++j) {
+    const GateOp& g = ops[j];
+    int q[kMaxQubitsSv];
+    bool x[kMaxQubitsSv];
+    int nu = 0;
+    auto use = [&](int qq, bool xx) { q[nu] = qq; x[nu++] = xx; };
+    switch (g.kind) {
+      case kDiagMarker: for (int qq = 0; qq < n; ++qq) use(qq, false); break;
+      case QCP_GATE_RX: case QCP_GATE_RY: case QCP_GATE_H: use(g.a, true); break;
+      case QCP_GATE_RZ: use(g.a, false); break;
+      case QCP_GATE_CRX: case QCP_GATE_CNOT: use(g.a, false); use(g.b, true); break;
+      case QCP_GATE_CRZ: use(g.a, false); use(g.b, false); break;
+      default: use(g.a, true); use(g.b, true); break;
+    }
+    std::vector<int> pred;
+    for (int u = 0; u < nu; ++u) {
+      if (x[u] && !z_since[q[u]].empty()) pred.insert(pred.end(), z_since[q[u]].begin(), z_since[q[u]].end());
+      else if (last_x[q[u]] >= 0) pred.push_back(last_x[q[u]]);
+      if (x[u]) { last_x[q[u]] = j; z_since[q[u]].clear(); }
+      else z_since[q[u]].push_back(j);
+    }
+    std::sort(pred.begin(), pred.end());
+    pred.erase(std::unique(pred.begin(), pred.end()), pred.end());
+    for (int i : pred) {
+      d.succ[i].push_back(j);
+      d.npred[j]++;
+      d.prio[i] = std::min(d.prio[i], j);
+    }
+  }
+  return d;
+}
+
+// reorder = false: sweeps are maximal runs of the gate list in program order.
+// reorder = true: every sweep takes all gates the dependency DAG allows on its tile qubits, and new
+// qubits join the tile in the order of the earliest blocked gate (a list scheduler); e.g. the
+// RY / CNOT-chain / RY / CNOT-ring layers of sim_circ_15 run as a wavefront over the qubits
+// instead of layer by layer.
+static void plan_sweeps(const GateOp* ops_in, int n_ops_in, int n, int LB, bool reorder,
+                        std::vector<ROp>& rops, std::vector<Sweep>& sweeps, int* final_bit,
+                        std::vector<rg::DiagGate>& dgs, std::vector<DiagOff>& doffs, int* n_blk) {
   const int TB = LB + 5, NA = 1 << LB;
   std::vector<GateOp> vops;
   std::vector<int> orig;
@@ -161,30 +213,93 @@ static void plan_sweeps(const GateOp* ops_in, int n_ops_in, int n, int LB, std::
   const int n_ops = (int)vops.size();
   std::vector<int> mbit(n), qatm(n);               // memory bit of qubit q / qubit at memory bit b
   for (int q = 0; q < n; ++q) { mbit[q] = n - 1 - q; qatm[n - 1 - q] = q; }
-  int g = 0;
-  while (g < n_ops) {
-    // ---- tile qubits of this sweep: the two on memory bits 0 / 1 are always inside ------------------
-    std::vector<int> seed = {qatm[0], qatm[1]}, Q;
-    const int g_end = grow_tile(ops, n_ops, g, TB, seed, Q);
-    // pad to TB qubits with the ones used next (keeps them handy; the tile always has TB bits)
-    for (int gg = g_end; gg < n_ops && (int)Q.size() < TB; ++gg) {
+  GateDag dag;
+  std::vector<int> left;
+  std::vector<char> done(n_ops, 0);
+  if (reorder) {
+    dag = build_dag(ops, n_ops, n);
+    left = dag.npred;
+  }
+  auto in_set = [](const std::vector<int>& v, int q) { return std::find(v.begin(), v.end(), q) != v.end(); };
+  // earliest unscheduled gate that needs qubit q inside a tile
+  auto next_need = [&](int q) {
+    for (int j = 0; j < n_ops; ++j) {
+      if (done[j]) continue;
       int t[2], nt;
-      gate_targets(ops[gg], t, &nt);
-      for (int k = 0; k < nt && (int)Q.size() < TB; ++k)
-        if (std::find(Q.begin(), Q.end(), t[k]) == Q.end()) Q.push_back(t[k]);
+      gate_targets(ops[j], t, &nt);
+      for (int k = 0; k < nt; ++k)
+        if (t[k] == q) return j;
     }
-    for (int q = 0; q < n && (int)Q.size() < TB; ++q)
-      if (std::find(Q.begin(), Q.end(), q) == Q.end()) Q.push_back(q);
-    // ---- seeds of the NEXT sweep: two of this tile's qubits, preferably ones it needs anyway -----------
-    std::vector<int> next_seed;
-    if (g_end < n_ops) {
-      std::vector<int> Qn;
-      grow_tile(ops, n_ops, g_end, TB - 2, {}, Qn);
-      for (int q : Qn)
-        if ((int)next_seed.size() < 2 && std::find(Q.begin(), Q.end(), q) != Q.end()) next_seed.push_back(q);
+    return 1 << 30;
+  };
+  int g = 0, n_done = 0;
+  while (n_done < n_ops) {
+    // ---- tile qubits of this sweep: the two on memory bits 0 / 1 are always inside ------------------
+    std::vector<int> seed = {qatm[0], qatm[1]}, Q, run, next_seed;
+    if (!reorder) {
+      const int g_end = grow_tile(ops, n_ops, g, TB, seed, Q);
+      for (int gg = g; gg < g_end; ++gg) run.push_back(gg);
+      // pad to TB qubits with the ones used next (keeps them handy; the tile always has TB bits)
+      for (int gg = g_end; gg < n_ops && (int)Q.size() < TB; ++gg) {
+        int t[2], nt;
+        gate_targets(ops[gg], t, &nt);
+        for (int k = 0; k < nt && (int)Q.size() < TB; ++k)
+          if (!in_set(Q, t[k])) Q.push_back(t[k]);
+      }
+      for (int q = 0; q < n && (int)Q.size() < TB; ++q)
+        if (!in_set(Q, q)) Q.push_back(q);
+      // ---- seeds of the NEXT sweep: two of this tile's qubits, preferably ones it needs anyway --------
+      if (g_end < n_ops) {
+        std::vector<int> Qn;
+        grow_tile(ops, n_ops, g_end, TB - 2, {}, Qn);
+        for (int q : Qn)
+          if ((int)next_seed.size() < 2 && in_set(Q, q)) next_seed.push_back(q);
+      }
+      g = g_end;
+    } else {
+      Q = seed;
+      auto schedule = [&](int j) {
+        done[j] = 1;
+        run.push_back(j);
+        for (int s2 : dag.succ[j]) --left[s2];
+      };
+      auto missing = [&](int j) {
+        int t[2], nt, add = 0;
+        gate_targets(ops[j], t, &nt);
+        for (int k = 0; k < nt; ++k)
+          if (!in_set(Q, t[k]) && (k == 0 || t[k] != t[0])) ++add;
+        return add;
+      };
+      for (;;) {
+        bool any = false;
+        for (int j = 0; j < n_ops; ++j)            // everything that is ready on the current tile
+          if (!done[j] && left[j] == 0 && missing(j) == 0) { schedule(j); any = true; }
+        if (any) continue;
+        int best = -1;
+        for (int j = 0; j < n_ops; ++j) {
+          if (done[j] || left[j] != 0 || (int)Q.size() + missing(j) > TB) continue;
+          if (best < 0 || dag.prio[j] < dag.prio[best]) best = j;
+        }
+        if (best < 0) break;
+        int t[2], nt;
+        gate_targets(ops[best], t, &nt);
+        for (int k = 0; k < nt; ++k)
+          if (!in_set(Q, t[k])) Q.push_back(t[k]);
+        schedule(best);
+      }
+      // pad the tile and pick the next seeds by the earliest pending need
+      std::vector<std::pair<int, int>> need;
+      for (int q = 0; q < n; ++q) need.push_back({next_need(q), q});
+      std::sort(need.begin(), need.end());
+      for (const auto& nq : need)
+        if ((int)Q.size() < TB && !in_set(Q, nq.second)) Q.push_back(nq.second);
+      for (const auto& nq : need)
+        if ((int)next_seed.size() < 2 && nq.first < (1 << 30) && in_set(Q, nq.second)) next_seed.push_back(nq.second);
     }
+    n_done += (int)run.size();
+    const int g_end = (int)run.size();              // gate loops below index `run`
     for (int k = (int)Q.size() - 1; k >= 0 && (int)next_seed.size() < 2; --k)
-      if (std::find(next_seed.begin(), next_seed.end(), Q[k]) == next_seed.end()) next_seed.push_back(Q[k]);
+      if (!in_set(next_seed, Q[k])) next_seed.push_back(Q[k]);
 
     // ---- load mapping: tile position j <-> memory bit ---------------------------------------------------
     LayoutTracker lt;
@@ -223,7 +338,7 @@ static void plan_sweeps(const GateOp* ops_in, int n_ops_in, int n, int LB, std::
 
     // ---- gates of the sweep in tile positions (engine R style: dense targets on local positions) ------
     sw.r0 = (int)rops.size();
-    auto targets = [&](int gg, int* t, int* nt) { gate_targets(ops[gg], t, nt); };
+    auto targets = [&](int gi, int* t, int* nt) { gate_targets(ops[run[gi]], t, nt); };
     auto make_local = [&](int q, int g_cur) { lt.make_local(q, g_cur, g_end, targets); };
     auto move_to = [&](int q, int X) { lt.move_to(q, X); };
     auto pair_mask = [&](int pt, int pc) {
@@ -235,7 +350,8 @@ static void plan_sweeps(const GateOp* ops_in, int n_ops_in, int n, int LB, std::
       }
       return m;
     };
-    for (int gg = g; gg < g_end; ++gg) {
+    for (int gi = 0; gi < g_end; ++gi) {
+      const int gg = run[gi];
       const GateOp op = ops[gg];
       switch (op.kind) {
         case kDiagMarker: {
@@ -255,20 +371,20 @@ static void plan_sweeps(const GateOp* ops_in, int n_ops_in, int n, int LB, std::
           break;
         }
         case QCP_GATE_RX: case QCP_GATE_RY: case QCP_GATE_RZ: case QCP_GATE_H: {
-          make_local(op.a, gg);
+          make_local(op.a, gi);
           const int type = op.kind == QCP_GATE_RX ? T_X : (op.kind == QCP_GATE_RZ ? T_Z : T_R);
           rops.push_back({R_L1, pos[op.a], -1, type, orig[gg], op.kind == QCP_GATE_H ? -1 : op.p, 0, 0});
           break;
         }
         case QCP_GATE_CRX: case QCP_GATE_CRZ: {
-          make_local(op.b, gg);
+          make_local(op.b, gi);
           const int pc = ctl_pos(op.a);
           rops.push_back({R_L1, pos[op.b], pc, op.kind == QCP_GATE_CRX ? T_X : T_Z, orig[gg], op.p,
                           pair_mask(pos[op.b], pc), 0});
           break;
         }
         case QCP_GATE_CNOT: {
-          make_local(op.b, gg);
+          make_local(op.b, gi);
           const int pc = ctl_pos(op.a);
           rops.push_back({R_CX, pos[op.b], pc, 0, orig[gg], -1, pair_mask(pos[op.b], pc), 0});
           break;
@@ -312,9 +428,30 @@ static void plan_sweeps(const GateOp* ops_in, int n_ops_in, int n, int LB, std::
     }
     for (int j = 0; j < TB; ++j) { mbit[qat[j]] = stbit[j]; qatm[stbit[j]] = qat[j]; }
     sweeps.push_back(sw);
-    g = g_end;
   }
   for (int q = 0; q < n; ++q) final_bit[q] = mbit[q];
+}
+
+// both gate orders are planned; the one with fewer sweeps (HBM round trips) wins, ties keep the
+// program order.  QCP_TILE_ORDER=program / dag forces one.
+static void plan_best(const GateOp* ops, int n_ops, int n, int LB, std::vector<ROp>& rops,
+                      std::vector<Sweep>& sweeps, int* final_bit, std::vector<rg::DiagGate>& dgs,
+                      std::vector<DiagOff>& doffs, int* n_blk) {
+  const char* env = std::getenv("QCP_TILE_ORDER");
+  const bool force_program = env && env[0] == 'p', force_dag = env && env[0] == 'd';
+  std::vector<ROp> r2;
+  std::vector<Sweep> s2;
+  std::vector<rg::DiagGate> g2;
+  std::vector<DiagOff> d2;
+  int fb2[kMaxQubitsSv], nb2 = 0;
+  if (!force_dag) plan_sweeps(ops, n_ops, n, LB, false, rops, sweeps, final_bit, dgs, doffs, n_blk);
+  if (force_program) return;
+  plan_sweeps(ops, n_ops, n, LB, true, r2, s2, fb2, g2, d2, &nb2);
+  if (force_dag || s2.size() < sweeps.size()) {
+    rops.swap(r2); sweeps.swap(s2); dgs.swap(g2); doffs.swap(d2);
+    for (int q = 0; q < n; ++q) final_bit[q] = fb2[q];
+    *n_blk = nb2;
+  }
 }
 
 // host-only entry for qcp_plancheck.cu
@@ -322,7 +459,7 @@ void tile_plan_host(const GateOp* ops, int n_ops, int n, int LB, std::vector<ROp
                     std::vector<Sweep>& sweeps, int* final_bit, std::vector<rg::DiagGate>& dgs,
                     std::vector<DiagOff>& doffs) {
   int n_blk = 0;
-  plan_sweeps(ops, n_ops, n, LB, rops, sweeps, final_bit, dgs, doffs, &n_blk);
+  plan_best(ops, n_ops, n, LB, rops, sweeps, final_bit, dgs, doffs, &n_blk);
 }
 
 TilePlan* tile_create(int n, int enc, int dtype, const GateOp* host_ops, int n_ops, int n_theta,
@@ -339,7 +476,7 @@ TilePlan* tile_create(int n, int enc, int dtype, const GateOp* host_ops, int n_o
   std::vector<Sweep> sweeps;
   std::vector<rg::DiagGate> dgs;
   std::vector<DiagOff> doffs;
-  plan_sweeps(host_ops, n_ops, n, r->LB, rops, sweeps, r->final_bit, dgs, doffs, &r->n_blk);
+  plan_best(host_ops, n_ops, n, r->LB, rops, sweeps, r->final_bit, dgs, doffs, &r->n_blk);
   r->n_rops = (int)rops.size(); r->n_sweeps = (int)sweeps.size();
   r->n_dg = (int)dgs.size(); r->n_doff = (int)doffs.size();
   for (const ROp& o : rops) r->kind_count[o.kind & 7]++;
