@@ -185,3 +185,27 @@ def test_statevector_planners_reproduce_the_logical_circuit():
             assert nphys > 0
             tiled = n > 10
             assert (nsw > 0) == tiled
+
+
+def test_tile_planner_gate_orders(monkeypatch):
+    """Engine T plans sweeps either in program order or with the dependency-aware list scheduler
+    (QCP_TILE_ORDER=program|dag; default = the one with fewer sweeps).  Both orders must reproduce
+    the logical circuit, the default is never worse than either, and BASELINE config 4 needs at
+    most half the program-order sweeps."""
+    cases = [("sim_circ_15", 16, 2, None), ("sim_circ_15", 12, 2, 1), ("layered", 16, 1, None),
+             ("layered", 12, 2, 1), ("cascade", 12, 2, None), ("farhi", 13, 2, None),
+             ("cross_mesh", 13, 1, None), ("cross_mesh", 11, 2, 1), ("alternate", 13, 1, 1)]
+    for ansatz, n, layers, seed in cases:
+        for dtype_code in (0, 1):
+            sweeps = {}
+            for order in ("program", "dag", None):
+                if order is None:
+                    monkeypatch.delenv("QCP_TILE_ORDER", raising=False)
+                else:
+                    monkeypatch.setenv("QCP_TILE_ORDER", order)
+                err, _, nsw = _check_plan(ansatz, n, layers, seed, dtype_code)
+                assert err < 1e-12, (ansatz, n, layers, seed, dtype_code, order, err)
+                sweeps[order] = nsw
+            assert sweeps[None] == min(sweeps["program"], sweeps["dag"]), (ansatz, n, sweeps)
+            if (ansatz, n, layers) == ("sim_circ_15", 16, 2):
+                assert 2 * sweeps[None] <= sweeps["program"] + 1, sweeps
