@@ -57,6 +57,95 @@ inline void fold_diagonals(const GateOp* ops, int n_ops, bool enable, std::vecto
   *n_blk = blocks;
 }
 
+// Dependency DAG of a gate list.  Two gates must keep their order iff they share a qubit on which at
+// least one of them is not diagonal: controls, RZ / CRZ targets and diagonal-block tables are
+// "Z-type" uses of a qubit and commute with each other.  prio[g] = earliest dependent gate.
+struct GateDag {
+  std::vector<std::vector<int>> succ;
+  std::vector<int> npred, prio;
+};
+
+inline GateDag build_dag(const GateOp* ops, int n_ops, int n) {
+  GateDag d;
+  d.succ.resize(n_ops);
+  d.npred.assign(n_ops, 0);
+  d.prio.assign(n_ops, 1 << 30);
+  std::vector<int> last_x(n, -1);
+  std::vector<std::vector<int>> z_since(n);
+  for (int j = 0; j < n_ops; ++j) {
+    const GateOp& g = ops[j];
+    int q[16];
+    bool x[16];
+    int nu = 0;
+    auto use = [&](int qq, bool xx) { q[nu] = qq; x[nu++] = xx; };
+    switch (g.kind) {
+      case kDiagMarker: for (int qq = 0; qq < n; ++qq) use(qq, false); break;
+      case QCP_GATE_RX: case QCP_GATE_RY: case QCP_GATE_H: use(g.a, true); break;
+      case QCP_GATE_RZ: use(g.a, false); break;
+      case QCP_GATE_CRX: case QCP_GATE_CNOT: use(g.a, false); use(g.b, true); break;
+      case QCP_GATE_CRZ: use(g.a, false); use(g.b, false); break;
+      default: use(g.a, true); use(g.b, true); break;
+    }
+    std::vector<int> pred;
+    for (int u = 0; u < nu; ++u) {
+      if (x[u] && !z_since[q[u]].empty()) pred.insert(pred.end(), z_since[q[u]].begin(), z_since[q[u]].end());
+      else if (last_x[q[u]] >= 0) pred.push_back(last_x[q[u]]);
+      if (x[u]) { last_x[q[u]] = j; z_since[q[u]].clear(); }
+      else z_since[q[u]].push_back(j);
+    }
+    std::sort(pred.begin(), pred.end());
+    pred.erase(std::unique(pred.begin(), pred.end()), pred.end());
+    for (int i : pred) {
+      d.succ[i].push_back(j);
+      d.npred[j]++;
+      d.prio[i] = std::min(d.prio[i], j);
+    }
+  }
+  return d;
+}
+
+// A dependency-respecting gate order that keeps the gates of a few qubits together: repeatedly take
+// every ready gate whose dense targets lie in the working set Q (at most `cap` qubits), else admit
+// the ready gate whose earliest dependent comes first; when nothing fits, start a new working set.
+// targets(g, t, &nt) = qubits gate g needs "near" (nt = 0: none).
+template <typename TargetsFn>
+inline std::vector<int> dag_order(const GateOp* ops, int n_ops, int n, int cap, TargetsFn targets) {
+  GateDag dag = build_dag(ops, n_ops, n);
+  std::vector<int> left = dag.npred, order, Q;
+  std::vector<char> done(n_ops, 0);
+  auto in_q = [&](int q) { return std::find(Q.begin(), Q.end(), q) != Q.end(); };
+  auto missing = [&](int j) {
+    int t[2], nt, add = 0;
+    targets(j, t, &nt);
+    for (int k = 0; k < nt; ++k)
+      if (!in_q(t[k]) && (k == 0 || t[k] != t[0])) ++add;
+    return add;
+  };
+  auto schedule = [&](int j) {
+    done[j] = 1;
+    order.push_back(j);
+    for (int s : dag.succ[j]) --left[s];
+  };
+  while ((int)order.size() < n_ops) {
+    bool any = false;
+    for (int j = 0; j < n_ops; ++j)
+      if (!done[j] && left[j] == 0 && missing(j) == 0) { schedule(j); any = true; }
+    if (any) continue;
+    int best = -1;
+    for (int j = 0; j < n_ops; ++j) {
+      if (done[j] || left[j] != 0 || (int)Q.size() + missing(j) > cap) continue;
+      if (best < 0 || dag.prio[j] < dag.prio[best]) best = j;
+    }
+    if (best < 0) { Q.clear(); continue; }          // working set full: start the next one
+    int t[2], nt;
+    targets(best, t, &nt);
+    for (int k = 0; k < nt; ++k)
+      if (!in_q(t[k])) Q.push_back(t[k]);
+    schedule(best);
+  }
+  return order;
+}
+
 struct LayoutTracker {
   int LB = 0;
   int lane_bits = 5;       // 6 when a vector spans two warps (every relayout is then a PERM)

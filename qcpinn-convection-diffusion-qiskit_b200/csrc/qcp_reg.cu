@@ -127,8 +127,11 @@ int reg_supported(int n, int dtype) {
 }
 
 // Translate the logical gate list into physical ops (see the header comment of qcp_reg.cuh).
-static void compile_physical(const GateOp* ops_in, int n_ops_in, int n, int LB, std::vector<ROp>& rops,
-                             std::vector<BlkPos>& bpos, std::vector<DiagGate>& dgs, int* meas_pos) {
+// reorder: run the gates in the dependency-respecting order of dag_order() (gates of the same few
+// qubits together -> fewer local<->lane relayouts) instead of program order
+static void compile_physical(const GateOp* ops_in, int n_ops_in, int n, int LB, bool reorder,
+                             std::vector<ROp>& rops, std::vector<BlkPos>& bpos, std::vector<DiagGate>& dgs,
+                             int* meas_pos) {
   std::vector<GateOp> vops;
   std::vector<int> orig;
   int n_blk = 0;
@@ -143,7 +146,7 @@ static void compile_physical(const GateOp* ops_in, int n_ops_in, int n, int LB, 
   lt.rops = &rops;
   for (int q = 0; q < n; ++q) { lt.pos[q] = n - 1 - q; lt.qat[n - 1 - q] = q; }
   std::vector<int>& pos = lt.pos;
-  auto targets = [&](int g, int* t, int* nt) {
+  auto gate_targets = [&](int g, int* t, int* nt) {
     *nt = 0;
     switch (ops[g].kind) {
       case QCP_GATE_RX: case QCP_GATE_RY: case QCP_GATE_H: t[(*nt)++] = ops[g].a; break;
@@ -152,6 +155,10 @@ static void compile_physical(const GateOp* ops_in, int n_ops_in, int n, int LB, 
       default: break;     // diagonal gates live in phase tables: no local target needed
     }
   };
+  std::vector<int> order(n_ops);
+  for (int g = 0; g < n_ops; ++g) order[g] = g;
+  if (reorder) order = dag_order(ops, n_ops, n, LB, gate_targets);
+  auto targets = [&](int gi, int* t, int* nt) { gate_targets(order[gi], t, nt); };   // by position
   auto make_local = [&](int q, int g_cur) { lt.make_local(q, g_cur, n_ops, targets); };
   auto move_to = [&](int q, int X) { lt.move_to(q, X); };
 
@@ -165,7 +172,8 @@ static void compile_physical(const GateOp* ops_in, int n_ops_in, int n, int LB, 
     }
     return m;
   };
-  for (int g = 0; g < n_ops; ++g) {
+  for (int gi = 0; gi < n_ops; ++gi) {
+    const int g = order[gi];
     const GateOp op = ops[g];
     if (op.kind == kDiagMarker) {          // phase table of block op.a, in the layout of this point
       BlkPos bp{};
@@ -177,16 +185,16 @@ static void compile_physical(const GateOp* ops_in, int n_ops_in, int n, int LB, 
     }
     switch (op.kind) {
       case QCP_GATE_RX: case QCP_GATE_RY: case QCP_GATE_H:
-        make_local(op.a, g);
+        make_local(op.a, gi);
         rops.push_back({R_L1, pos[op.a], -1, op.kind == QCP_GATE_RX ? T_X : T_R, orig[g],
                         op.kind == QCP_GATE_H ? -1 : op.p, 0, 0});
         break;
       case QCP_GATE_CRX:
-        make_local(op.b, g);
+        make_local(op.b, gi);
         rops.push_back({R_L1, pos[op.b], pos[op.a], T_X, orig[g], op.p, pair_mask(pos[op.b], pos[op.a]), 0});
         break;
       case QCP_GATE_CNOT:
-        make_local(op.b, g);
+        make_local(op.b, gi);
         rops.push_back({R_CX, pos[op.b], pos[op.a], 0, g, -1, pair_mask(pos[op.b], pos[op.a]), 0});
         break;
       default:   // U4 on (wire_hi = a, wire_lo = b): local positions (1, 0)
@@ -199,11 +207,30 @@ static void compile_physical(const GateOp* ops_in, int n_ops_in, int n, int LB, 
   for (int q = 0; q < n; ++q) meas_pos[q] = pos[q];
 }
 
+// both gate orders are compiled; the shorter physical program wins (ties keep the program order).
+// QCP_REG_ORDER=program / dag forces one.
+static void compile_best(const GateOp* ops, int n_ops, int n, int LB, std::vector<ROp>& rops,
+                         std::vector<BlkPos>& bpos, std::vector<DiagGate>& dgs, int* meas_pos) {
+  const char* env = std::getenv("QCP_REG_ORDER");
+  const bool force_program = env && env[0] == 'p', force_dag = env && env[0] == 'd';
+  std::vector<ROp> r2;
+  std::vector<BlkPos> b2;
+  std::vector<DiagGate> g2;
+  int m2[16];
+  if (!force_dag) compile_physical(ops, n_ops, n, LB, false, rops, bpos, dgs, meas_pos);
+  if (force_program) return;
+  compile_physical(ops, n_ops, n, LB, true, r2, b2, g2, m2);
+  if (force_dag || r2.size() < rops.size()) {
+    rops.swap(r2); bpos.swap(b2); dgs.swap(g2);
+    for (int q = 0; q < n; ++q) meas_pos[q] = m2[q];
+  }
+}
+
 // host-only entry for qcp_plancheck.cu
 void reg_compile_host(const GateOp* ops, int n_ops, int n, int LB, std::vector<ROp>& rops,
                       std::vector<std::vector<int>>& blk_pos, std::vector<DiagGate>& dgs, int* meas_pos) {
   std::vector<BlkPos> bpos;
-  compile_physical(ops, n_ops, n, LB, rops, bpos, dgs, meas_pos);
+  compile_best(ops, n_ops, n, LB, rops, bpos, dgs, meas_pos);
   for (const BlkPos& b : bpos) blk_pos.emplace_back(b.pos, b.pos + n);
 }
 
@@ -222,7 +249,7 @@ RegPlan* reg_create(int n, int enc, int dtype, const GateOp* host_ops, int n_ops
   std::vector<ROp> rops;
   std::vector<BlkPos> bpos;
   std::vector<DiagGate> dgs;
-  compile_physical(host_ops, n_ops, n, r->LB, rops, bpos, dgs, r->meas_pos);
+  compile_best(host_ops, n_ops, n, r->LB, rops, bpos, dgs, r->meas_pos);
   r->n_rops = (int)rops.size(); r->n_blk = (int)bpos.size(); r->n_dg = (int)dgs.size();
   for (const ROp& o : rops) r->kind_count[o.kind & 7]++;
   const size_t es = es_of(dtype);

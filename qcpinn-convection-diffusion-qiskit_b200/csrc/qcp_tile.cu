@@ -150,53 +150,6 @@ static bool tile_diag_tables() {
   return !(env && env[0] == '0');
 }
 
-// Dependency DAG of a gate list.  Two gates must keep their order iff they share a qubit on which at
-// least one of them is not diagonal: controls, RZ / CRZ targets and diagonal-block tables are
-// "Z-type" uses of a qubit and commute with each other.  prio[g] = earliest dependent gate.
-struct GateDag {
-  std::vector<std::vector<int>> succ;
-  std::vector<int> npred, prio;
-};
-
-static GateDag build_dag(const GateOp* ops, int n_ops, int n) {
-  GateDag d;
-  d.succ.resize(n_ops);
-  d.npred.assign(n_ops, 0);
-  d.prio.assign(n_ops, 1 << 30);
-  std::vector<int> last_x(n, -1);
-  std::vector<std::vector<int>> z_since(n);
-  for (int j = 0; j < n_ops; ++j) {
-    const GateOp& g = ops[j];
-    int q[kMaxQubitsSv];
-    bool x[kMaxQubitsSv];
-    int nu = 0;
-    auto use = [&](int qq, bool xx) { q[nu] = qq; x[nu++] = xx; };
-    switch (g.kind) {
-      case kDiagMarker: for (int qq = 0; qq < n; ++qq) use(qq, false); break;
-      case QCP_GATE_RX: case QCP_GATE_RY: case QCP_GATE_H: use(g.a, true); break;
-      case QCP_GATE_RZ: use(g.a, false); break;
-      case QCP_GATE_CRX: case QCP_GATE_CNOT: use(g.a, false); use(g.b, true); break;
-      case QCP_GATE_CRZ: use(g.a, false); use(g.b, false); break;
-      default: use(g.a, true); use(g.b, true); break;
-    }
-    std::vector<int> pred;
-    for (int u = 0; u < nu; ++u) {
-      if (x[u] && !z_since[q[u]].empty()) pred.insert(pred.end(), z_since[q[u]].begin(), z_since[q[u]].end());
-      else if (last_x[q[u]] >= 0) pred.push_back(last_x[q[u]]);
-      if (x[u]) { last_x[q[u]] = j; z_since[q[u]].clear(); }
-      else z_since[q[u]].push_back(j);
-    }
-    std::sort(pred.begin(), pred.end());
-    pred.erase(std::unique(pred.begin(), pred.end()), pred.end());
-    for (int i : pred) {
-      d.succ[i].push_back(j);
-      d.npred[j]++;
-      d.prio[i] = std::min(d.prio[i], j);
-    }
-  }
-  return d;
-}
-
 // reorder = false: sweeps are maximal runs of the gate list in program order.
 // reorder = true: every sweep takes all gates the dependency DAG allows on its tile qubits, and new
 // qubits join the tile in the order of the earliest blocked gate (a list scheduler); e.g. the
