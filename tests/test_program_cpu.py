@@ -152,14 +152,24 @@ def _check_plan(ansatz, n, layers, seed, dtype_code):
 
     lib = qb._lib.load()
     prog = compile_program(ansatz, n, layers, seed)
-    ops = np.ascontiguousarray(prog.ops, dtype=np.int32)
-    consts = np.ascontiguousarray(prog.consts, dtype=np.complex128).view(np.float64)
-    theta = np.random.default_rng(7).normal(size=max(prog.n_theta, 1))
+    return _check_ops(n, dtype_code, prog.ops, prog.consts, prog.n_theta)
+
+
+def _check_ops(n, dtype_code, ops, consts, n_theta):
+    import ctypes
+
+    from qcpinn_b200 import _lib
+
+    lib = _lib.load()
+    ops = np.ascontiguousarray(ops, dtype=np.int32)
+    n_consts = len(consts)
+    consts = np.ascontiguousarray(consts, dtype=np.complex128).view(np.float64)
+    theta = np.random.default_rng(7).normal(size=max(n_theta, 1))
     err, nphys, nsw = ctypes.c_double(), ctypes.c_int(), ctypes.c_int()
     rc = lib.qcp_debug_check_plan(
         n, dtype_code, ops.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ops.shape[0],
-        consts.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), prog.consts.shape[0],
-        theta.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), prog.n_theta,
+        consts.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n_consts,
+        theta.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n_theta,
         ctypes.byref(err), ctypes.byref(nphys), ctypes.byref(nsw))
     assert rc == 0, lib.qcp_last_error()
     return err.value, nphys.value, nsw.value
@@ -209,3 +219,42 @@ def test_tile_planner_gate_orders(monkeypatch):
             assert sweeps[None] == min(sweeps["program"], sweeps["dag"]), (ansatz, n, sweeps)
             if (ansatz, n, layers) == ("sim_circ_15", 16, 2):
                 assert 2 * sweeps[None] <= sweeps["program"] + 1, sweeps
+
+
+def test_planners_on_random_gate_programs(monkeypatch):
+    """Random gate lists (all eight gate kinds, random wires, Haar-style two-qubit blocks) through
+    both planners, both gate orders, with and without the diagonal-block tables of engine T: the
+    dependency rules of the list scheduler (controls / RZ / CRZ / tables commute, everything else
+    keeps its order) must hold for circuits that look nothing like the six ansaetze."""
+    from scipy.stats import unitary_group
+
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        n = int(rng.integers(5, 14))
+        n_gates = int(rng.integers(20, 70))
+        ops, consts, n_theta = [], [], 0
+        for _ in range(n_gates):
+            kind = int(rng.choice([P.RX, P.RY, P.RZ, P.CRX, P.CRZ, P.CNOT, P.HAD, P.U4],
+                                  p=[.17, .17, .14, .12, .14, .14, .06, .06]))
+            a, b = (int(v) for v in rng.choice(n, size=2, replace=False))
+            if kind in (P.RX, P.RY, P.RZ):
+                ops.append([kind, a, -1, n_theta]); n_theta += 1
+            elif kind in (P.CRX, P.CRZ):
+                ops.append([kind, a, b, n_theta]); n_theta += 1
+            elif kind == P.CNOT:
+                ops.append([kind, a, b, -1])
+            elif kind == P.HAD:
+                ops.append([kind, a, -1, -1])
+            else:
+                ops.append([kind, a, b, len(consts)])
+                consts.append(unitary_group.rvs(4, random_state=np.random.RandomState(trial * 100 + len(consts))))
+        consts = np.array(consts, dtype=np.complex128).reshape(-1, 4, 4)
+        for dtype_code in (0, 1):
+            for order in ("program", "dag"):
+                for diag in ("1", "0"):
+                    monkeypatch.setenv("QCP_TILE_ORDER", order)
+                    monkeypatch.setenv("QCP_REG_ORDER", order)
+                    monkeypatch.setenv("QCP_TILE_DIAG", diag)
+                    err, nphys, _ = _check_ops(n, dtype_code, ops, consts, n_theta)
+                    assert err < 1e-11, (trial, n, dtype_code, order, diag, err)
+                    assert nphys > 0
