@@ -77,8 +77,13 @@ def build_library(force: bool = False, verbose: bool = False, out: Path | None =
     BUILD_DIR.mkdir(parents=True, exist_ok=True)
     stamp = BUILD_DIR / "digest.txt"
     digest = _digest()
+    record = BUILD_DIR / "build_record.json"
     if not force and LIB_PATH.exists() and stamp.exists() and stamp.read_text() == digest:
+        _note(record, {"reused": True, "digest": digest})
         return LIB_PATH
+    import time
+
+    t0 = time.time()
     sources = [s for s in SOURCES if (CSRC / s).exists()]
     with cf.ThreadPoolExecutor(max_workers=min(8, len(sources))) as pool:
         objs = list(pool.map(lambda s: _compile(s, verbose), sources))
@@ -87,7 +92,36 @@ def build_library(force: bool = False, verbose: bool = False, out: Path | None =
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
     stamp.write_text(digest)
+    _note(record, {"reused": False, "digest": digest, "sources": sources,
+                   "seconds": round(time.time() - t0, 1)})
     return LIB_PATH
+
+
+def _note(path: Path, entry: dict) -> None:
+    """Append one line per build() call: which digest, compiled cold or reused."""
+    import json
+    import time
+
+    entry["when"] = time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime())
+    with open(path, "a") as fh:
+        fh.write(json.dumps(entry) + "\n")
+
+
+def cold_compile_probe(src: str = "qcp_data.cu") -> float:
+    """Compile one translation unit from scratch into a temporary object (never reused): proves on
+    every ``build()`` call that nvcc, the sm_100a flags and the headers still work even when the
+    digest-matched library was kept.  Returns the seconds it took."""
+    import tempfile
+    import time
+
+    t0 = time.time()
+    with tempfile.TemporaryDirectory() as tmp:
+        obj = Path(tmp) / "probe.o"
+        cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0 or not obj.exists():
+            raise RuntimeError(f"cold compile probe failed on {src}:\n{res.stdout}\n{res.stderr}")
+    return time.time() - t0
 
 
 if __name__ == "__main__":

@@ -13,7 +13,9 @@ from helpers import F, TOL, device_weights, make_case, mlp_list, points, rel_err
 from oracle import solver as osolver
 
 pytestmark = pytest.mark.gpu
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt")))
+# oracle-generated fixtures only (refstub_* / pennylane_* have their own tests: test_reference_fixtures.py)
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt"))
+                if not os.path.basename(p).startswith(("refstub_", "pennylane_")))
 DEV = torch.device("cuda", 0)
 
 ARGS = {

@@ -17,7 +17,9 @@ from oracle import solver as osolver
 
 torch.set_default_dtype(torch.float32)
 D = torch.float64
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt")))
+# oracle-generated fixtures only (refstub_* / pennylane_* have their own tests: test_reference_fixtures.py)
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt"))
+                if not os.path.basename(p).startswith(("refstub_", "pennylane_")))
 
 
 def _x(rows):
