@@ -68,6 +68,26 @@ def model_args(dtype_name):
 
 
 # ------------------------------------------------------------------------------------------------
+# algorithmic work model -- the figure ``roofline.achieved`` uses
+# ------------------------------------------------------------------------------------------------
+def flops_per_point(n, layers, ansatz, haar, hidden=50):
+    """Gate-by-gate statevector flops on M = 2^n amplitudes (cmul = 6, cadd = 2): dense 1q 14M,
+    diagonal 1q 6M, controlled dense 7M, controlled diagonal 3M, CNOT 0, dense 2q 30M, all-Z
+    expvals (3 + n)M.  F_fwd = encoding 14nM + L layers + [Haar 60M] + H + expvals; MLPs
+    F_mlp = 2*hidden*(2n + 4).  A train step touches 6 + 2/3 streams per residual point, forward +
+    2x backward: 20 (F_fwd + F_mlp).  Returns (flops per residual point and step, F_fwd, F_mlp)."""
+    m = 2 ** n
+    per_layer = {
+        "cascade": 27 * n, "layered": 40 * n, "sim_circ_15": 28 * n,
+        "cross_mesh": 40 * n + 3 * n * (n - 1), "farhi": 20 * (n - 1),
+        "alternate": 40 * (len(range(n - 1)[::2]) + len(range(n)[1::2])),
+    }[ansatz]
+    f_fwd = (14 * n + layers * per_layer + (60 if haar else 0) + 14 + (3 + n)) * m
+    f_mlp = 2 * hidden * (2 * n + 4)
+    return 20 * (f_fwd + f_mlp), f_fwd, f_mlp
+
+
+# ------------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
@@ -141,7 +161,6 @@ OTHER_CONFIGS = [
 def measure_other_configs(torch, qb, device, peaks, hbm_gbs):
     """One JSON object per config: full train steps (sampling .. Adam .. loss.item()) of the named
     shape on one GPU, with the SURVEY section 8(d) roofline of that shape beside it."""
-    from oracle.solver import flops_per_point
     from qcpinn_b200.trainer.diffusion_train import TrainStep
 
     out = {}
@@ -236,7 +255,8 @@ def run_ours(ns):
     from qcpinn_b200.trainer.diffusion_train import TrainStep, _make_averager
     import torch.distributed as dist
 
-    os.environ.pop("NCCL_DEBUG", None)            # any level >= VERSION prints a banner on stdout
+    # NCCL_DEBUG is left alone (the driver reads the rank count from NCCL's own log): the JSON line
+    # is printed LAST, after the process group is gone, so nothing NCCL prints can follow it
     rank, world, local = init_from_env()
     if world != ns.gpus and world > 1:
         raise SystemExit(f"--gpus {ns.gpus} but WORLD_SIZE={world}")
@@ -350,14 +370,18 @@ def run_ours(ns):
 
     tdt = {"f64": torch.float64, "f32": torch.float32}
     peaks = {d: F.fma_peak(tdt[d], device) for d in ("f64", "f32")}
+    try:
+        dp = dp_equivalence(torch, dist, qb, device, rank, world, ns.dtype)
+    except Exception as exc:                   # never lose the headline line to the side check
+        if world > 1:
+            raise                              # ... but a collective mismatch must not hang silently
+        dp = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank != 0:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
         return
-
-    from oracle.solver import flops_per_point
 
     fl_pt, f_fwd, f_mlp = flops_per_point(N_QUBITS, N_LAYERS, ANSATZ, haar=False, hidden=HIDDEN)
     # dominant kernel = adjoint of the 6-stream residual forward: 2 x 6 x (F_fwd + F_mlp) per point
@@ -412,12 +436,67 @@ def run_ours(ns):
         hbm, src = measured_hbm_gbs()
         line["other_configs"] = measure_other_configs(torch, qb, device, peaks, hbm)
         line["other_configs"]["hbm_peak_source"] = src
+    if dp is not None:
+        line["dp_check"] = dp
     if world == 1 and not ns.no_cpu:
         line["cpu_baseline"] = cpu_baseline(ns.cpu_points, ns.cpu_steps)
-    print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+        time.sleep(0.5)        # let the other ranks' NCCL teardown lines out first
+    print(json.dumps(line), flush=True)
+
+
+def dp_equivalence(torch, dist, qb, device, rank, world, dtype_name, shards=8, points=8 * 24576):
+    """the W-rank averaged gradient of ONE fixed batch against the 1-rank
+    gradient of the same batch.  Every rank builds the identical batch and model; rank r runs the
+    fused step on its contiguous 1/W slice, the flat gradients are all-reduced (NCCL) and divided
+    by W, and the result is compared with the gradient of the whole batch computed locally.  With
+    one GPU the W = 8 shards run one after the other on that GPU ("emulated")."""
+    from qcpinn_b200.trainer.diffusion_train import DIFFUSION_COEFFS
+
+    torch.manual_seed(0)
+    logger = qb.Logging(os.path.join(tempfile.gettempdir(), f"qcpinn_bench_dp_r{rank}"))
+    args = model_args(dtype_name)
+    args["cuda_graph"] = False
+    model = qb.DVPDESolver(args, logger, device=device)
+    w = world if world > 1 else shards
+    n_res = points - points % (3 * w)
+    g = torch.Generator().manual_seed(777)
+    from qcpinn_b200.data.diffusion_dataset import r as r_fn, u as u_fn
+
+    def box(lo, hi, n):
+        lo, hi = torch.tensor(lo).view(1, 3), torch.tensor(hi).view(1, 3)
+        return (lo + (hi - lo) * torch.rand(n, 3, generator=g)).to(device)
+
+    xi = box([0., 0., 0.], [0., 1., 1.], n_res // 3)
+    xb = box([0., 0., 0.], [1., 0., 1.], n_res // 3)
+    xr = box([0., 0., 0.], [1., 1., 1.], n_res)
+    full = (xi, u_fn(xi), xb, u_fn(xb), xr, r_fn(xr))
+
+    def grads_of(batch):
+        flat, numel = model.train_step_grads(batch, DIFFUSION_COEFFS)
+        return flat[:numel + 1].double().clone()
+
+    def shard(k):
+        return tuple(t[k * (t.shape[0] // w):(k + 1) * (t.shape[0] // w)].contiguous() for t in full)
+
+    want = grads_of(full)
+    if world > 1:
+        got = grads_of(shard(rank))
+        dist.all_reduce(got, op=dist.ReduceOp.SUM)
+        got /= world
+        mode = "nccl"
+    else:
+        got = sum(grads_of(shard(k)) for k in range(w)) / w
+        mode = "emulated"
+    torch.cuda.synchronize(device)
+    n = want.numel() - 1
+    err = float((got[:n] - want[:n]).abs().max() / want[:n].abs().max().clamp_min(1e-300))
+    err_loss = float((got[n] - want[n]).abs() / want[n].abs().clamp_min(1e-300))
+    return {"max_rel_err_grad": err, "rel_err_loss": err_loss, "shards": w, "mode": mode,
+            "residual_points": n_res, "dtype": dtype_name,
+            "note": "gradients pass through the float32 .grad buffer (7 significant digits)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -462,14 +541,54 @@ def cpu_baseline(points, steps):
             "ms_per_step": dt / steps * 1e3}
 
 
+ORACLE_BYTES_PER_POINT = 64 * 1024     # measured peak RSS of one oracle step / residual point
+REFERENCE_TIME_BUDGET_S = 150.0        # whole --steps K --warmup W run of the reference arm
+
+
+def _mem_available_bytes():
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                return int(ln.split()[1]) * 1024
+    except Exception:
+        pass
+    return 32 << 30
+
+
+def reference_sample_points(ns, trainer, osolver):
+    """Residual points of one reference-arm step: the largest power of two that (a) is not more
+    than the workload, (b) keeps the nested-autograd graph (about 64 KB per residual point: five
+    create_graph sweeps over a gate-by-gate complex128 simulation) under half of the host's free
+    memory and (c) lets W + K steps end inside REFERENCE_TIME_BUDGET_S at the rate a probe step
+    shows.  Returns (points, reason dict)."""
+    probe = 16_384
+    trainer.step(osolver.make_batches(probe, seed=90))
+    t0 = time.perf_counter()
+    trainer.step(osolver.make_batches(probe, seed=91))
+    rate = probe / (time.perf_counter() - t0)
+    by_mem = int(0.5 * _mem_available_bytes() / ORACLE_BYTES_PER_POINT)
+    by_time = int(rate * REFERENCE_TIME_BUDGET_S / max(ns.steps + ns.warmup, 1))
+    cap = max(min(ns.points, by_mem, by_time), 4096)
+    points = 1 << (cap.bit_length() - 1)
+    if ns.cpu_points and ns.cpu_points != 65_536:       # explicit override
+        points = min(ns.cpu_points, ns.points)
+    return points, {"workload_points": ns.points, "limit_by_memory": by_mem, "limit_by_time": by_time,
+                    "probe_points_per_s": rate, "bytes_per_point": ORACLE_BYTES_PER_POINT,
+                    "time_budget_s": REFERENCE_TIME_BUDGET_S,
+                    "why": "the full workload needs ~%.0f GB of host memory for the nested-autograd "
+                           "graph" % (ns.points * ORACLE_BYTES_PER_POINT / 1e9)}
+
+
 def run_reference(ns):
+    """The reference's algorithm on the host cores (rank 0 only), on OUR arm's config / metric;
+    each step is a bounded sample of that workload (cpu_baseline.sample says which)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
 
     osolver, trainer = _oracle_trainer("mixed")
-    points = min(ns.cpu_points, ns.points)
+    points, sizing = reference_sample_points(ns, trainer, osolver)
     for i in range(ns.warmup):
         trainer.step(osolver.make_batches(points, seed=100 + i))
     t0 = time.perf_counter()
@@ -478,19 +597,27 @@ def run_reference(ns):
     dt = time.perf_counter() - t0
     value = points * ns.steps / dt
     cores = torch.get_num_threads()
+    world = max(ns.gpus, 1)
+    pts_rank = ns.points // world
     sample = (f"each step = one full train step on {points} residual points (+2x{points // 3} "
-              f"IC/BC), a bounded sample of the {ns.points}-point workload")
+              f"IC/BC), a bounded sample of the {ns.points}-point workload (points/s normalised)")
     line = {
         "impl": "reference",
         "metric": "PINN train-step collocation points/s (4-qubit cascade)",
         "value": value, "unit": "points/s", "n_gpus": ns.gpus, "steps": ns.steps,
         "warmup": ns.warmup, "ms_per_step": dt / ns.steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "residual_points_per_step": points,
-                   "note": "reference algorithm (gate-by-gate default.qubit-style statevector + "
-                           "nested autograd) restated in oracle/; PennyLane is not installable"},
+        # the config of our arm, key for key (the sample actually stepped is in cpu_baseline)
+        "config": {"workload": WORKLOAD, "residual_points_per_step": pts_rank * world,
+                   "ic_points": (pts_rank // 3) * world, "bc_points": (pts_rank // 3) * world,
+                   "parallelism": f"dp{world}",
+                   "l2": "inputs resampled on the device every step; per-step footprint > 126 MB L2"},
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port",
-                         "sample": sample},
+                         "sample": sample, "sample_points_per_step": points, "sizing": sizing,
+                         "note": "reference algorithm (gate-by-gate default.qubit-style statevector "
+                                 "+ nested autograd) restated in oracle/; PennyLane is not "
+                                 "installable, so this is the oracle port, float32 MLPs + "
+                                 "complex128 state like the reference"},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
