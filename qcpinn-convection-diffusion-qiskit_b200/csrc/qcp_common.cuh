@@ -15,6 +15,7 @@ constexpr int kCStride = 4;          // feature-matrix row stride (outputs padde
 constexpr int kMaxHidden = 128;      // hidden width of the pre/post MLP held in shared memory
 constexpr int kWarpsPerBlock = 4;
 constexpr int kThreads = kWarpsPerBlock * 32;
+constexpr int kMaxBlocksPerSm = 8;   // persistent grids never exceed this many blocks per SM
 constexpr int kStageRows = 32;       // rows of the per-warp gradient staging tile
 constexpr int kStagePitch = 33;      // +1 padding: column sums are bank-conflict free
 

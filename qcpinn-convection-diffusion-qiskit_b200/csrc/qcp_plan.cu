@@ -823,6 +823,12 @@ int qcp_plan_create(qcp_plan_t** out, int n_qubits, int encoding, int dtype, int
     alloc((void**)&p->d_C64, sizeof(double) * p->F * kCStride);
     alloc((void**)&p->d_C, elem_size(dtype) * p->F * kCStride);
     alloc((void**)&p->d_Cbar, sizeof(double) * p->F * n_qubits);
+    // partial-sum slots of the deferred reduction, sized once here: no cudaMalloc can then happen
+    // inside a CUDA-graph capture of the train step, and slices handed out never move
+    const size_t pe = (size_t)kMaxPending * p->num_sms * kMaxBlocksPerSm *
+                      (size_t)nacc_solver(n_qubits, encoding, hidden);
+    alloc((void**)&p->d_partials, pe * elem_size(dtype));
+    if (e == cudaSuccess) p->partials_elems = pe;
   }
   if (e == cudaSuccess && n_ops) e = cudaMemcpy(p->d_ops, ops, sizeof(GateOp) * n_ops, cudaMemcpyHostToDevice);
   if (e == cudaSuccess && n_consts)
@@ -1155,7 +1161,18 @@ int qcp_solver_forward(qcp_plan_t* p, const qcp_mlp_t* w, const void* X, long lo
 }
 
 static size_t partial_slot_elems(const qcp_plan* p) {
-  return (size_t)p->num_sms * 8 * (size_t)nacc_solver(p->n, p->enc, p->H);
+  return (size_t)p->num_sms * kMaxBlocksPerSm * (size_t)nacc_solver(p->n, p->enc, p->H);
+}
+
+// the next slice of d_partials must fit: growing the buffer here would free slices that earlier
+// pending calls already wrote (and cudaMalloc is illegal under stream capture)
+static int check_partials_room(const qcp_plan* p, size_t need, const char* who) {
+  if (p->pending_used + need > p->partials_elems) {
+    set_error("%s: partial-sum buffer exhausted (%zu used + %zu needed > %zu elements)", who,
+              p->pending_used, need, p->partials_elems);
+    return 1;
+  }
+  return 0;
 }
 
 int qcp_solver_backward_begin(qcp_plan_t* p) {
@@ -1201,6 +1218,7 @@ int qcp_solver_backward_add(qcp_plan_t* p, const qcp_mlp_t* w, const void* X, co
     if (gr.contract > want_blocks) gr.contract = (int)want_blocks;
     if (gr.pre > want_blocks) gr.pre = (int)want_blocks;
     const size_t e0 = (size_t)gr.post * n0, e1 = (size_t)gr.contract * n1, e2 = (size_t)gr.pre * n2;
+    if (check_partials_room(p, e0 + e1 + e2, "qcp_solver_backward_add")) return 1;
     void* p0 = base; void* p1 = base + e0 * es; void* p2 = base + (e0 + e1) * es;
     int rc = f64 ? launch_solver_backward_split<double>(p->n, p->enc, mode, a, gr, p0, p1, p2, s)
                  : launch_solver_backward_split<float>(p->n, p->enc, mode, a, gr, p0, p1, p2, s);
@@ -1217,6 +1235,7 @@ int qcp_solver_backward_add(qcp_plan_t* p, const qcp_mlp_t* w, const void* X, co
       cached = f64 ? solver_backward_max_grid<double>(p->n, p->enc, mode, p->H, p->num_sms)
                    : solver_backward_max_grid<float>(p->n, p->enc, mode, p->H, p->num_sms);
     const int grid = (int)(want_blocks > cached ? cached : want_blocks);
+    if (check_partials_room(p, (size_t)grid * nacc, "qcp_solver_backward_add")) return 1;
     a.partials = base;
     int rc = f64 ? launch_solver_backward<double>(p->n, p->enc, mode, a, grid, s)
                  : launch_solver_backward<float>(p->n, p->enc, mode, a, grid, s);

@@ -1155,6 +1155,8 @@ int blocks_per_sm(K kernel, size_t smem) {
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess ||
       per_sm < 1)
     per_sm = 1;
+  // the plan's partial-sum slots are sized for kMaxBlocksPerSm blocks per SM (qcp_plan.cu)
+  if (per_sm > kMaxBlocksPerSm) per_sm = kMaxBlocksPerSm;
   return per_sm;
 }
 

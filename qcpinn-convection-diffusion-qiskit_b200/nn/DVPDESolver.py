@@ -351,11 +351,40 @@ class DVPDESolver(nn.Module):
         self.quantum_layer.mark_updated()
         self.postprocessor.load_state_dict(state["postprocessor"])
         if "optimizer" in state:
-            self.optimizer.load_state_dict(state["optimizer"])
+            self._load_optimizer_state(state["optimizer"])
         if "scheduler" in state:
             self.scheduler.load_state_dict(state["scheduler"])
         self.loss_history = list(state.get("loss_history", []))
         return self
+
+    def _load_optimizer_state(self, opt_state):
+        """``optimizer.load_state_dict`` replaces ``param_groups`` wholesale: a reference checkpoint
+        brings a float lr without capturable / fused, one of ours read with the default
+        ``map_location="cpu"`` a CPU lr tensor.  Either would break the CUDA-graph step (capture
+        fails, or the lr is frozen into the graph and plateau reductions stop applying), so the
+        invariants of ``__init__`` are re-installed: device-resident lr tensor (the SAME tensor
+        object a captured graph already reads), capturable + fused, ``step`` counters on the device."""
+        lr_tensors = [g["lr"] for g in self.optimizer.param_groups]
+        self.optimizer.load_state_dict(opt_state)
+        dev = self.quantum_layer.params.device
+        if dev.type != "cuda":
+            return
+        for g, lr0 in zip(self.optimizer.param_groups, lr_tensors):
+            loaded = float(g["lr"])
+            if isinstance(lr0, torch.Tensor) and lr0.device.type == "cuda":
+                lr0.fill_(loaded)
+                g["lr"] = lr0
+            else:
+                g["lr"] = torch.tensor(loaded, dtype=torch.float32, device=dev)
+            g["capturable"] = True
+            g["fused"] = True
+            g["foreach"] = False
+        for st in self.optimizer.state.values():
+            if "step" in st:
+                st["step"] = torch.as_tensor(st["step"], dtype=torch.float32).to(dev)
+            for k in ("exp_avg", "exp_avg_sq", "max_exp_avg_sq"):
+                if k in st:
+                    st[k] = st[k].to(dev)
 
     def draw_quantum_circuit(self, x):
         # matplotlib / qml.draw_mpl are not part of this stack: log the gate program instead.

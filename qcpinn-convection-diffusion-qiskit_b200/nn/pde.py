@@ -30,7 +30,11 @@ def diffusion_operator(model, t, x, y, sigma_t=1.0, sigma_x=1.0, sigma_y=1.0,
     y.requires_grad = True
     fused = getattr(model, "taylor_residual", None)
     if fused is not None:
-        return fused(torch.cat((t, x, y), 1),
+        # The fused route returns (u, r) connected to every PARAMETER; the coordinates are detached
+        # on purpose: d(u, r)/d(t, x, y) would need third derivatives that the six Taylor streams
+        # do not carry, so ``autograd.grad(r, x)`` fails loudly ("not used in the graph") instead
+        # of returning silent zeros.  ``model.forward(X)`` (value mode) does give d u / d X.
+        return fused(torch.cat((t, x, y), 1).detach(),
                      _diffusion_coeffs(sigma_t, sigma_x, sigma_y, D, v_x, v_y))
     u = model(torch.cat((t, x, y), 1))
     ones = torch.ones_like(u)
@@ -58,7 +62,8 @@ def _two_input_residual(model, a, b, c_aa, c_bb):
     fused = getattr(model, "taylor_residual", None)
     if fused is not None:
         # the two coordinates sit in the kernel's x / y slots (the ones with second derivatives)
-        return fused(torch.cat((a, b), 1), (0.0, 0.0, 0.0, c_aa, c_bb))
+        # (coordinates detached: see diffusion_operator)
+        return fused(torch.cat((a, b), 1).detach(), (0.0, 0.0, 0.0, c_aa, c_bb))
     u = model(torch.cat((a, b), 1))
     u_aa = _grad(_grad(u, a), a)
     u_bb = _grad(_grad(u, b), b)

@@ -234,6 +234,10 @@ class TrainStep:
             if staged is not None:
                 self._release_stage(staged)
         graph.replay()
+        # the replayed fused Adam changed every parameter behind Python's back (no version bump,
+        # no optimizer hook): move the cache keys on, so that an eager forward / evaluation between
+        # replays re-casts the weights and re-runs qcp_prepare instead of reusing stale copies
+        self.model.quantum_layer.mark_updated()
         F.launch_counter += launches
         self.last_terms = outs
         return self._host_update(outs[0])

@@ -484,3 +484,81 @@ def test_prefetched_host_batches_give_the_same_steps(tmp_path):
 
     a, b = run(False), run(True)
     assert len(a) == 6 and all(abs(x - y) <= 1e-6 * abs(x) for x, y in zip(a, b)), (a, b)
+
+
+def test_eager_forward_between_graph_replays_sees_fresh_parameters(tmp_path):
+    """A replayed CUDA graph updates the parameters behind Python's back; an eager forward between
+    replays (periodic validation) must re-cast the weights and re-run qcp_prepare every time."""
+    from qcpinn_b200.trainer.diffusion_train import TrainStep
+
+    model = _model(tmp_path)
+    step = TrainStep(model, 96)
+    X = points(33).float().to(DEV)
+    assert step.use_graph
+    for round_ in range(3):
+        for _ in range(5):
+            step()
+        assert round_ == 0 or step.steady()
+        got = model(X)                                           # cached plan of the module
+        fresh = F.Plan(model.quantum_layer.program, 0, torch.float64, 50, DEV)
+        want = F.solver_value(fresh, X, model.quantum_layer.params.detach(),
+                              [t.detach() for t in model._mlp_tensors()])
+        assert rel_err(got, want) < 1e-6, round_
+        u, r = qb.diffusion_operator(model, X[:, 0:1].clone(), X[:, 1:2].clone(), X[:, 2:3].clone())
+        _, r_want = F.solver_residual(fresh, X, model.quantum_layer.params.detach(),
+                                      [t.detach() for t in model._mlp_tensors()],
+                                      (1.0, 1.0, 1.0, -0.01, -0.01))
+        assert rel_err(r, r_want) < 1e-6, round_
+
+
+def test_restore_on_cuda_keeps_graph_step_invariants(tmp_path):
+    """restore() of our own checkpoint (read with the default map_location='cpu') and of a
+    reference-style one (float lr, no capturable / fused): the lr stays the device tensor the
+    captured step reads, and a graph-captured TrainStep still trains and follows lr reductions."""
+    from qcpinn_b200.trainer.diffusion_train import TrainStep
+
+    model = _model(tmp_path)
+    step = TrainStep(model, 48)
+    for _ in range(5):
+        step()
+    path = os.path.join(str(tmp_path), "ckpt.pth")
+    model.save_state(path)
+    state = qb.DVPDESolver.load_state(path)                      # CPU tensors, CPU lr tensor
+    ref_style = dict(state)
+    ref_opt = {"state": {k: {kk: (float(vv) if kk == "step" else vv) for kk, vv in v.items()}
+                         for k, v in state["optimizer"]["state"].items()},
+               "param_groups": [dict(g, lr=float(g["lr"]), capturable=False, fused=None, foreach=None)
+                                for g in state["optimizer"]["param_groups"]]}
+    ref_style["optimizer"] = ref_opt
+    for st in (state, ref_style):
+        m2 = _model(tmp_path)
+        lr_tensor = m2.optimizer.param_groups[0]["lr"]
+        m2.restore(st)
+        g = m2.optimizer.param_groups[0]
+        assert g["lr"] is lr_tensor and lr_tensor.is_cuda and g["capturable"] and g["fused"]
+        assert abs(float(lr_tensor) - 0.005) < 1e-9
+        for p_a, p_b in zip(model.parameters(), m2.parameters()):
+            assert torch.equal(p_a, p_b)
+        s2 = TrainStep(m2, 48)
+        torch.manual_seed(77)
+        losses = [s2() for _ in range(6)]                         # 3 eager, capture, replays
+        assert s2.steady() and all(math.isfinite(v) for v in losses)
+        before = [p.detach().clone() for p in m2.parameters()]
+        for grp in m2.optimizer.param_groups:                    # what ReduceLROnPlateau does
+            grp["lr"].fill_(0.0) if isinstance(grp["lr"], torch.Tensor) else None
+        s2()
+        # lr = 0 reached the captured Adam kernel: parameters did not move
+        assert all(torch.equal(a, b) for a, b in zip(before, m2.parameters()))
+
+
+def test_residual_outputs_are_not_connected_to_the_coordinates(tmp_path):
+    """d(u, r)/d(t, x, y) on the fused route fails loudly instead of returning silent zeros."""
+    model = _model(tmp_path)
+    X = points(9).float().to(DEV)
+    t, x, y = (X[:, i:i + 1].clone() for i in range(3))
+    u, r = qb.diffusion_operator(model, t, x, y)
+    with pytest.raises(RuntimeError, match="not have been used in the graph"):
+        torch.autograd.grad(r.sum(), x)
+    Xv = X.clone().requires_grad_(True)                          # value mode does give du/dX
+    (gx,) = torch.autograd.grad(model(Xv).sum(), Xv)
+    assert gx.shape == X.shape and float(gx.abs().max()) > 0
