@@ -65,10 +65,12 @@ def _compile(src: str, verbose: bool) -> Path:
 
 
 def build_library(force: bool = False, verbose: bool = False, out: Path | None = None,
-                  defines: list[str] | None = None) -> Path:
+                  defines: list[str] | None = None, only: list[str] | None = None) -> Path:
     """Compile every CUDA source for sm_100a and link the shared library (idempotent).
-    ``out`` / ``defines`` build an experimental variant next to the default library."""
+    ``out`` / ``defines`` build an experimental variant next to the default library; ``only``
+    names the sources the defines affect (the other objects are taken from the default build)."""
     global BUILD_DIR, LIB_PATH
+    main_build = BUILD_DIR
     if out is not None or defines:
         EXTRA_DEFINES[:] = [f"-D{d}" for d in (defines or [])]
         LIB_PATH = Path(out) if out is not None else LIB_PATH
@@ -85,8 +87,13 @@ def build_library(force: bool = False, verbose: bool = False, out: Path | None =
 
     t0 = time.time()
     sources = [s for s in SOURCES if (CSRC / s).exists()]
-    with cf.ThreadPoolExecutor(max_workers=min(8, len(sources))) as pool:
-        objs = list(pool.map(lambda s: _compile(s, verbose), sources))
+    if only:
+        with cf.ThreadPoolExecutor(max_workers=min(8, len(only))) as pool:
+            fresh = dict(zip(only, pool.map(lambda s: _compile(s, verbose), only)))
+        objs = [fresh.get(s, main_build / (Path(s).stem + ".o")) for s in sources]
+    else:
+        with cf.ThreadPoolExecutor(max_workers=min(8, len(sources))) as pool:
+            objs = list(pool.map(lambda s: _compile(s, verbose), sources))
     cmd = [_nvcc(), *ARCH_FLAGS, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-lcudart"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
@@ -130,6 +137,9 @@ if __name__ == "__main__":
     ap.add_argument("--verbose", action="store_true", help="keep ptxas -v output in csrc/build/")
     ap.add_argument("--out", default=None, help="write an experimental variant to this path")
     ap.add_argument("-D", dest="defines", action="append", default=[], help="extra -D macro")
+    ap.add_argument("--only", default=None,
+                    help="comma-separated sources the defines affect (others reuse the default build)")
     ns = ap.parse_args()
-    print(build_library(force=ns.force, verbose=ns.verbose, out=ns.out, defines=ns.defines))
+    print(build_library(force=ns.force, verbose=ns.verbose, out=ns.out, defines=ns.defines,
+                        only=ns.only.split(",") if ns.only else None))
     sys.exit(0)

@@ -162,9 +162,60 @@ struct Math<float> {
   static __device__ __forceinline__ void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
 };
 
+// Branch-free double-precision tanh:  tanh|x| = 1 - 2 / (exp(2|x|) + 1).
+// libm's tanh() takes one of two code paths per lane (|x| < 0.55: odd polynomial, else expm1-style),
+// so a warp with mixed arguments executes both (~35 FP64-pipe + ~45 other instructions); this one
+// is 24 FP64-pipe instructions and no branch.  exp: k = rint(y log2 e) by the magic-number trick,
+// r = y - k ln2 in two pieces, Taylor polynomial of degree 13 on |r| <= 0.347 (truncation 5e-18),
+// scaled by an exponent add (y <= 40, so k <= 58); reciprocal: MUFU seed + two Newton steps.
+// Absolute error <= 2e-16 (it is a difference from 1, so tiny |x| lose RELATIVE accuracy; the
+// activations enter every result additively next to O(1) terms, far inside the 1e-10 parity bar).
+#ifndef QCP_FAST_TANH
+#define QCP_FAST_TANH 1
+#endif
+__device__ __forceinline__ double tanh_branchfree(double x) {
+  const double y = fmin(fabs(x) * 2.0, 40.0);
+  const double magic = 6755399441055744.0;                    // 1.5 * 2^52
+  const double kf = fma(y, 1.4426950408889634074, magic);
+  const int k = __double2loint(kf);
+  const double kd = kf - magic;
+  double r = fma(kd, -6.93147180369123816490e-01, y);
+  r = fma(kd, -1.90821492927058770002e-10, r);
+  double p = 1.6059043836821614599e-10;                       // 1/13!
+  p = fma(p, r, 2.0876756987868098979e-09);                   // 1/12!
+  p = fma(p, r, 2.5052108385441718775e-08);                   // 1/11!
+  p = fma(p, r, 2.7557319223985890653e-07);                   // 1/10!
+  p = fma(p, r, 2.7557319223985892511e-06);                   // 1/9!
+  p = fma(p, r, 2.4801587301587301566e-05);                   // 1/8!
+  p = fma(p, r, 1.9841269841269841253e-04);                   // 1/7!
+  p = fma(p, r, 1.3888888888888889419e-03);                   // 1/6!
+  p = fma(p, r, 8.3333333333333332177e-03);                   // 1/5!
+  p = fma(p, r, 4.1666666666666664354e-02);                   // 1/4!
+  p = fma(p, r, 1.6666666666666665741e-01);                   // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const double e = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+  const double d = e + 1.0;
+  double inv;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(d));
+  double t = fma(-d, inv, 1.0);
+  inv = fma(inv, t, inv);
+  t = fma(-d, inv, 1.0);
+  inv = fma(inv, t, inv);
+  const double th = copysign(fma(-2.0, inv, 1.0), x);
+  return x != x ? x : th;                                     // NaN in, NaN out (like libm)
+}
+
 template <>
 struct Math<double> {
-  static __device__ __forceinline__ double tanh_(double x) { return tanh(x); }
+  static __device__ __forceinline__ double tanh_(double x) {
+#if QCP_FAST_TANH
+    return tanh_branchfree(x);
+#else
+    return tanh(x);
+#endif
+  }
   static __device__ __forceinline__ void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
 };
 

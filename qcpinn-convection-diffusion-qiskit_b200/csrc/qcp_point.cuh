@@ -51,6 +51,17 @@ namespace qcp {
 #define QCP_TUNE_F32_1 4444401
 #endif
 
+// roll the loop over the output qubit i inside the contraction adjoint (the body is ~170 FMAs; with
+// i unrolled the float64 residual kernel is 21 k SASS instructions = 336 KB, far beyond the
+// instruction caches: `no_instruction` was its second largest stall).  digits: F64 F32
+#ifndef QCP_ROLL_I
+#define QCP_ROLL_I 0
+#endif
+template <typename T>
+struct RollI { static constexpr bool value = ((QCP_ROLL_I) % 10) != 0; };
+template <>
+struct RollI<double> { static constexpr bool value = (((QCP_ROLL_I) / 10) % 10) != 0; };
+
 template <int V>
 struct TuneValues {
   static constexpr int kFwd = (V / 1000000) % 10, kFused = (V / 100000) % 10,
@@ -188,9 +199,12 @@ __device__ __forceinline__ Jet<T, S> pre_activation(const Vec4<T>& w, const T (&
   return a;
 }
 
+// `act` (optional): the tanh values of the hidden units are stored at act[k * B] (the caller has
+// already offset the pointer by the point index), so that the split backward does not have to
+// evaluate tanh again (in float64 a tanh is ~35 FP64-pipe instructions, a third of an adjoint step)
 template <typename T, int NQ, int S>
 __device__ __forceinline__ void pre_forward(const SmemWeights<T>& s, int H, const T (&X)[3],
-                                            Jet<T, S> (&z)[NQ]) {
+                                            Jet<T, S> (&z)[NQ], T* act = nullptr, long long B = 0) {
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {
     jzero(z[j]);
@@ -202,6 +216,7 @@ __device__ __forceinline__ void pre_forward(const SmemWeights<T>& s, int H, cons
     const Vec4<T> w2 = s.w2t[k];
     const Jet<T, S> a = pre_activation<T, S>(w, X);
     const T h0 = Math<T>::tanh_(a.c[0]);
+    if (act) act[(size_t)k * B] = h0;
     const T f1 = fma(-h0, h0, T(1));
     const T f2 = T(-2) * h0 * f1;
     const Jet<T, S> h = jfunc(a, h0, f1, f2);
@@ -215,7 +230,8 @@ __device__ __forceinline__ void pre_forward(const SmemWeights<T>& s, int H, cons
 // ------------------------------------------------------------------------------------------
 template <typename T, int NQ, int S>
 __device__ __forceinline__ void post_forward(const SmemWeights<T>& s, int H,
-                                             const Jet<T, S> (&q)[NQ], Jet<T, S>& u) {
+                                             const Jet<T, S> (&q)[NQ], Jet<T, S>& u,
+                                             T* act = nullptr, long long B = 0) {
   jzero(u);
   u.c[0] = s.b4[0];
 #pragma unroll 2
@@ -228,6 +244,7 @@ __device__ __forceinline__ void post_forward(const SmemWeights<T>& s, int H,
 #pragma unroll
     for (int i = 0; i < NQ; ++i) jaxpy(p, w3.v[i], q[i]);
     const T g0 = Math<T>::tanh_(p.c[0]);
+    if (act) act[(size_t)k * B] = g0;
     const T f1 = fma(-g0, g0, T(1));
     const T f2 = T(-2) * g0 * f1;
     const Jet<T, S> g = jfunc(p, g0, f1, f2);
@@ -514,15 +531,55 @@ struct Stager {
 };
 
 // ------------------------------------------------------------------------------------------
+// saved activations (workspace slot 2: act[2H][B], pre-MLP tanh values then post-MLP ones).  The
+// reader keeps kActAhead values in flight so the HBM latency of act[k * B] hides behind the
+// adjoint steps of the previous hidden units.
+// ------------------------------------------------------------------------------------------
+constexpr int kActAhead = 4;
+
+template <typename T>
+__device__ __forceinline__ void tanh_derivs_saved(T f0, T& f1, T& f2, T& f3) {
+  f1 = fma(-f0, f0, T(1));
+  f2 = T(-2) * f0 * f1;
+  f3 = f1 * fma(T(6) * f0, f0, T(-2));
+}
+
+// for_hidden<T, SAVED>(H, act, B, body): body(k, saved tanh value of unit k) for k = 0..H-1;
+// SAVED = false passes zeros that the body ignores (it evaluates tanh itself then)
+template <typename T, bool SAVED, typename Body>
+__device__ __forceinline__ void for_hidden(int H, const T* act, long long B, Body&& body) {
+  if constexpr (!SAVED) {
+    for (int k = 0; k < H; ++k) body(k, T(0));
+    return;
+  }
+  T nxt[kActAhead];
+#pragma unroll
+  for (int j = 0; j < kActAhead; ++j) nxt[j] = j < H ? act[(size_t)j * B] : T(0);
+  for (int k0 = 0; k0 < H; k0 += kActAhead) {
+    T cur[kActAhead];
+#pragma unroll
+    for (int j = 0; j < kActAhead; ++j) {
+      cur[j] = nxt[j];
+      const int kn = k0 + kActAhead + j;
+      nxt[j] = kn < H ? act[(size_t)kn * B] : T(0);
+    }
+#pragma unroll
+    for (int j = 0; j < kActAhead; ++j)
+      if (k0 + j < H) body(k0 + j, cur[j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // reverse sweeps
 // ------------------------------------------------------------------------------------------
-template <typename T, int NQ, int S>
+template <typename T, int NQ, int S, bool SAVED = false>
 __device__ __forceinline__ void post_backward(const SmemWeights<T>& s, int H,
                                               const Jet<T, S> (&q)[NQ], const Jet<T, S>& ub,
-                                              Jet<T, S> (&qb)[NQ], Stager<T>& st) {
+                                              Jet<T, S> (&qb)[NQ], Stager<T>& st,
+                                              const T* act = nullptr, long long B = 0) {
 #pragma unroll
   for (int i = 0; i < NQ; ++i) jzero(qb[i]);
-  for (int k = 0; k < H; ++k) {
+  for_hidden<T, SAVED>(H, act, B, [&](int k, T saved) {
     const Vec4<T> w3 = s.w3[k];
     const T b3 = s.b3w4[2 * k], w4 = s.b3w4[2 * k + 1];
     Jet<T, S> p;
@@ -531,7 +588,8 @@ __device__ __forceinline__ void post_backward(const SmemWeights<T>& s, int H,
 #pragma unroll
     for (int i = 0; i < NQ; ++i) jaxpy(p, w3.v[i], q[i]);
     T g0, f1, f2, f3;
-    tanh_derivs(p.c[0], g0, f1, f2, f3);
+    if constexpr (SAVED) { g0 = saved; tanh_derivs_saved(g0, f1, f2, f3); }
+    else tanh_derivs(p.c[0], g0, f1, f2, f3);
     const Jet<T, S> g = jfunc(p, g0, f1, f2);
     Jet<T, S> gb;
 #pragma unroll
@@ -546,7 +604,18 @@ __device__ __forceinline__ void post_backward(const SmemWeights<T>& s, int H,
     st.put(jdot(ub, g));                                  // d w4[k]
 #pragma unroll
     for (int i = 0; i < NQ; ++i) jaxpy(qb[i], w3.v[i], pb);
+  });
+}
+
+// qb[i] for a runtime (warp-uniform) i without indexing the register array
+template <typename T, int NQ, int S>
+__device__ __forceinline__ Jet<T, S> jet_pick(const Jet<T, S> (&v)[NQ], int i) {
+  Jet<T, S> r = v[0];
+#pragma unroll
+  for (int k = 1; k < NQ; ++k) {
+    if (i == k) r = v[k];
   }
+  return r;
 }
 
 // Adjoint of features + contraction for one jet layout.  Pushes d C in (a, i, b) order and ADDS
@@ -571,16 +640,15 @@ __device__ __forceinline__ void angle_backward(const T* sC, const Jet<T, S> (&z)
     pa.set2(f, t0, t1);
     Jet<T, S> pab;
     jzero(pab);
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) {
+    auto step = [&](int i, const Jet<T, S>& qbi) {
       CRow<T, NQ> c;
       c.load(sC, a, i);
       // D = pullback of qb_i through the multiplication by P_a
       Jet<T, S> D;
       jzero(D);
-      jmul_pull_acc(D, qb[i], pa.p);
+      jmul_pull_acc(D, qbi, pa.p);
       const Jet<T, S> t = contract_row<T, NQ, S>(c, f.Q);
-      jmul_pull_acc(pab, qb[i], t);
+      jmul_pull_acc(pab, qbi, t);
       st.reserve(A::FB);
       st.put(D.c[0]);                                      // d C[i, a, 0]  (Q[0] == 1)
 #pragma unroll
@@ -588,6 +656,13 @@ __device__ __forceinline__ void angle_backward(const T* sC, const Jet<T, S> (&z)
         st.put(jdot(D, f.Q[b]));                           // d C[i, a, b]
         jaxpy(Qb[b], c.at(b), D);
       }
+    };
+    if constexpr (RollI<T>::value && S != 1) {
+#pragma unroll 1
+      for (int i = 0; i < NQ; ++i) step(i, jet_pick<T, NQ, S>(qb, i));   // i is warp uniform
+    } else {
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) step(i, qb[i]);
     }
     pa.pull(pab, yb, wb);
   };
@@ -721,20 +796,22 @@ __device__ __forceinline__ void feature_forward(const T* sC, const Jet<T, S> (&z
   }
 }
 
-template <typename T, int NQ, int S>
+template <typename T, int NQ, int S, bool SAVED = false>
 __device__ __forceinline__ void pre_backward(const SmemWeights<T>& s, int H, const T (&X)[3],
                                              const Jet<T, S> (&zb)[NQ], T (&Xb)[3],
-                                             Stager<T>& st) {
+                                             Stager<T>& st, const T* act = nullptr,
+                                             long long B = 0) {
   st.reserve(NQ);
 #pragma unroll
   for (int j = 0; j < NQ; ++j) st.put(zb[j].c[0]);          // d b2[j]
   Xb[0] = Xb[1] = Xb[2] = T(0);
-  for (int k = 0; k < H; ++k) {
+  for_hidden<T, SAVED>(H, act, B, [&](int k, T saved) {
     const Vec4<T> w = s.w1b[k];
     const Vec4<T> w2 = s.w2t[k];
     const Jet<T, S> a = pre_activation<T, S>(w, X);
     T h0, f1, f2, f3;
-    tanh_derivs(a.c[0], h0, f1, f2, f3);
+    if constexpr (SAVED) { h0 = saved; tanh_derivs_saved(h0, f1, f2, f3); }
+    else tanh_derivs(a.c[0], h0, f1, f2, f3);
     const Jet<T, S> h = jfunc(a, h0, f1, f2);
     Jet<T, S> hb;
     jzero(hb);
@@ -754,7 +831,7 @@ __device__ __forceinline__ void pre_backward(const SmemWeights<T>& s, int H, con
     st.put(ab.c[0]);                                       // d b1[k]
 #pragma unroll
     for (int j = 0; j < NQ; ++j) st.put(jdot(zb[j], h));    // d w2[j,k]
-  }
+  });
 }
 
 // ------------------------------------------------------------------------------------------
@@ -780,6 +857,16 @@ __device__ __forceinline__ void ws_load(const T* ws, long long B, int slot, long
   for (int j = 0; j < NQ; ++j)
 #pragma unroll
     for (int c = 0; c < S; ++c) v[j].c[c] = base[(size_t)(j * S + c) * B];
+}
+
+// slot 2 of the workspace: saved tanh values act[2H][B] behind the two jet slots
+template <typename T, int NQ, int S>
+__device__ __forceinline__ T* ws_act(T* ws, long long B) {
+  return ws + (size_t)2 * NQ * S * B;
+}
+template <typename T, int NQ, int S>
+__device__ __forceinline__ const T* ws_act(const T* ws, long long B) {
+  return ws + (size_t)2 * NQ * S * B;
 }
 
 // cotangent seed of the outputs: (grad_u, grad_r) -> jet cotangent of u
@@ -848,11 +935,12 @@ solver_forward_kernel(const SolverArgs a) {
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < a.B; p += stride) {
     T X[3] = {(T)Xg[3 * p], (T)Xg[3 * p + 1], (T)Xg[3 * p + 2]};
     Jet<T, S> z[NQ], q[NQ], u;
-    pre_forward<T, NQ, S>(sw, H, X, z);
+    T* act = (SaveAct<T>::value && wsg) ? ws_act<T, NQ, S>(wsg, a.B) + p : nullptr;
+    pre_forward<T, NQ, S>(sw, H, X, z, act, a.B);
     if (wsg) ws_store<T, NQ, S>(wsg, a.B, 0, p, z);
     feature_forward<T, NQ, ENC, S>(sw.C, z, q);
     if (wsg) ws_store<T, NQ, S>(wsg, a.B, 1, p, q);
-    post_forward<T, NQ, S>(sw, H, q, u);
+    post_forward<T, NQ, S>(sw, H, q, u, act ? act + (size_t)H * a.B : nullptr, a.B);
     ug[p] = (TIO)u.c[0];
     if constexpr (S == 6) {
       if (rg) {
@@ -944,7 +1032,8 @@ post_backward_kernel(const SolverArgs a) {
     ws_load<T, NQ, S>(wsg, a.B, 1, p, q);
     st.begin();
     st.put(ub.c[0]);                                       // d b4
-    post_backward<T, NQ, S>(sw, H, q, ub, qb, st);
+    post_backward<T, NQ, S, SaveAct<T>::value>(sw, H, q, ub, qb, st,
+                                  ws_act<T, NQ, S>(wsg, a.B) + (size_t)H * a.B + p, a.B);
     st.flush();
     if (valid) ws_store<T, NQ, S>(wsg, a.B, 1, p, qb);
   }
@@ -1018,7 +1107,8 @@ pre_backward_kernel(const SolverArgs a) {
     }
     T Xb[3];
     st.begin();
-    pre_backward<T, NQ, S>(sw, H, X, zb, Xb, st);
+    pre_backward<T, NQ, S, SaveAct<T>::value>(sw, H, X, zb, Xb, st,
+                                              ws_act<T, NQ, S>(wsg, a.B) + p, a.B);
     st.flush();
     if (gXg && valid) {
       gXg[3 * p] = (TIO)Xb[0]; gXg[3 * p + 1] = (TIO)Xb[1]; gXg[3 * p + 2] = (TIO)Xb[2];

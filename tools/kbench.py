@@ -11,7 +11,10 @@ ansatz = sys.argv[2] if len(sys.argv) > 2 else "cascade"
 dev = torch.device("cuda", 0)
 prog = qb.program.compile_program(ansatz, 4, 1, None)
 out = {}
+only = os.environ.get("KBENCH_DTYPES", "f64,f32").split(",")
 for dt, name in ((torch.float64, "f64"), (torch.float32, "f32")):
+    if name not in only:
+        continue
     plan = F.Plan(prog, 0, dt, 50, dev)
     torch.manual_seed(0)
     X = torch.rand(pts, 3, device=dev, dtype=dt)
