@@ -54,6 +54,10 @@ namespace qcp {
 // roll the loop over the output qubit i inside the contraction adjoint (the body is ~170 FMAs; with
 // i unrolled the float64 residual kernel is 21 k SASS instructions = 336 KB, far beyond the
 // instruction caches: `no_instruction` was its second largest stall).  digits: F64 F32
+// split contraction adjoint in two-pass mode: stream the sub-jet components through the workspace
+#ifndef QCP_STREAM_PASSES
+#define QCP_STREAM_PASSES 1
+#endif
 #ifndef QCP_ROLL_I
 #define QCP_ROLL_I 0
 #endif
@@ -343,26 +347,31 @@ struct PA {
 
 // loop over the A-half feature index a = 3*s0 + s1 (or a = s0 for a one-qubit half), rolled /
 // unrolled per Tune<>::kRollMode; body(a, s0, s1)
-template <typename T, int NQ, int S, typename Body>
-__device__ __forceinline__ void for_each_a(Body&& body) {
+struct NoOp { __device__ __forceinline__ void operator()() const {} };
+
+template <typename T, int NQ, int S, typename Body, typename After = NoOp>
+__device__ __forceinline__ void for_each_a(Body&& body, After&& after_rolled = After{}) {
+  // after_rolled(): runs at the end of every iteration of a ROLLED loop (lets the caller bring
+  // loop-carried state, e.g. the staging row counter, back to a compile-time known value)
   using A = AngleShape<NQ>;
   constexpr int mode = Tune<T, (S == 1 ? 1 : 6)>::kRollMode;
   if constexpr (A::NA == 1) {
     if constexpr (mode == 1) {
 #pragma unroll 1
-      for (int a = 0; a < 3; ++a) body(a, a, 0);
+      for (int a = 0; a < 3; ++a) { body(a, a, 0); after_rolled(); }
     } else {
 #pragma unroll
       for (int a = 0; a < 3; ++a) body(a, a, 0);
     }
   } else if constexpr (mode == 1) {
 #pragma unroll 1
-    for (int a = 0; a < 9; ++a) body(a, a / 3, a % 3);
+    for (int a = 0; a < 9; ++a) { body(a, a / 3, a % 3); after_rolled(); }
   } else if constexpr (mode == 2) {
 #pragma unroll 1
     for (int t0 = 0; t0 < 3; ++t0) {
 #pragma unroll
       for (int t1 = 0; t1 < 3; ++t1) body(3 * t0 + t1, t0, t1);
+      after_rolled();
     }
   } else {
 #pragma unroll
@@ -666,7 +675,11 @@ __device__ __forceinline__ void angle_backward(const T* sC, const Jet<T, S> (&z)
     }
     pa.pull(pab, yb, wb);
   };
-  for_each_a<T, NQ, S>(body);
+  // rolled variants: close the staging tile at the end of every rolled iteration, so that inside
+  // the iteration the row counter is a compile-time constant again (immediate-offset STS, no
+  // per-put address arithmetic or reserve() branches)
+  st.flush();
+  for_each_a<T, NQ, S>(body, [&]() { st.flush(); });
   prod_pull<T, S, A::NB>(Qb, f.y + A::NA, f.w + A::NA, yb + A::NA, wb + A::NA);
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {
@@ -780,6 +793,69 @@ __device__ __forceinline__ void feature_backward(const T* sC, const Jet<T, S> (&
     angle_forward<T, NQ, S>(z, f);
     angle_backward<T, NQ, S>(sC, z, f, qb, zb, st);
   }
+}
+
+// Two-pass S = 6 contraction adjoint of the SPLIT kernel, streaming through the workspace: each
+// sub-jet pass loads just its own components of z (slot 0) and qb (slot 1) and stores its own
+// components of zb (slot 0) right away, so no full 6-component jets stay live across the passes
+// (the register-array version keeps z, qb and zb = 72 doubles alive and spills ~1 KB per thread).
+// Slot 0 is overwritten component by component: a pass only overwrites derivative components it
+// has loaded itself; the value component (needed by every pass for nothing but sin / cos, which
+// are taken first) is written by the last pass from the sum of the partial value cotangents.
+template <typename T, int NQ>
+__device__ __forceinline__ void angle_backward_ws(const T* sC, T* ws, long long B, long long p,
+                                                  bool valid, Stager<T>& st) {
+  constexpr int S = 6;
+  T* zrow = ws + p;                                   // slot 0, component-major
+  const T* qrow = ws + (size_t)NQ * S * B + p;        // slot 1
+  T sn[NQ], cs[NQ], zb0[NQ];
+  {
+    T z0[NQ];
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) { z0[j] = zrow[(size_t)(j * S) * B]; zb0[j] = T(0); }
+    angle_sincos<T, NQ>(z0, sn, cs);
+  }
+  st.flush();                  // all passes must start at the same accumulator index
+  const int base0 = st.base;
+  auto pass = [&](auto tag, const int (&idx)[decltype(tag)::value], bool carry_value, bool last) {
+    constexpr int SS = decltype(tag)::value;
+    Jet<T, SS> zs[NQ], qs[NQ], zbs[NQ];
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+#pragma unroll
+      for (int c = 0; c < SS; ++c) {
+        zs[j].c[c] = zrow[(size_t)(j * S + idx[c]) * B];
+        qs[j].c[c] = valid ? qrow[(size_t)(j * S + idx[c]) * B] : T(0);
+      }
+      if (!carry_value) qs[j].c[0] = T(0);
+      jzero(zbs[j]);
+    }
+    AngleFeat<T, NQ, SS> f;
+    angle_features<T, NQ, SS>(zs, sn, cs, f);
+    angle_backward<T, NQ, SS>(sC, zs, f, qs, zbs, st);
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      zb0[j] += zbs[j].c[0];
+      if (valid) {
+#pragma unroll
+        for (int c = 1; c < SS; ++c) zrow[(size_t)(j * S + idx[c]) * B] = zbs[j].c[c];
+        if (last) zrow[(size_t)(j * S) * B] = zb0[j];
+      }
+    }
+    st.flush();
+    st.base = base0;           // the next pass adds onto the same accumulator segment
+  };
+  if constexpr (Tune<T, S>::kPasses == 1) {
+    const int ix[4] = {0, 1, 2, 4}, iy[3] = {0, 3, 5};
+    pass(std::integral_constant<int, 4>{}, ix, true, false);
+    pass(std::integral_constant<int, 3>{}, iy, false, true);
+  } else {
+    const int it[2] = {0, 1}, ix[3] = {0, 2, 4}, iy[3] = {0, 3, 5};
+    pass(std::integral_constant<int, 3>{}, ix, true, false);
+    pass(std::integral_constant<int, 3>{}, iy, false, false);
+    pass(std::integral_constant<int, 2>{}, it, false, true);
+  }
+  st.base = base0 + nacc_contract(NQ, QCP_ENC_ANGLE);
 }
 
 template <typename T, int NQ, int ENC, int S>
@@ -1060,17 +1136,22 @@ contract_backward_kernel(const SolverArgs a) {
   for (long long p0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; p0 < Bpad; p0 += stride) {
     const bool valid = p0 < a.B;
     const long long p = valid ? p0 : a.B - 1;
-    Jet<T, S> z[NQ], qb[NQ], zb[NQ];
-    ws_load<T, NQ, S>(wsg, a.B, 0, p, z);
-    ws_load<T, NQ, S>(wsg, a.B, 1, p, qb);
-    if (!valid) {
-#pragma unroll
-      for (int i = 0; i < NQ; ++i) jzero(qb[i]);
-    }
     st.begin();
-    feature_backward<T, NQ, ENC, S>(sC, z, qb, zb, st);
-    st.flush();
-    if (valid) ws_store<T, NQ, S>(wsg, a.B, 0, p, zb);
+    if constexpr (ENC == QCP_ENC_ANGLE && S == 6 && Tune<T, S>::kTwoPass && QCP_STREAM_PASSES) {
+      angle_backward_ws<T, NQ>(sC, wsg, a.B, p, valid, st);
+      st.flush();
+    } else {
+      Jet<T, S> z[NQ], qb[NQ], zb[NQ];
+      ws_load<T, NQ, S>(wsg, a.B, 0, p, z);
+      ws_load<T, NQ, S>(wsg, a.B, 1, p, qb);
+      if (!valid) {
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) jzero(qb[i]);
+      }
+      feature_backward<T, NQ, ENC, S>(sC, z, qb, zb, st);
+      st.flush();
+      if (valid) ws_store<T, NQ, S>(wsg, a.B, 0, p, zb);
+    }
   }
   write_partials<T>(acc_all, nacc, static_cast<T*>(a.partials));
 }
