@@ -352,6 +352,8 @@ struct ScatterArgs {
   const void* seg_ptr[kMaxPending][3];
   int seg_grid[kMaxPending][3];
   int fused[kMaxPending];   // 1: the call's partials are one [grid][nacc] array (fused kernel)
+  int idx_begin, idx_end;   // accumulator window of this launch ([0, nacc) = everything)
+  int skip_begin, skip_end; // ... minus this window (already reduced by an earlier launch)
   int seg_len[3];
 };
 
@@ -362,9 +364,10 @@ __global__ void __launch_bounds__(32 * kReduceSlices)
 reduce_solver_kernel(const ScatterArgs a) {
   __shared__ double part[kReduceSlices][33];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  const int idx = blockIdx.x * 32 + lane;
+  const int idx = a.idx_begin + blockIdx.x * 32 + lane;
+  const bool live = idx < a.idx_end && !(idx >= a.skip_begin && idx < a.skip_end);
   double s = 0.0;
-  if (idx < a.nacc) {
+  if (live) {
     int seg = 0, local = idx;
     while (seg < 2 && local >= a.seg_len[seg]) { local -= a.seg_len[seg]; ++seg; }
     const int len = a.seg_len[seg];
@@ -382,7 +385,7 @@ reduce_solver_kernel(const ScatterArgs a) {
   }
   part[slice][lane] = s;
   __syncthreads();
-  if (slice != 0 || idx >= a.nacc) return;
+  if (slice != 0 || !live) return;
 #pragma unroll
   for (int k = 1; k < kReduceSlices; ++k) s += part[k][lane];
   const int n = a.n, H = a.H;
@@ -667,6 +670,13 @@ struct qcp_plan {
   // deferred reduction: kernels of up to kMaxPending backward calls, one reduce + theta_grad
   int pending;
   size_t pending_used;      // elements of d_partials handed out so far
+  // theta-gradient overlap: d C is complete after the contraction adjoints, so its reduction and
+  // theta_grad (single-CTA, latency bound) run on `aux` next to the pre-MLP adjoints
+  cudaStream_t aux;
+  cudaEvent_t ev_contract[kMaxPending];
+  cudaEvent_t ev_theta;
+  bool pend_split[kMaxPending];
+  bool overlap_theta;       // QCP_THETA_OVERLAP != 0 (default on)
   const void* pend_ptr[kMaxPending][3];
   int pend_grid[kMaxPending][3];
   int pend_fused[kMaxPending];
@@ -806,6 +816,10 @@ int qcp_plan_create(qcp_plan_t** out, int n_qubits, int encoding, int dtype, int
   p->n = n_qubits; p->enc = encoding; p->dtype = dtype; p->H = hidden;
   p->n_ops = n_ops; p->n_consts = n_consts; p->n_theta = n_theta;
   p->engine_l = n_qubits > kMaxQubitsFused;
+  {
+    const char* ov = getenv("QCP_THETA_OVERLAP");
+    p->overlap_theta = !(ov && ov[0] == '0');
+  }
   p->F = p->engine_l ? 0 : num_features(n_qubits, encoding);
   p->M = 1 << n_qubits;
   cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -829,6 +843,10 @@ int qcp_plan_create(qcp_plan_t** out, int n_qubits, int encoding, int dtype, int
                       (size_t)nacc_solver(n_qubits, encoding, hidden);
     alloc((void**)&p->d_partials, pe * elem_size(dtype));
     if (e == cudaSuccess) p->partials_elems = pe;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->aux, cudaStreamNonBlocking);
+    for (int k = 0; k < kMaxPending && e == cudaSuccess; ++k)
+      e = cudaEventCreateWithFlags(&p->ev_contract[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_theta, cudaEventDisableTiming);
   }
   if (e == cudaSuccess && n_ops) e = cudaMemcpy(p->d_ops, ops, sizeof(GateOp) * n_ops, cudaMemcpyHostToDevice);
   if (e == cudaSuccess && n_consts)
@@ -856,6 +874,9 @@ int qcp_plan_destroy(qcp_plan_t* p) {
   cudaFree(p->d_ops); cudaFree(p->d_consts); cudaFree(p->d_V); cudaFree(p->d_O); cudaFree(p->d_Lam);
   cudaFree(p->d_C64); cudaFree(p->d_C); cudaFree(p->d_Cbar); cudaFree(p->d_partials);
   cudaFree(p->d_theta); cudaFree(p->d_ws); cudaFree(p->d_slab); cudaFree(p->d_theta_partials);
+  if (p->aux) cudaStreamDestroy(p->aux);
+  for (int k = 0; k < kMaxPending; ++k) if (p->ev_contract[k]) cudaEventDestroy(p->ev_contract[k]);
+  if (p->ev_theta) cudaEventDestroy(p->ev_theta);
   reg_destroy(p->reg);
   tile_destroy(p->tile);
   delete p;
@@ -1222,9 +1243,11 @@ int qcp_solver_backward_add(qcp_plan_t* p, const qcp_mlp_t* w, const void* X, co
     const size_t e0 = (size_t)gr.post * n0, e1 = (size_t)gr.contract * n1, e2 = (size_t)gr.pre * n2;
     if (check_partials_room(p, e0 + e1 + e2, "qcp_solver_backward_add")) return 1;
     void* p0 = base; void* p1 = base + e0 * es; void* p2 = base + (e0 + e1) * es;
-    int rc = f64 ? launch_solver_backward_split<double>(p->n, p->enc, mode, a, gr, p0, p1, p2, s)
-                 : launch_solver_backward_split<float>(p->n, p->enc, mode, a, gr, p0, p1, p2, s);
+    cudaEvent_t ev = p->overlap_theta ? p->ev_contract[k] : nullptr;
+    int rc = f64 ? launch_solver_backward_split<double>(p->n, p->enc, mode, a, gr, p0, p1, p2, s, ev)
+                 : launch_solver_backward_split<float>(p->n, p->enc, mode, a, gr, p0, p1, p2, s, ev);
     if (rc) return rc;
+    p->pend_split[k] = true;
     p->pend_ptr[k][0] = p0; p->pend_grid[k][0] = gr.post;
     p->pend_ptr[k][1] = p1; p->pend_grid[k][1] = gr.contract;
     p->pend_ptr[k][2] = p2; p->pend_grid[k][2] = gr.pre;
@@ -1245,6 +1268,7 @@ int qcp_solver_backward_add(qcp_plan_t* p, const qcp_mlp_t* w, const void* X, co
     // a fused array [grid][nacc] is not segment-major: flagged so the reduce reads pitch nacc
     for (int q = 0; q < 3; ++q) { p->pend_ptr[k][q] = base; p->pend_grid[k][q] = grid; }
     p->pend_fused[k] = 1;
+    p->pend_split[k] = false;
     p->pending_used += (size_t)grid * nacc;
   }
   p->pending = k + 1;
@@ -1279,13 +1303,35 @@ int qcp_solver_backward_finish(qcp_plan_t* p, const void* theta, const qcp_mlp_t
       for (int k = 0; k < 3; ++k) { sc.seg_ptr[c][k] = p->pend_ptr[c][k]; sc.seg_grid[c][k] = p->pend_grid[c][k]; }
     }
   }
-  const int rb = (nacc + 31) / 32;
-  if (f64) reduce_solver_kernel<double><<<rb, 32 * kReduceSlices, 0, s>>>(sc);
-  else reduce_solver_kernel<float><<<rb, 32 * kReduceSlices, 0, s>>>(sc);
-  QCP_CUDA(cudaGetLastError());
+  sc.idx_begin = 0; sc.idx_end = nacc; sc.skip_begin = sc.skip_end = 0;
+  bool overlap = p->overlap_theta && p->pending > 0;
+  for (int c = 0; c < p->pending; ++c) overlap = overlap && p->pend_split[c];
+  const int npend = p->pending;
   p->pending = 0;
   p->pending_used = 0;
-  return run_theta_grad(p, theta, grad_theta, s);
+  auto reduce = [&](const ScatterArgs& args, cudaStream_t st) -> int {
+    const int rb = (args.idx_end - args.idx_begin + 31) / 32;
+    if (f64) reduce_solver_kernel<double><<<rb, 32 * kReduceSlices, 0, st>>>(args);
+    else reduce_solver_kernel<float><<<rb, 32 * kReduceSlices, 0, st>>>(args);
+    QCP_CUDA(cudaGetLastError());
+    return 0;
+  };
+  if (!overlap) {
+    if (reduce(sc, s)) return 1;
+    return run_theta_grad(p, theta, grad_theta, s);
+  }
+  // aux: wait for every call's contraction adjoint, reduce the d C window, run theta_grad; the
+  // caller's stream meanwhile finishes the pre-MLP adjoints, reduces the other windows and joins
+  for (int c = 0; c < npend; ++c) QCP_CUDA(cudaStreamWaitEvent(p->aux, p->ev_contract[c], 0));
+  ScatterArgs sc_c = sc;
+  sc_c.idx_begin = sc.seg_len[0]; sc_c.idx_end = sc.seg_len[0] + sc.seg_len[1];
+  if (reduce(sc_c, p->aux)) return 1;
+  if (run_theta_grad(p, theta, grad_theta, p->aux)) return 1;
+  QCP_CUDA(cudaEventRecord(p->ev_theta, p->aux));
+  sc.skip_begin = sc_c.idx_begin; sc.skip_end = sc_c.idx_end;
+  if (reduce(sc, s)) return 1;
+  QCP_CUDA(cudaStreamWaitEvent(s, p->ev_theta, 0));
+  return 0;
 }
 
 int qcp_solver_backward(qcp_plan_t* p, const qcp_mlp_t* w, const void* theta, const void* X,
@@ -1338,6 +1384,7 @@ int qcp_solver_backward(qcp_plan_t* p, const qcp_mlp_t* w, const void* theta, co
     QCP_CUDA(cudaMemsetAsync(grad_theta, 0, es * p->n_theta, s));
   }
   sc.nacc = n0 + n2;
+  sc.idx_begin = 0; sc.idx_end = sc.nacc; sc.skip_begin = sc.skip_end = 0;
   sc.calls = 1;
   sc.seg_len[0] = n0; sc.seg_len[1] = 0; sc.seg_len[2] = n2;
   sc.seg_ptr[0][0] = p0; sc.seg_grid[0][0] = gb;

@@ -349,12 +349,12 @@ struct PA {
 // unrolled per Tune<>::kRollMode; body(a, s0, s1)
 struct NoOp { __device__ __forceinline__ void operator()() const {} };
 
-template <typename T, int NQ, int S, typename Body, typename After = NoOp>
+template <typename T, int NQ, int S, int MODE = -1, typename Body = NoOp, typename After = NoOp>
 __device__ __forceinline__ void for_each_a(Body&& body, After&& after_rolled = After{}) {
   // after_rolled(): runs at the end of every iteration of a ROLLED loop (lets the caller bring
   // loop-carried state, e.g. the staging row counter, back to a compile-time known value)
   using A = AngleShape<NQ>;
-  constexpr int mode = Tune<T, (S == 1 ? 1 : 6)>::kRollMode;
+  constexpr int mode = MODE >= 0 ? MODE : Tune<T, (S == 1 ? 1 : 6)>::kRollMode;
   if constexpr (A::NA == 1) {
     if constexpr (mode == 1) {
 #pragma unroll 1
@@ -629,7 +629,7 @@ __device__ __forceinline__ Jet<T, S> jet_pick(const Jet<T, S> (&v)[NQ], int i) {
 
 // Adjoint of features + contraction for one jet layout.  Pushes d C in (a, i, b) order and ADDS
 // the pulled-back cotangent into zb (so sub-jet passes can accumulate).
-template <typename T, int NQ, int S>
+template <typename T, int NQ, int S, int MODE = -1>
 __device__ __forceinline__ void angle_backward(const T* sC, const Jet<T, S> (&z)[NQ],
                                                const AngleFeat<T, NQ, S>& f,
                                                const Jet<T, S> (&qb)[NQ], Jet<T, S> (&zb)[NQ],
@@ -679,7 +679,7 @@ __device__ __forceinline__ void angle_backward(const T* sC, const Jet<T, S> (&z)
   // the iteration the row counter is a compile-time constant again (immediate-offset STS, no
   // per-put address arithmetic or reserve() branches)
   st.flush();
-  for_each_a<T, NQ, S>(body, [&]() { st.flush(); });
+  for_each_a<T, NQ, S, MODE>(body, [&]() { st.flush(); });
   prod_pull<T, S, A::NB>(Qb, f.y + A::NA, f.w + A::NA, yb + A::NA, wb + A::NA);
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {
@@ -802,7 +802,7 @@ __device__ __forceinline__ void feature_backward(const T* sC, const Jet<T, S> (&
 // Slot 0 is overwritten component by component: a pass only overwrites derivative components it
 // has loaded itself; the value component (needed by every pass for nothing but sin / cos, which
 // are taken first) is written by the last pass from the sum of the partial value cotangents.
-template <typename T, int NQ>
+template <typename T, int NQ, int MODE = -1>
 __device__ __forceinline__ void angle_backward_ws(const T* sC, T* ws, long long B, long long p,
                                                   bool valid, Stager<T>& st) {
   constexpr int S = 6;
@@ -832,7 +832,7 @@ __device__ __forceinline__ void angle_backward_ws(const T* sC, T* ws, long long 
     }
     AngleFeat<T, NQ, SS> f;
     angle_features<T, NQ, SS>(zs, sn, cs, f);
-    angle_backward<T, NQ, SS>(sC, zs, f, qs, zbs, st);
+    angle_backward<T, NQ, SS, MODE>(sC, zs, f, qs, zbs, st);
 #pragma unroll
     for (int j = 0; j < NQ; ++j) {
       zb0[j] += zbs[j].c[0];
@@ -1116,7 +1116,9 @@ post_backward_kernel(const SolverArgs a) {
   write_partials<T>(acc_all, nacc, static_cast<T*>(a.partials));
 }
 
-template <typename T, int NQ, int ENC, int S>
+// MODE >= 0 overrides the A-half loop rolling of Tune<> (the small-batch variant, see
+// kRollSmallIters below)
+template <typename T, int NQ, int ENC, int S, int MODE = -1>
 __global__ void __launch_bounds__(kThreads, Tune<T, S>::kContract)
 contract_backward_kernel(const SolverArgs a) {
   extern __shared__ __align__(32) unsigned char smem_raw[];
@@ -1138,7 +1140,7 @@ contract_backward_kernel(const SolverArgs a) {
     const long long p = valid ? p0 : a.B - 1;
     st.begin();
     if constexpr (ENC == QCP_ENC_ANGLE && S == 6 && Tune<T, S>::kTwoPass && QCP_STREAM_PASSES) {
-      angle_backward_ws<T, NQ>(sC, wsg, a.B, p, valid, st);
+      angle_backward_ws<T, NQ, MODE>(sC, wsg, a.B, p, valid, st);
       st.flush();
     } else {
       Jet<T, S> z[NQ], qb[NQ], zb[NQ];
@@ -1406,10 +1408,24 @@ int solver_split_grids(int n, int enc, int mode, int H, int num_sms, SplitGrids*
   return 1;
 }
 
+#ifndef QCP_ROLL_SMALL_ITERS
+#define QCP_ROLL_SMALL_ITERS 20
+#endif
+constexpr long long kRollSmallIters = QCP_ROLL_SMALL_ITERS;
+// the small-batch variant exists where the default is the unrolled two-pass float64 kernel
+template <typename T, int NQ, int ENC>
+struct ContractSmall {
+  static constexpr bool value = std::is_same<T, double>::value && NQ == 4 && ENC == QCP_ENC_ANGLE &&
+                                Tune<T, 6>::kTwoPass && Tune<T, 6>::kRollMode == 0 &&
+                                (QCP_STREAM_PASSES != 0) && kRollSmallIters > 0;
+};
+
 template <typename T>
 int launch_solver_backward_split(int n, int enc, int mode, const SolverArgs& a, const SplitGrids& g,
                                  void* part_post, void* part_contract, void* part_pre,
-                                 cudaStream_t s) {
+                                 cudaStream_t s, cudaEvent_t after_contract) {
+  // after_contract (optional) is recorded between the contraction adjoint and the pre-MLP adjoint:
+  // d C is complete there, so the caller can reduce it and run theta_grad next to pre_backward
   SolverArgs a0 = a, a1 = a, a2 = a;
   a0.partials = part_post; a1.partials = part_contract; a2.partials = part_pre;
   const size_t m0 = split_smem<T>(0, n, enc, a.H), m1 = split_smem<T>(1, n, enc, a.H),
@@ -1417,11 +1433,20 @@ int launch_solver_backward_split(int n, int enc, int mode, const SolverArgs& a, 
   QCP_DISPATCH_NQ_ENC(n, enc, {
     if (mode == QCP_MODE_RESIDUAL) {
       if (QCP_IO_LAUNCH(post_backward_kernel, 6, g.post, m0, "post_backward", a0)) return 1;
-      if (launch_checked(&contract_backward_kernel<T, NQ, ENC, 6>, g.contract, m1, s, "contract_backward", a1)) return 1;
+      // few iterations per thread: the fully unrolled body (336 KB of SASS in float64) is fetched
+      // cold at every launch and the first pass over it costs as much as several warm ones, so a
+      // variant with the outer A-half trit loop rolled (3x less code) wins below ~20 iterations
+      // (measured: -4.7 % at 524 288 points, -13 % at 65 536, +2 % at 1 048 576, +8 % at 4 194 304)
+      const long long iters = (a.B + (long long)g.contract * kThreads - 1) / ((long long)g.contract * kThreads);
+      if (ContractSmall<T, NQ, ENC>::value && iters <= kRollSmallIters) {
+        if (launch_checked(&contract_backward_kernel<T, NQ, ENC, 6, 2>, g.contract, m1, s, "contract_backward", a1)) return 1;
+      } else if (launch_checked(&contract_backward_kernel<T, NQ, ENC, 6>, g.contract, m1, s, "contract_backward", a1)) return 1;
+      if (after_contract && cudaEventRecord(after_contract, s) != cudaSuccess) { set_error("cudaEventRecord failed"); return 1; }
       return QCP_IO_LAUNCH(pre_backward_kernel, 6, g.pre, m2, "pre_backward", a2);
     }
     if (QCP_IO_LAUNCH(post_backward_kernel, 1, g.post, m0, "post_backward", a0)) return 1;
     if (launch_checked(&contract_backward_kernel<T, NQ, ENC, 1>, g.contract, m1, s, "contract_backward", a1)) return 1;
+    if (after_contract && cudaEventRecord(after_contract, s) != cudaSuccess) { set_error("cudaEventRecord failed"); return 1; }
     return QCP_IO_LAUNCH(pre_backward_kernel, 1, g.pre, m2, "pre_backward", a2);
   });
   return 1;

@@ -328,7 +328,9 @@ def solver_backward_many(plan: Plan, items, mlp, theta):
             plan._handle, ctypes.c_void_p(theta.data_ptr()), ctypes.byref(g),
             ctypes.c_void_p(views[8].data_ptr()), stream)
         _lib.check(rc, "qcp_solver_backward_finish")
-        _count(2)
+        # reduce + theta_grad; with saved jets everywhere the d C window is reduced separately on
+        # the library's auxiliary stream (theta_grad runs next to the pre-MLP adjoints)
+        _count(3 if items and all(it[5] is not None and it[0].shape[0] for it in items) else 2)
     return views, gxs
 
 

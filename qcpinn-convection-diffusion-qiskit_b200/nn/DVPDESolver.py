@@ -240,6 +240,14 @@ class DVPDESolver(nn.Module):
         except Exception:
             return False
 
+    def prepare_step(self):
+        """Cast the current weights to the plan dtype and run ``qcp_prepare`` for the current angles
+        (both cached on ``theta_key``): lets a trainer issue them early, next to unrelated work."""
+        plan = self._plan(self.quantum_layer.params.device)
+        key = self.quantum_layer.theta_key()
+        tt, _ = plan.typed_weights(self.quantum_layer.params, self._mlp_tensors(), key)
+        plan.prepare(tt, key)
+
     def train_step_grads(self, batch, coeffs, weights=(2.0, 4.0, 2.0)):
         """The reference objective ``w_r MSE_r + w_bc MSE_bc + w_ic MSE_ic`` (reference
         trainer/diffusion_train.py:30-49) and ALL its parameter gradients without an autograd

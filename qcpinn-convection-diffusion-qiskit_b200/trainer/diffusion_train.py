@@ -123,7 +123,21 @@ class TrainStep:
 
         model = self.model
         if batch is None:
-            batch = self.sample()
+            # the samplers (six small launches) run on the side stream while the main stream casts
+            # the weights and runs the single-CTA qcp_prepare of this step's angles
+            dev = model.quantum_layer.params.device
+            main = torch.cuda.current_stream(dev)
+            side = model._value_stream(dev)
+            if side != main:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    batch = self.sample()
+                model.prepare_step()
+                main.wait_stream(side)
+                for t in batch:
+                    t.record_stream(main)
+            else:
+                batch = self.sample()
         flat, numel = model.train_step_grads(batch, DIFFUSION_COEFFS)
         world = 1
         if self.averager is not None:
