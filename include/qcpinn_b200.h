@@ -157,6 +157,15 @@ int qcp_solver_backward_add(qcp_plan_t* plan, const qcp_mlp_t* weights, const vo
 int qcp_solver_backward_finish(qcp_plan_t* plan, const void* theta, const qcp_mlp_t* grads,
                                void* grad_theta, void* stream);
 
+/* Reverse mode for operators that are NONLINEAR in the Taylor streams (reference nn/pde.py:2-25,
+ * navier_stokes_2D_operator: products like u * u_x): the caller differentiates its own residual
+ * with respect to the six streams of qcp_solver_forward(..., streams) and passes
+ * grad_streams [B,6] = d loss / d (u, u_t, u_x, u_y, u_xx, u_yy); outputs as in
+ * qcp_solver_backward().  n <= 4; ``save`` as above (residual-mode workspace or NULL). */
+int qcp_solver_backward_streams(qcp_plan_t* plan, const qcp_mlp_t* weights, const void* theta,
+                                const void* X, const void* grad_streams, long long batch,
+                                void* save, const qcp_mlp_t* grads, void* grad_theta, void* stream);
+
 /* Sampler.sample() tail fused in one kernel (reference data/diffusion_dataset.py:12-38): maps
  * uniform random numbers rnd [n,3] (float32, from torch.rand) into the box lo_hi = HOST float[6]
  * (lo[3], hi[3]) -> X [n,3], and evaluates the analytic target y [n]: kind 0 = solution u,

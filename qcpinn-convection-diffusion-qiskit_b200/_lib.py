@@ -50,6 +50,9 @@ SIGNATURES = {
     "qcp_solver_backward": (_c_int, [_c_void_p, ctypes.POINTER(QcpMlp), _c_void_p, _c_void_p,
                                      _c_void_p, _c_void_p, _c_ll, _c_int, _dptr, _c_void_p,
                                      ctypes.POINTER(QcpMlp), _c_void_p, _c_void_p, _c_void_p]),
+    "qcp_solver_backward_streams": (_c_int, [_c_void_p, ctypes.POINTER(QcpMlp), _c_void_p, _c_void_p,
+                                             _c_void_p, _c_ll, _c_void_p, ctypes.POINTER(QcpMlp),
+                                             _c_void_p, _c_void_p]),
     "qcp_solver_backward_begin": (_c_int, [_c_void_p]),
     "qcp_solver_backward_add": (_c_int, [_c_void_p, ctypes.POINTER(QcpMlp), _c_void_p, _c_void_p,
                                          _c_void_p, _c_ll, _c_int, _dptr, _c_void_p, _c_void_p,

@@ -54,6 +54,7 @@ struct SolverArgs {
   void* streams;       // [B,6]      optional: all Taylor streams of u (tests / eval) or null
   const void* gu;      // [B]        backward in (may be null => 0)
   const void* gr;      // [B]        backward in (may be null => 0)
+  const void* gs;      // [B,6]      backward in: cotangent of all six Taylor streams (or null)
   void* gX;            // [B,3]      backward out or null
   void* partials;      // [grid, nacc] backward out (plan-owned)
   void* ws;            // saved-jet workspace [2][n*S][B] or null (forward: save; split backward: use)

@@ -1206,9 +1206,37 @@ int qcp_solver_backward_begin(qcp_plan_t* p) {
 }
 
 // launch the adjoint kernels of one call; partial sums stay in the plan until _finish()
+static int backward_add_impl(qcp_plan_t* p, const qcp_mlp_t* w, const void* X, const void* grad_u,
+                             const void* grad_r, const void* grad_streams, long long B, int mode,
+                             const double* coeffs, void* save, void* grad_X, void* stream);
+
 int qcp_solver_backward_add(qcp_plan_t* p, const qcp_mlp_t* w, const void* X, const void* grad_u,
                             const void* grad_r, long long B, int mode, const double* coeffs,
                             void* save, void* grad_X, void* stream) {
+  return backward_add_impl(p, w, X, grad_u, grad_r, nullptr, B, mode, coeffs, save, grad_X, stream);
+}
+
+int qcp_solver_backward_streams(qcp_plan_t* p, const qcp_mlp_t* w, const void* theta, const void* X,
+                                const void* grad_streams, long long B, void* save,
+                                const qcp_mlp_t* g, void* grad_theta, void* stream) {
+  if (!p || !w || !theta || !g || !grad_theta || (B > 0 && (!X || !grad_streams))) {
+    set_error("qcp_solver_backward_streams: NULL argument");
+    return 1;
+  }
+  if (p->engine_l) {
+    set_error("qcp_solver_backward_streams: stream cotangents are an n <= %d feature", kMaxQubitsFused);
+    return 1;
+  }
+  static const double zero[5] = {0, 0, 0, 0, 0};
+  if (qcp_solver_backward_begin(p)) return 1;
+  if (backward_add_impl(p, w, X, nullptr, nullptr, grad_streams, B, QCP_MODE_RESIDUAL, zero, save,
+                        nullptr, stream)) return 1;
+  return qcp_solver_backward_finish(p, theta, g, grad_theta, stream);
+}
+
+static int backward_add_impl(qcp_plan_t* p, const qcp_mlp_t* w, const void* X, const void* grad_u,
+                             const void* grad_r, const void* grad_streams, long long B, int mode,
+                             const double* coeffs, void* save, void* grad_X, void* stream) {
   if (!p || !w || (B > 0 && !X)) { set_error("qcp_solver_backward_add: NULL argument"); return 1; }
   if (!p->prepared) { set_error("qcp_solver_backward_add: qcp_prepare() has not run"); return 1; }
   if (p->engine_l) { set_error("qcp_solver_backward_add: deferred reduction is an n <= %d feature", kMaxQubitsFused); return 1; }
@@ -1223,7 +1251,7 @@ int qcp_solver_backward_add(qcp_plan_t* p, const qcp_mlp_t* w, const void* X, co
   if (ensure_partials(p, kMaxPending * partial_slot_elems(p))) return 1;
   SolverArgs a{};
   fill_solver_args(a, p, w, X, B, coeffs);
-  a.gu = grad_u; a.gr = grad_r; a.gX = grad_X; a.ws = save;
+  a.gu = grad_u; a.gr = grad_r; a.gs = grad_streams; a.gX = grad_X; a.ws = save;
   const long long want_blocks = (B + kThreads - 1) / kThreads;
   char* base = static_cast<char*>(p->d_partials) + es * p->pending_used;
   const int k = p->pending;

@@ -955,6 +955,13 @@ __device__ __forceinline__ Jet<T, S> seed_cotangent(const SolverArgs& a, long lo
     const TIO* grg = static_cast<const TIO*>(a.gr);
     if (gug) ub.c[0] = (T)gug[p];
     if constexpr (S == 6) {
+      const TIO* gsg = static_cast<const TIO*>(a.gs);
+      if (gsg) {
+        // differentiable-streams mode (nn/pde.py operators that are nonlinear in the streams):
+        // the caller's autograd supplies d loss / d (u, u_t, u_x, u_y, u_xx, u_yy) per point
+#pragma unroll
+        for (int c = 0; c < 6; ++c) ub.c[c] += (T)gsg[6 * p + c];
+      }
       if (grg) {
         const T g = (T)grg[p];
         ub.c[1] = T(a.pde.ct) * g; ub.c[2] = T(a.pde.cx) * g; ub.c[3] = T(a.pde.cy) * g;

@@ -73,8 +73,8 @@ struct RgArgs {
   void* ws;                      // saved-jet workspace [2][n*S][B]
   long long B;
   void* state;                   // final psi streams [B][S][2^n] complex, or null
-  double* theta_partials;        // [grid][n_theta]
-  void* w_partials;              // T[grid][n_blk << n]
+  double* theta_partials;        // [grid * warps][n_theta]     one row per WARP: plain read-modify-
+  void* w_partials;              // T[grid * warps][n_blk << n]  write, summed in row order afterwards
 };
 
 template <typename T>
@@ -759,11 +759,13 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
   const int n = a.n, G = 1 << (n - LB), PP = WV == 2 ? 1 : 32 / G, NPT = S == 6 ? PP : (NW / WV) * PP, NE = NA + G;
   const Ctx<T, S> c{a};
   load_program<T, S>(a);
-  // per-CTA accumulator rows in global memory (zeroed by the host): fire-and-forget RED.ADD, which
-  // shared memory only offers as a compare-and-swap loop for floating point
-  double* const gth = a.theta_partials + (size_t)blockIdx.x * (a.n_theta > 0 ? a.n_theta : 1);
-  T* const wacc = static_cast<T*>(a.w_partials) + ((size_t)blockIdx.x * a.n_blk << n);
+  // per-WARP accumulator rows in global memory (zeroed by the host).  Every row has exactly one
+  // writer, so plain read-modify-writes in program order replace the atomicAdd of round 1 and the
+  // gradients are bit-reproducible (the rows are summed in row order by the reduction kernels)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t wrow = (size_t)blockIdx.x * NW + warp;
+  double* const gth = a.theta_partials + wrow * (a.n_theta > 0 ? a.n_theta : 1);
+  T* const wacc = static_cast<T*>(a.w_partials) + (wrow * a.n_blk << n);
   const int wv = WV == 2 ? warp & 1 : 0, vec = warp / WV;          // half of / index of this warp's vector
   const int lig = WV == 2 ? (wv << 5) | lane : lane & (G - 1), sub = WV == 2 ? 0 : lane / G;
   const int slot = S == 6 ? sub : vec * PP + sub;
@@ -901,7 +903,7 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
           }
           if (op.p >= 0) {
             for (int m = 16; m > 0; m >>= 1) part += shx(part, m);
-            if (lane == 0) atomicAdd(gth + op.p, 0.5 * (double)part);
+            if (lane == 0) gth[op.p] += 0.5 * (double)part;
           }
           break;
         }
@@ -925,7 +927,13 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
         case R_DIAG: {
           T* wa = wacc + ((size_t)op.g << n) + lig;
 #pragma unroll
-          for (int i = 0; i < NA; ++i) atomicAdd(wa + i * G, fma(lx[i], ay[i], -ly[i] * ax[i]));
+          for (int i = 0; i < NA; ++i) {
+            T w = fma(lx[i], ay[i], -ly[i] * ax[i]);             // Im(conj(lambda) psi)
+            // a warp carries 32 / G points when a vector needs fewer than 32 lanes: fold the
+            // copies that address the same table entry before the single write
+            for (int m = G; m < 32; m <<= 1) w += shx(w, m);
+            if (sub == 0) wa[i * G] += w;
+          }
           const C2A<T>* tb = diag + ((size_t)op.g << n) + lig;
           diag_apply<T, LB>(ax, ay, tb, G, true);
           diag_apply<T, LB>(lx, ly, tb, G, true);

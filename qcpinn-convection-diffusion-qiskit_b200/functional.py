@@ -280,6 +280,23 @@ class Plan:
         return views, gx
 
 
+def _solver_backward_streams(plan: Plan, X, mlp, theta, grad_streams, save=None):
+    """Adjoint of the six-stream forward for a per-point cotangent of ALL streams [B,6]."""
+    flat, views = _flat_grad_views(plan, mlp, theta)
+    m = plan._mlp(mlp)
+    g = plan._mlp(views[:8])
+    plan._sync_state_flag(save)
+    with torch.cuda.device(plan.device):
+        rc = plan.lib.qcp_solver_backward_streams(
+            plan._handle, ctypes.byref(m), ctypes.c_void_p(theta.data_ptr()),
+            ctypes.c_void_p(X.data_ptr()), ctypes.c_void_p(grad_streams.data_ptr()), X.shape[0],
+            ctypes.c_void_p(save.data_ptr() if save is not None else None), ctypes.byref(g),
+            ctypes.c_void_p(views[8].data_ptr()), plan._stream())
+    _lib.check(rc, "qcp_solver_backward_streams")
+    _count(6 if (save is not None and X.shape[0] > 0) else 3)
+    return views
+
+
 def _flat_grad_views(plan: Plan, mlp, theta):
     sizes = [t.numel() for t in mlp] + [plan.n_theta]
     flat = torch.empty(sum(sizes), dtype=plan.dtype, device=plan.device)
@@ -435,6 +452,49 @@ class _SolverFn(torch.autograd.Function):
         gm = [v.to(d) if need else None
               for v, d, need in zip(views[:8], dt[2:], ctx.needs_input_grad[6:])]
         return (None, None, None, None, gX, gtheta, *gm)
+
+
+class _SolverStreamsFn(torch.autograd.Function):
+    """X -> streams [B,6] = (u, u_t, u_x, u_y, u_xx, u_yy), differentiable with respect to every
+    parameter: the building block of residual operators that are nonlinear in the streams
+    (Navier-Stokes, reference nn/pde.py:2-25).  The coordinates are not differentiated."""
+
+    @staticmethod
+    def forward(ctx, plan: Plan, key, X, theta, *mlp):
+        Xt = plan._io(X)
+        tt, mt = plan.typed_weights(theta, mlp, key)
+        plan.prepare(tt, key)
+        needs_grad = any(ctx.needs_input_grad[3:])
+        save = (plan.workspace(Xt.shape[0], MODE_RESIDUAL)
+                if (needs_grad and SAVE_JETS and Xt.shape[0]) else None)
+        _, _, streams = plan.solver_forward(Xt, mt, MODE_RESIDUAL, (0.0,) * 5, want_streams=True,
+                                            save=save)
+        ctx.save = save
+        ctx.plan, ctx.key = plan, key
+        ctx.save_for_backward(Xt, tt, *mt)
+        ctx.in_dtypes = [theta.dtype] + [w.dtype for w in mlp]
+        ctx.theta_shape = theta.shape
+        return streams
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_streams):
+        plan = ctx.plan
+        Xt, tt, *mt = ctx.saved_tensors
+        plan.prepare(tt, ctx.key)
+        gs = _grad_in(plan, grad_streams, (Xt.shape[0], 6), io=True)
+        views = _solver_backward_streams(plan, Xt, mt, tt, gs, save=ctx.save)
+        ctx.save = None
+        gtheta, gm = _cast_grads(plan, views, ctx.in_dtypes[0], ctx.in_dtypes[1:], ctx.theta_shape,
+                                 ctx.needs_input_grad[3], ctx.needs_input_grad[4:12])
+        return (None, None, None, gtheta, *gm)
+
+
+def solver_streams_grad(plan: Plan, X, theta, mlp, key=None):
+    """Differentiable six-stream forward (n <= 4): [B,6]."""
+    if not plan.fused_engine:
+        raise NotImplementedError("differentiable Taylor streams cover the n <= 4 engine")
+    return _SolverStreamsFn.apply(plan, key, X, theta, *mlp)
 
 
 def _cast_grads(plan, views, dt_theta, dt_mlp, theta_shape, needs_theta, needs_mlp):

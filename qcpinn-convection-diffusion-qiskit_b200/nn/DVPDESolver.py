@@ -113,11 +113,18 @@ class DVPDESolver(nn.Module):
     # -- fused path ----------------------------------------------------------------------------
     def _check_fused(self):
         net = self.classic_network
-        if net[0] not in (2, 3) or net[-1] != 1:
+        if net[0] not in (2, 3) or net[-1] < 1:
             raise NotImplementedError(
-                f"fused kernels cover classic_network=[3, H, 1] and [2, H, 1]; got {net}")
+                f"fused kernels cover classic_network=[3, H, k] and [2, H, k]; got {net}")
 
-    def _mlp_tensors(self):
+    @property
+    def n_outputs(self):
+        return int(self.classic_network[-1])
+
+    def _mlp_tensors(self, output=None):
+        """The eight MLP tensors the kernels read.  Multi-output solvers (Navier-Stokes: u, v, p,
+        reference nn/pde.py:2-25) run the single-output kernels once per output row of the last
+        Linear layer (``output`` = row index); autograd sums the shared parameters' gradients."""
         pre, post = self.preprocessor, self.postprocessor
         w1 = pre[0].weight
         if w1.shape[1] == 2:
@@ -125,8 +132,15 @@ class DVPDESolver(nn.Module):
             # the coordinates ride in the kernel's x / y slots behind a zero t column; autograd
             # slices the gradient of the padded weight back
             w1 = torch.nn.functional.pad(w1, (1, 0))
+        w4, b4 = post[2].weight, post[2].bias
+        if self.n_outputs != 1:
+            if output is None:
+                raise NotImplementedError(
+                    f"this entry point covers single-output solvers; the model has {self.n_outputs} "
+                    "outputs (use forward() / taylor_streams_grad())")
+            w4, b4 = w4[output:output + 1], b4[output:output + 1]
         return (w1, pre[0].bias, pre[2].weight, pre[2].bias,
-                post[0].weight, post[0].bias, post[2].weight, post[2].bias)
+                post[0].weight, post[0].bias, w4, b4)
 
     def _kernel_input(self, x):
         """(B, 3) kernel input: two-input solvers get a zero t column in front."""
@@ -155,6 +169,11 @@ class DVPDESolver(nn.Module):
                 self.draw_quantum_circuit(x)
                 self.draw_quantum_circuit_flag = False
             plan = self._plan(self._device_of(x))
+            if self.n_outputs != 1:
+                cols = [F.solver_value(plan, self._kernel_input(x), self.quantum_layer.params,
+                                       self._mlp_tensors(o), self.quantum_layer.theta_key())
+                        for o in range(self.n_outputs)]
+                return torch.cat(cols, dim=1).to(torch.float32)
             u = F.solver_value(plan, self._kernel_input(x), self.quantum_layer.params,
                                self._mlp_tensors(), self.quantum_layer.theta_key())
             return u.to(torch.float32)
@@ -235,7 +254,7 @@ class DVPDESolver(nn.Module):
         try:
             dev = self.quantum_layer.params.device
             return dev.type == "cuda" and self.classic_network[0] == 3 and \
-                self._plan(dev).fused_engine and \
+                self.n_outputs == 1 and self._plan(dev).fused_engine and \
                 all(p.dtype == torch.float32 for p in self.parameters())
         except Exception:
             return False
@@ -307,6 +326,24 @@ class DVPDESolver(nn.Module):
         if dev not in streams:
             streams[dev] = torch.cuda.Stream(device=dev)
         return streams[dev]
+
+    def taylor_streams_grad(self, X: torch.Tensor):
+        """(B, n_outputs, 6) = (u, u_t, u_x, u_y, u_xx, u_yy) of every output, connected to every
+        parameter (first-order adjoint kernels): what residual operators that multiply streams
+        need (``nn.pde.navier_stokes_2D_operator``).  The coordinates are detached."""
+        try:
+            if X.dim() != 2:
+                raise ValueError(f"Expected 2D input tensor, got shape {X.shape}")
+            plan = self._plan(self._device_of(X))
+            Xk = self._kernel_input(X).detach()
+            key = self.quantum_layer.theta_key()
+            outs = [F.solver_streams_grad(plan, Xk, self.quantum_layer.params,
+                                          self._mlp_tensors(o if self.n_outputs != 1 else None), key)
+                    for o in range(self.n_outputs)]
+            return torch.stack(outs, dim=1).to(torch.float32)
+        except Exception as e:
+            self.logger.print(f"Forward pass failed: {str(e)}")
+            raise
 
     def taylor_streams(self, X: torch.Tensor):
         """No-grad evaluation helper: (B,6) = u, u_t, u_x, u_y, u_xx, u_yy."""

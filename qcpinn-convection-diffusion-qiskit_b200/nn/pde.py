@@ -11,7 +11,8 @@ reference (nested ``autograd.grad(create_graph=True)`` calls).
 (``classic_network=[2, H, 1]``): their two coordinates ride in the kernel's two second-derivative
 slots, the linear part of the residual is the kernel's coefficient vector and the ``u`` / ``u**k``
 terms are added on the (differentiable) outputs.  ``navier_stokes_2D_operator`` (:2-25) needs three
-outputs and products of streams; it is kept for generic modules only.
+outputs and products of streams: a three-output solver returns the six streams of every output as
+differentiable tensors (``taylor_streams_grad``) and the products are plain tensor ops.
 """
 
 import torch
@@ -95,23 +96,34 @@ def helmholtz_operator(fluid_model, x1, x2):
 
 def navier_stokes_2D_operator(model, t, x, y, min_x=0, max_x=1):
     """[continuity, f_u, f_v] of the incompressible 2-D Navier-Stokes equations for a three-output
-    model (u, v, p) (reference nn/pde.py:2-25).  Generic nested-autograd formulation: the fused
-    DVPDESolver has one output and a first-order-only adjoint, so it is rejected loudly."""
-    if getattr(model, "taylor_residual", None) is not None:
-        raise NotImplementedError(
-            "navier_stokes_2D_operator needs a three-output, twice-differentiable model; the fused "
-            "DVPDESolver kernels cover one output (diffusion / wave / Klein-Gordon / Helmholtz)")
+    model (u, v, p) (reference nn/pde.py:2-25).  A B200 ``DVPDESolver`` with
+    ``classic_network=[3, H, 3]`` takes the fused route: the six Taylor streams of each output come
+    from the forward kernel (``model.taylor_streams_grad``: 12 derivatives + 3 values, no nested
+    autograd), the stream products ``u u_x + v u_y`` are ordinary differentiable tensor ops on them,
+    and the adjoint kernels take the per-stream cotangents back to every parameter.  Any other
+    module uses the reference's nested-autograd formulation."""
     mu, density = 0.00345, 1056.0
     t.requires_grad = True
     x.requires_grad = True
     y.requires_grad = True
-    uvp = model(torch.cat((t, x, y), 1))
-    u, v, p = uvp[:, 0:1], uvp[:, 1:2], uvp[:, 2:3]
-    u_t, u_x, u_y = _grad(u, t), _grad(u, x), _grad(u, y)
-    v_t, v_x, v_y = _grad(v, t), _grad(v, x), _grad(v, y)
-    p_x, p_y = _grad(p, x), _grad(p, y)
-    u_xx, u_yy = _grad(u_x, x), _grad(u_y, y)
-    v_xx, v_yy = _grad(v_x, x), _grad(v_y, y)
+    fused = getattr(model, "taylor_streams_grad", None)
+    if fused is not None:
+        if getattr(model, "n_outputs", 1) != 3:
+            raise ValueError("navier_stokes_2D_operator needs a three-output model (u, v, p): "
+                             "classic_network=[3, H, 3]")
+        S = fused(torch.cat((t, x, y), 1).detach())           # (B, 3, 6)
+        col = lambda o, c: S[:, o, c:c + 1]
+        u, u_t, u_x, u_y, u_xx, u_yy = (col(0, c) for c in range(6))
+        v, v_t, v_x, v_y, v_xx, v_yy = (col(1, c) for c in range(6))
+        p_x, p_y = col(2, 2), col(2, 3)
+    else:
+        uvp = model(torch.cat((t, x, y), 1))
+        u, v, p = uvp[:, 0:1], uvp[:, 1:2], uvp[:, 2:3]
+        u_t, u_x, u_y = _grad(u, t), _grad(u, x), _grad(u, y)
+        v_t, v_x, v_y = _grad(v, t), _grad(v, x), _grad(v, y)
+        p_x, p_y = _grad(p, x), _grad(p, y)
+        u_xx, u_yy = _grad(u_x, x), _grad(u_y, y)
+        v_xx, v_yy = _grad(v_x, x), _grad(v_y, y)
     continuity = u_x + v_y
     f_u = u_t + (u * u_x + v * u_y) + p_x / density - mu * (u_xx + u_yy)
     f_v = v_t + (u * v_x + v * v_y) + p_y / density - mu * (v_xx + v_yy)

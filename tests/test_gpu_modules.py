@@ -410,13 +410,43 @@ def test_two_input_operators_match_oracle(tmp_path, name, dtype):
     assert _weights_of(model)["w1"].grad.shape == (50, 2)
 
 
-def test_navier_stokes_operator_rejects_the_fused_solver(tmp_path):
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_navier_stokes_operator_on_the_fused_kernels(tmp_path, dtype):
+    """reference nn/pde.py:2-25 with a three-output solver (u, v, p): continuity / momentum
+    residuals (12 derivatives, products of streams) and every parameter gradient against the
+    reference's own nested-autograd formulation evaluated on the CPU oracle."""
     from qcpinn_b200.nn import pde
 
-    model = _model(tmp_path)
-    t = torch.rand(4, 1, device=DEV)
-    with pytest.raises(NotImplementedError):
-        pde.navier_stokes_2D_operator(model, t, t.clone(), t.clone())
+    model = _model(tmp_path, dtype=dtype, classic_network=[3, 50, 3], seed=1)
+    assert model.n_outputs == 3
+    with torch.no_grad():
+        model.preprocessor[2].bias.add_(0.3)
+    oracle = _oracle_of(model)
+    g = torch.Generator().manual_seed(5)
+    X = torch.rand(37, 3, generator=g, dtype=torch.float64)
+    coef = [torch.randn(37, 1, generator=g, dtype=torch.float64) for _ in range(3)]
+
+    want = pde.navier_stokes_2D_operator(lambda Z: oracle.forward(Z), X[:, 0:1].clone(),
+                                         X[:, 1:2].clone(), X[:, 2:3].clone())
+    sum(((w_ * c).sum() for w_, c in zip(want, coef))).backward()
+
+    Xd = X.to(DEV, torch.float32)
+    uvp = model(Xd)
+    assert uvp.shape == (37, 3) and uvp.dtype == torch.float32
+    assert rel_err(uvp, oracle.forward(Xd.cpu().double())) < 2e-6
+    got = pde.navier_stokes_2D_operator(model, Xd[:, 0:1].clone(), Xd[:, 1:2].clone(), Xd[:, 2:3].clone())
+    sum(((g_ * c.to(DEV, torch.float32)).sum() for g_, c in zip(got, coef))).backward()
+    tol = 3e-5 if dtype == "float32" else 5e-6        # module tensors / outputs are float32
+    for a, b in zip(got, want):
+        assert a.shape == (37, 1) and rel_err(a, b) < tol
+    for k, p in _weights_of(model).items():
+        assert rel_err(p.grad, oracle.w[k].grad) < 10 * tol, k
+    # a one-output solver is rejected with the reference's requirement spelled out
+    with pytest.raises(ValueError, match="three-output"):
+        pde.navier_stokes_2D_operator(_model(tmp_path), Xd[:, 0:1], Xd[:, 1:2], Xd[:, 2:3])
+    # the streams themselves, output by output
+    S = model.taylor_streams_grad(Xd)
+    assert S.shape == (37, 3, 6)
 
 
 def test_single_file_trainer_entry_point(tmp_path):

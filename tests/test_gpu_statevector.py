@@ -264,3 +264,26 @@ def test_full_size_properties_configs_3_and_4(ansatz, n, layers, n_pts, n_check)
     Xs = X[idx].cpu().double()
     uo, ro = osolver.diffusion_operator(oracle, Xs[:, 0:1].clone(), Xs[:, 1:2].clone(), Xs[:, 2:3].clone())
     assert rel_err(u1[idx], uo[:, 0]) < 1e-5 and rel_err(r1[idx], ro[:, 0]) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f64", "f32"])
+@pytest.mark.parametrize("case", [("cross_mesh", 10, 2, "angle", None), ("layered", 7, 2, "angle", 1),
+                                  ("sim_circ_15", 8, 1, "angle", None)], ids=_ids)
+def test_register_engine_gradients_are_bit_reproducible(case, dtype):
+    """Engine R accumulates dL/dtheta and the diagonal-block sums in one global row per warp (plain
+    read-modify-write, rows summed in order): repeated backward passes over the same batch give
+    bit-identical gradients -- what data-parallel equivalence checks rely on."""
+    ansatz, n, layers, enc, seed = case
+    w, _, prog = make_case(ansatz, n, layers, enc, seed)
+    plan = F.Plan(prog, F.encoding_code(enc), dtype, 50, DEV)
+    assert plan.engine == "register"
+    X = points(700, seed=9).to(DEV, dtype)
+    runs = []
+    for _ in range(3):
+        dw = device_weights(w, dtype, DEV, requires_grad=True)
+        u, r = F.solver_residual(plan, X, dw["theta"], mlp_list(dw), (1, 1, 1, -0.01, -0.01))
+        ((u ** 2).sum() + (r ** 2).sum()).backward()
+        runs.append({k: v.grad.detach().clone() for k, v in dw.items()})
+    for other in runs[1:]:
+        for k, g in runs[0].items():
+            assert torch.equal(g, other[k]), k
