@@ -58,6 +58,11 @@ namespace qcp {
 #ifndef QCP_STREAM_PASSES
 #define QCP_STREAM_PASSES 1
 #endif
+// block-wide barrier at every A-half iteration of the streamed contraction adjoint: the four warps
+// of a block then run the (huge, fully unrolled) body together and share its instruction fetches
+#ifndef QCP_LOCKSTEP
+#define QCP_LOCKSTEP 0
+#endif
 #ifndef QCP_ROLL_I
 #define QCP_ROLL_I 0
 #endif
@@ -629,7 +634,7 @@ __device__ __forceinline__ Jet<T, S> jet_pick(const Jet<T, S> (&v)[NQ], int i) {
 
 // Adjoint of features + contraction for one jet layout.  Pushes d C in (a, i, b) order and ADDS
 // the pulled-back cotangent into zb (so sub-jet passes can accumulate).
-template <typename T, int NQ, int S, int MODE = -1>
+template <typename T, int NQ, int S, int MODE = -1, bool LOCK = false>
 __device__ __forceinline__ void angle_backward(const T* sC, const Jet<T, S> (&z)[NQ],
                                                const AngleFeat<T, NQ, S>& f,
                                                const Jet<T, S> (&qb)[NQ], Jet<T, S> (&zb)[NQ],
@@ -645,6 +650,7 @@ __device__ __forceinline__ void angle_backward(const T* sC, const Jet<T, S> (&z)
   for (int b = 0; b < A::FB; ++b) jzero(Qb[b]);
 
   auto body = [&](int a, int t0, int t1) {
+    if constexpr (LOCK) __syncthreads();
     PA<T, NQ, S> pa;
     pa.set2(f, t0, t1);
     Jet<T, S> pab;
@@ -832,7 +838,7 @@ __device__ __forceinline__ void angle_backward_ws(const T* sC, T* ws, long long 
     }
     AngleFeat<T, NQ, SS> f;
     angle_features<T, NQ, SS>(zs, sn, cs, f);
-    angle_backward<T, NQ, SS, MODE>(sC, zs, f, qs, zbs, st);
+    angle_backward<T, NQ, SS, MODE, (QCP_LOCKSTEP != 0)>(sC, zs, f, qs, zbs, st);
 #pragma unroll
     for (int j = 0; j < NQ; ++j) {
       zb0[j] += zbs[j].c[0];
@@ -1142,7 +1148,10 @@ contract_backward_kernel(const SolverArgs a) {
   T* wsg = static_cast<T*>(a.ws);
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long Bpad = (a.B + 31) & ~31LL;
-  for (long long p0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; p0 < Bpad; p0 += stride) {
+  // the loop bound is uniform over the block (warps past the end run with valid == false), so the
+  // body may contain block-wide barriers
+  for (long long b0 = (long long)blockIdx.x * blockDim.x; b0 < Bpad; b0 += stride) {
+    const long long p0 = b0 + threadIdx.x;
     const bool valid = p0 < a.B;
     const long long p = valid ? p0 : a.B - 1;
     st.begin();

@@ -9,7 +9,8 @@ different: the circuit is never handed to PennyLane; it is compiled to a gate ta
 
 New optional ``args`` keys (defaults keep a reference dict working unchanged):
 ``dtype`` = ``"float64"`` (default; complex128-equivalent arithmetic like ``default.qubit``) or
-``"float32"``.
+``"float32"``; ``diff_mode`` = ``"kernels"`` (default) or ``"autograd"`` (opt-in slow path that is
+differentiable to any order, :mod:`.torch_circuit`).
 """
 
 from __future__ import annotations
@@ -46,6 +47,9 @@ class DVQuantumLayer(nn.Module):
         self.encoding = args.get("encoding", "angle")
         self.use_ibm_hardware = args.get("use_ibm_hardware", False)
         self.compute_dtype = resolve_dtype(args.get("dtype", "float64"))
+        self.diff_mode = args.get("diff_mode", "kernels")
+        if self.diff_mode not in ("kernels", "autograd"):
+            raise ValueError(f"diff_mode must be 'kernels' or 'autograd', got {self.diff_mode!r}")
         if self.use_ibm_hardware:
             raise NotImplementedError(
                 "use_ibm_hardware=True (remote QPU execution) is outside the B200 hot path")
@@ -111,6 +115,16 @@ class DVQuantumLayer(nn.Module):
             raise RuntimeError(
                 f"quantum_layer.params on {self.params.device} but input on {z.device}; "
                 "move the module with .to(device)")
-        plan = self.plan(z.device)
-        out = F.layer_apply(plan, z, self.params, self.theta_key())
+        if self.diff_mode == "autograd":
+            from .torch_circuit import run_layer
+
+            if z.device.type != "cuda":        # same rule as the kernels: this package has no CPU path
+                raise RuntimeError(
+                    f"qcpinn_b200 runs on CUDA devices only (got {z.device}); there is no CPU path")
+
+            cdtype = torch.complex128 if self.compute_dtype == torch.float64 else torch.complex64
+            out = run_layer(self.program, self.encoding, z, self.params, cdtype)
+        else:
+            plan = self.plan(z.device)
+            out = F.layer_apply(plan, z, self.params, self.theta_key())
         return out[:, 0] if single else out

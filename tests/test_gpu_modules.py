@@ -592,3 +592,45 @@ def test_residual_outputs_are_not_connected_to_the_coordinates(tmp_path):
     Xv = X.clone().requires_grad_(True)                          # value mode does give du/dX
     (gx,) = torch.autograd.grad(model(Xv).sum(), Xv)
     assert gx.shape == X.shape and float(gx.abs().max()) > 0
+
+
+def test_opt_in_autograd_mode_is_differentiable_to_any_order(tmp_path):
+    """args["diff_mode"] = "autograd": the reference's literal nested-autograd usage
+    (nn/pde.py:60-70: autograd.grad(u, t, create_graph=True), second derivatives, backward through
+    all of it) runs on the module; values, residual and gradients agree with the kernel mode and
+    with the CPU oracle; mixed second derivatives -- which the six Taylor streams do not carry --
+    are available here."""
+    model_k = _model(tmp_path)
+    model_a = _model(tmp_path, diff_mode="autograd")
+    for pa, pk in zip(model_a.parameters(), model_k.parameters()):
+        assert torch.equal(pa, pk)
+    assert model_a.taylor_residual is None and not model_a.supports_fused_step()
+    oracle = _oracle_of(model_k, "mixed")
+    X = points(21).float().to(DEV)
+    t, x, y = (X[:, i:i + 1].clone().requires_grad_(True) for i in range(3))
+    u = model_a(torch.cat((t, x, y), 1))
+    ones = torch.ones_like(u)
+    u_x = torch.autograd.grad(u, x, ones, create_graph=True)[0]
+    u_xy = torch.autograd.grad(u_x, y, ones, create_graph=True)[0]            # a MIXED derivative
+    u_xx = torch.autograd.grad(u_x, x, ones, create_graph=True)[0]
+    assert rel_err(u, model_k(X)) < 1e-6
+    S = model_k.taylor_streams(X)
+    assert rel_err(u_x, S[:, 2:3]) < 1e-5 and rel_err(u_xx, S[:, 4:5]) < 1e-4
+    Xc = X.cpu()
+    to, xo, yo = (Xc[:, i:i + 1].clone().requires_grad_(True) for i in range(3))
+    uo = oracle.forward(torch.cat((to, xo, yo), 1))
+    uo_x = torch.autograd.grad(uo, xo, torch.ones_like(uo), create_graph=True)[0]
+    uo_xy = torch.autograd.grad(uo_x, yo, torch.ones_like(uo), create_graph=True)[0]
+    assert rel_err(u_xy, uo_xy) < 1e-4
+    # the generic formulation of nn.pde on the autograd-mode module == the fused operator
+    ua, ra = qb.diffusion_operator(model_a, X[:, 0:1].clone(), X[:, 1:2].clone(), X[:, 2:3].clone())
+    uk, rk = qb.diffusion_operator(model_k, X[:, 0:1].clone(), X[:, 1:2].clone(), X[:, 2:3].clone())
+    assert rel_err(ra, rk) < 1e-4
+    (ra ** 2).mean().backward()
+    (rk ** 2).mean().backward()
+    for pa, pk in zip(model_a.parameters(), model_k.parameters()):
+        assert rel_err(pa.grad, pk.grad) < 2e-3        # float32 nested autograd vs float64 kernels
+    with pytest.raises(RuntimeError, match="CUDA devices only"):
+        qb.DVQuantumLayer(dict(ARGS, diff_mode="autograd"))(torch.zeros(2, 4))
+    with pytest.raises(ValueError, match="diff_mode"):
+        qb.DVQuantumLayer(dict(ARGS, diff_mode="nope"))
