@@ -140,12 +140,13 @@ struct SmemWeights {
   T* b3w4;        // [H][2] (b3[k], w4[k])
   T* b2;          // [4]
   T* b4;          // [4]  (only [0] used)
+  T* etab;        // [64] 2^(j/64): exp table of the float64 tanh (unused in float32)
   T* C;           // feature matrix image (layout above)
 };
 
 template <typename T>
 __host__ __device__ inline size_t smem_weights_bytes(int H, int celems) {
-  return sizeof(T) * (size_t)(4 * H * 3 + 2 * H + 4 + 4 + celems);
+  return sizeof(T) * (size_t)(4 * H * 3 + 2 * H + 4 + 4 + kExpTabSize + celems);
 }
 
 template <typename T>
@@ -159,6 +160,7 @@ __device__ __forceinline__ SmemWeights<T> carve_weights(unsigned char* base, int
   s.b3w4 = p; p += 2 * H;
   s.b2 = p;   p += 4;
   s.b4 = p;   p += 4;
+  s.etab = p; p += kExpTabSize;
   return s;
 }
 
@@ -193,6 +195,7 @@ __device__ __forceinline__ void load_weights(const SmemWeights<T>& s, const Solv
     s.b2[threadIdx.x] = threadIdx.x < NQ ? b2[threadIdx.x] : T(0);
     s.b4[threadIdx.x] = b4[0];
   }
+  if (threadIdx.x < kExpTabSize) s.etab[threadIdx.x] = (T)exp2((double)threadIdx.x / kExpTabSize);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -224,7 +227,7 @@ __device__ __forceinline__ void pre_forward(const SmemWeights<T>& s, int H, cons
     const Vec4<T> w = s.w1b[k];
     const Vec4<T> w2 = s.w2t[k];
     const Jet<T, S> a = pre_activation<T, S>(w, X);
-    const T h0 = Math<T>::tanh_(a.c[0]);
+    const T h0 = Math<T>::tanh_tab(a.c[0], s.etab);
     if (act) act[(size_t)k * B] = h0;
     const T f1 = fma(-h0, h0, T(1));
     const T f2 = T(-2) * h0 * f1;
@@ -252,7 +255,7 @@ __device__ __forceinline__ void post_forward(const SmemWeights<T>& s, int H,
     p.c[0] = b3;
 #pragma unroll
     for (int i = 0; i < NQ; ++i) jaxpy(p, w3.v[i], q[i]);
-    const T g0 = Math<T>::tanh_(p.c[0]);
+    const T g0 = Math<T>::tanh_tab(p.c[0], s.etab);
     if (act) act[(size_t)k * B] = g0;
     const T f1 = fma(-g0, g0, T(1));
     const T f2 = T(-2) * g0 * f1;

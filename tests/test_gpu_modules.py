@@ -629,7 +629,12 @@ def test_opt_in_autograd_mode_is_differentiable_to_any_order(tmp_path):
     (ra ** 2).mean().backward()
     (rk ** 2).mean().backward()
     for pa, pk in zip(model_a.parameters(), model_k.parameters()):
-        assert rel_err(pa.grad, pk.grad) < 2e-3        # float32 nested autograd vs float64 kernels
+        # (the residual does not depend on the output bias: autograd leaves its .grad unset)
+        ga = pa.grad if pa.grad is not None else torch.zeros_like(pa)
+        if float(pk.grad.abs().max()) == 0.0:
+            assert float(ga.abs().max()) == 0.0
+        else:
+            assert rel_err(ga, pk.grad) < 2e-3         # float32 nested autograd vs float64 kernels
     with pytest.raises(RuntimeError, match="CUDA devices only"):
         qb.DVQuantumLayer(dict(ARGS, diff_mode="autograd"))(torch.zeros(2, 4))
     with pytest.raises(ValueError, match="diff_mode"):
