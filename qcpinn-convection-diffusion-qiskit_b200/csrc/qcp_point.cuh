@@ -63,6 +63,14 @@ namespace qcp {
 #ifndef QCP_LOCKSTEP
 #define QCP_LOCKSTEP 0
 #endif
+// value mode (S = 1, the IC / BC points): points per thread of the post / pre MLP adjoints.  Their
+// per-point arithmetic is ~15 FMAs per hidden unit, so with one point per thread the kernels were
+// bound by the gradient staging (LDS + STS + DADD per parameter and point: LSU pipe 47 %, FP64 pipe
+// 26 %, profiles/r02_*): K points per thread add their contributions in registers first and stage
+// once, and the weight rows are fetched once for K points.
+#ifndef QCP_VALUE_PPT
+#define QCP_VALUE_PPT 4
+#endif
 #ifndef QCP_ROLL_I
 #define QCP_ROLL_I 0
 #endif
@@ -920,6 +928,121 @@ __device__ __forceinline__ void pre_backward(const SmemWeights<T>& s, int H, con
 }
 
 // ------------------------------------------------------------------------------------------
+// value mode with K points per thread (S = 1: plain scalars, no jets).  Accumulator order is the
+// one of post_backward / pre_backward, so the reduction and the fused kernel see no difference.
+// `act` points at this MLP's saved tanh row 0 (unused when !SAVED); pts[] are the point indices.
+// ------------------------------------------------------------------------------------------
+template <typename T, int NQ, int K, bool SAVED>
+__device__ __forceinline__ void post_backward_value(const SmemWeights<T>& s, int H,
+                                                    const T (&q)[K][NQ], const T (&ub)[K],
+                                                    T (&qb)[K][NQ], Stager<T>& st, const T* act,
+                                                    long long B, const long long (&pts)[K]) {
+#pragma unroll
+  for (int j = 0; j < K; ++j)
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) qb[j][i] = T(0);
+  T nxt[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) nxt[j] = SAVED ? act[pts[j]] : T(0);
+  for (int k = 0; k < H; ++k) {
+    const Vec4<T> w3 = s.w3[k];
+    const T b3 = s.b3w4[2 * k], w4 = s.b3w4[2 * k + 1];
+    T g0[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      g0[j] = nxt[j];
+      if constexpr (SAVED) {
+        if (k + 1 < H) nxt[j] = act[(size_t)(k + 1) * B + pts[j]];
+      } else {
+        T pre = b3;
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) pre = fma(w3.v[i], q[j][i], pre);
+        g0[j] = Math<T>::tanh_tab(pre, s.etab);
+      }
+    }
+    T dw3[NQ], db3 = T(0), dw4 = T(0);
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) dw3[i] = T(0);
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const T f1 = fma(-g0[j], g0[j], T(1));
+      const T pb = w4 * ub[j] * f1;
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        dw3[i] = fma(pb, q[j][i], dw3[i]);
+        qb[j][i] = fma(w3.v[i], pb, qb[j][i]);
+      }
+      db3 += pb;
+      dw4 = fma(ub[j], g0[j], dw4);
+    }
+    st.reserve(NQ + 2);
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) st.put(dw3[i]);             // d w3[k,i]
+    st.put(db3);                                           // d b3[k]
+    st.put(dw4);                                           // d w4[k]
+  }
+}
+
+template <typename T, int NQ, int K, bool SAVED>
+__device__ __forceinline__ void pre_backward_value(const SmemWeights<T>& s, int H,
+                                                   const T (&X)[K][3], const T (&zb)[K][NQ],
+                                                   T (&Xb)[K][3], Stager<T>& st, const T* act,
+                                                   long long B, const long long (&pts)[K]) {
+  st.reserve(NQ);
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    T sum = T(0);
+#pragma unroll
+    for (int j = 0; j < K; ++j) sum += zb[j][i];
+    st.put(sum);                                           // d b2[i]
+  }
+#pragma unroll
+  for (int j = 0; j < K; ++j) Xb[j][0] = Xb[j][1] = Xb[j][2] = T(0);
+  T nxt[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) nxt[j] = SAVED ? act[pts[j]] : T(0);
+  for (int k = 0; k < H; ++k) {
+    const Vec4<T> w = s.w1b[k];
+    const Vec4<T> w2 = s.w2t[k];
+    T h0[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      h0[j] = nxt[j];
+      if constexpr (SAVED) {
+        if (k + 1 < H) nxt[j] = act[(size_t)(k + 1) * B + pts[j]];
+      } else {
+        const T pre = fma(w.v[0], X[j][0], fma(w.v[1], X[j][1], fma(w.v[2], X[j][2], w.v[3])));
+        h0[j] = Math<T>::tanh_tab(pre, s.etab);
+      }
+    }
+    T dw1[3] = {T(0), T(0), T(0)}, db1 = T(0), dw2[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) dw2[i] = T(0);
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      T hb = T(0);
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) hb = fma(w2.v[i], zb[j][i], hb);
+      const T ab = hb * fma(-h0[j], h0[j], T(1));
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        dw1[d] = fma(ab, X[j][d], dw1[d]);
+        Xb[j][d] = fma(ab, w.v[d], Xb[j][d]);
+      }
+      db1 += ab;
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) dw2[i] = fma(zb[j][i], h0[j], dw2[i]);
+    }
+    st.reserve(4 + NQ);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) st.put(dw1[d]);              // d w1[k,d]
+    st.put(db1);                                           // d b1[k]
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) st.put(dw2[i]);             // d w2[i,k]
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // saved-jet workspace: ws[slot][j*S + c][B] (component-major => coalesced across the warp).
 // slot 0: z jets (pre-MLP output), overwritten by their cotangents zb;
 // slot 1: q jets (<Z_i> streams),  overwritten by their cotangents qb.
@@ -1114,6 +1237,39 @@ post_backward_kernel(const SolverArgs a) {
   Stager<T> st = make_stager<T>(acc_all, tile_all, nacc);
 
   T* wsg = static_cast<T*>(a.ws);
+  if constexpr (S == 1 && QCP_VALUE_PPT > 1) {
+    constexpr int K = QCP_VALUE_PPT;
+    const long long chunk = (long long)blockDim.x * K;
+    const T* act = ws_act<T, NQ, S>(wsg, a.B) + (size_t)H * a.B;
+    for (long long b0 = (long long)blockIdx.x * chunk; b0 < a.B; b0 += (long long)gridDim.x * chunk) {
+      long long pts[K];
+      bool ok[K];
+      T q[K][NQ], qb[K][NQ], ub[K];
+      T db4 = T(0);
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const long long p0 = b0 + (long long)j * blockDim.x + threadIdx.x;
+        ok[j] = p0 < a.B;
+        pts[j] = ok[j] ? p0 : a.B - 1;
+        ub[j] = seed_cotangent<T, 1, TIO>(a, pts[j], ok[j]).c[0];
+        db4 += ub[j];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) q[j][i] = wsg[(size_t)(NQ + i) * a.B + pts[j]];   // slot 1
+      }
+      st.begin();
+      st.put(db4);                                         // d b4
+      post_backward_value<T, NQ, K, SaveAct<T>::value>(sw, H, q, ub, qb, st, act, a.B, pts);
+      st.flush();
+#pragma unroll
+      for (int j = 0; j < K; ++j)
+        if (ok[j]) {
+#pragma unroll
+          for (int i = 0; i < NQ; ++i) wsg[(size_t)(NQ + i) * a.B + pts[j]] = qb[j][i];
+        }
+    }
+    write_partials<T>(acc_all, nacc, static_cast<T*>(a.partials));
+    return;
+  }
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long Bpad = (a.B + 31) & ~31LL;
   for (long long p0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; p0 < Bpad; p0 += stride) {
@@ -1195,6 +1351,39 @@ pre_backward_kernel(const SolverArgs a) {
   const TIO* Xg = static_cast<const TIO*>(a.X);
   TIO* gXg = static_cast<TIO*>(a.gX);
   const T* wsg = static_cast<const T*>(a.ws);
+  if constexpr (S == 1 && QCP_VALUE_PPT > 1) {
+    constexpr int K = QCP_VALUE_PPT;
+    const long long chunk = (long long)blockDim.x * K;
+    const T* act = ws_act<T, NQ, S>(wsg, a.B);
+    for (long long b0 = (long long)blockIdx.x * chunk; b0 < a.B; b0 += (long long)gridDim.x * chunk) {
+      long long pts[K];
+      bool ok[K];
+      T X[K][3], zb[K][NQ], Xb[K][3];
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const long long p0 = b0 + (long long)j * blockDim.x + threadIdx.x;
+        ok[j] = p0 < a.B;
+        pts[j] = ok[j] ? p0 : a.B - 1;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) X[j][d] = (T)Xg[3 * pts[j] + d];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) zb[j][i] = ok[j] ? wsg[(size_t)i * a.B + pts[j]] : T(0);   // slot 0
+      }
+      st.begin();
+      pre_backward_value<T, NQ, K, SaveAct<T>::value>(sw, H, X, zb, Xb, st, act, a.B, pts);
+      st.flush();
+      if (gXg) {
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+          if (ok[j]) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) gXg[3 * pts[j] + d] = (TIO)Xb[j][d];
+          }
+      }
+    }
+    write_partials<T>(acc_all, nacc, static_cast<T*>(a.partials));
+    return;
+  }
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long Bpad = (a.B + 31) & ~31LL;
   for (long long p0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; p0 < Bpad; p0 += stride) {
