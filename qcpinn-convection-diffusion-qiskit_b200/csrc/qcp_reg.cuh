@@ -759,9 +759,11 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
   const int n = a.n, G = 1 << (n - LB), PP = WV == 2 ? 1 : 32 / G, NPT = S == 6 ? PP : (NW / WV) * PP, NE = NA + G;
   const Ctx<T, S> c{a};
   load_program<T, S>(a);
-  // per-WARP accumulator rows in global memory (zeroed by the host).  Every row has exactly one
-  // writer, so plain read-modify-writes in program order replace the atomicAdd of round 1 and the
-  // gradients are bit-reproducible (the rows are summed in row order by the reduction kernels)
+  // per-WARP accumulator rows in global memory (zeroed by the host).  Every address has exactly one
+  // writing THREAD, whose fire-and-forget RED.ADDs to it are applied in program order, so the sums
+  // are bit-reproducible (round 1 shared one row per CTA between its warps: the order of their
+  // atomics varied); the rows are summed in row order by the reduction kernels.  (A plain
+  // load-add-store instead of the RED costs 26 % of the step: its latency is exposed.)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t wrow = (size_t)blockIdx.x * NW + warp;
   double* const gth = a.theta_partials + wrow * (a.n_theta > 0 ? a.n_theta : 1);
@@ -903,7 +905,7 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
           }
           if (op.p >= 0) {
             for (int m = 16; m > 0; m >>= 1) part += shx(part, m);
-            if (lane == 0) gth[op.p] += 0.5 * (double)part;
+            if (lane == 0) atomicAdd(gth + op.p, 0.5 * (double)part);
           }
           break;
         }
@@ -932,7 +934,7 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
             // a warp carries 32 / G points when a vector needs fewer than 32 lanes: fold the
             // copies that address the same table entry before the single write
             for (int m = G; m < 32; m <<= 1) w += shx(w, m);
-            if (sub == 0) wa[i * G] += w;
+            if (sub == 0) atomicAdd(wa + i * G, w);
           }
           const C2A<T>* tb = diag + ((size_t)op.g << n) + lig;
           diag_apply<T, LB>(ax, ay, tb, G, true);
