@@ -1067,6 +1067,25 @@ __device__ __forceinline__ void ws_load(const T* ws, long long B, int slot, long
     for (int c = 0; c < S; ++c) v[j].c[c] = base[(size_t)(j * S + c) * B];
 }
 
+// L2 prefetch of the rows a LATER iteration of the persistent loop will load (this thread's element
+// of `rows` consecutive component rows of one slot): the loads at the top of an iteration are used
+// immediately, so without it every iteration exposes one full HBM latency
+#ifndef QCP_PREFETCH
+#define QCP_PREFETCH 1
+#endif
+template <typename T>
+__device__ __forceinline__ void ws_prefetch(const T* row0, long long B, int rows) {
+#if QCP_PREFETCH
+  // float64 only: -0.4 % at 4 194 304 points, -3.4 % at 524 288; float32 measured +1 % (its
+  // iterations are short enough for the hardware to cover the latency across warps)
+  if constexpr (sizeof(T) == 8) {
+#pragma unroll 4
+    for (int r = 0; r < rows; ++r)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(row0 + (size_t)r * B));
+  }
+#endif
+}
+
 // slot 2 of the workspace: saved tanh values act[2H][B] behind the two jet slots
 template <typename T, int NQ, int S>
 __device__ __forceinline__ T* ws_act(T* ws, long long B) {
@@ -1278,6 +1297,7 @@ post_backward_kernel(const SolverArgs a) {
     const Jet<T, S> ub = seed_cotangent<T, S, TIO>(a, p, valid);
     Jet<T, S> q[NQ], qb[NQ];
     ws_load<T, NQ, S>(wsg, a.B, 1, p, q);
+    if (p0 + stride < a.B) ws_prefetch<T>(wsg + (size_t)NQ * S * a.B + p0 + stride, a.B, NQ * S);
     st.begin();
     st.put(ub.c[0]);                                       // d b4
     post_backward<T, NQ, S, SaveAct<T>::value>(sw, H, q, ub, qb, st,
@@ -1313,6 +1333,7 @@ contract_backward_kernel(const SolverArgs a) {
     const long long p0 = b0 + threadIdx.x;
     const bool valid = p0 < a.B;
     const long long p = valid ? p0 : a.B - 1;
+    if (p0 + stride < a.B) ws_prefetch<T>(wsg + p0 + stride, a.B, 2 * NQ * S);   // z and qb rows
     st.begin();
     if constexpr (ENC == QCP_ENC_ANGLE && S == 6 && Tune<T, S>::kTwoPass && QCP_STREAM_PASSES) {
       angle_backward_ws<T, NQ, MODE>(sC, wsg, a.B, p, valid, st);
@@ -1392,6 +1413,7 @@ pre_backward_kernel(const SolverArgs a) {
     T X[3] = {(T)Xg[3 * p], (T)Xg[3 * p + 1], (T)Xg[3 * p + 2]};
     Jet<T, S> zb[NQ];
     ws_load<T, NQ, S>(wsg, a.B, 0, p, zb);
+    if (p0 + stride < a.B) ws_prefetch<T>(wsg + p0 + stride, a.B, NQ * S);
     if (!valid) {
 #pragma unroll
       for (int j = 0; j < NQ; ++j) jzero(zb[j]);
