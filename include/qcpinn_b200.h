@@ -38,13 +38,22 @@ enum qcp_gate_kind {
   QCP_GATE_CRZ = 4,
   QCP_GATE_CNOT = 5, /* (control, target, -1)             */
   QCP_GATE_H = 6,    /* (wire, -, -1)                     */
-  QCP_GATE_U4 = 7    /* (wire_hi, wire_lo, const_index): fixed 4x4 unitary (the Haar blocks,
+  QCP_GATE_U4 = 7,   /* (wire_hi, wire_lo, const_index): fixed 4x4 unitary (the Haar blocks,
                         reference nn/DVQuantumLayer.py:203-209) */
+  /* Per-SAMPLE gates inside the program ("jet gates"): the angle is scale * z[input], z = the
+   * layer's per-point input vector, and the six Taylor streams are coupled through the gate's
+   * derivatives.  They serve the data re-uploading circuit family of reference
+   * hybrid_testing/CG_HQPINN_IBMtest_16qubits.py:217-235 (RY(x_i) encoding, RZ(0.5 x_j) re-upload
+   * in every layer).  Fields: (wire, input index, scale in quarters: 4 = 1.0, 2 = 0.5). */
+  QCP_GATE_RY_IN = 8,
+  QCP_GATE_RZ_IN = 9,
+  QCP_GATE_CZ = 10   /* (wire, wire, -1): diag(1, 1, 1, -1), reference :230-234 */
 };
 
 enum qcp_encoding {
   QCP_ENC_ANGLE = 0,     /* AngleEmbedding(rotation="X"), reference nn/DVQuantumLayer.py:182   */
-  QCP_ENC_AMPLITUDE = 1  /* AmplitudeEmbedding(normalize=True, pad_with=0), reference :178-180 */
+  QCP_ENC_AMPLITUDE = 1, /* AmplitudeEmbedding(normalize=True, pad_with=0), reference :178-180 */
+  QCP_ENC_NONE = 2       /* start from |0...0>: the program itself holds the per-sample gates */
 };
 
 enum qcp_dtype { QCP_F32 = 0, QCP_F64 = 1 };

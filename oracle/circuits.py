@@ -15,6 +15,9 @@ import numpy as np
 import torch
 
 ANSATZ_NAMES = ("layered", "alternate", "cascade", "farhi", "sim_circ_15", "cross_mesh")
+# data re-uploading family of reference hybrid_testing/CG_HQPINN_IBMtest_16qubits.py:217-235 (its own
+# entry point: no separate encoding stage, no Haar blocks, no final Hadamard)
+REUPLOAD_NAMES = ("cz_melt",)
 
 
 def params_per_layer(ansatz: str, n: int) -> int:
@@ -31,6 +34,8 @@ def params_per_layer(ansatz: str, n: int) -> int:
         return 2 * n
     if ansatz == "cross_mesh":
         return 4 * n + n * (n - 1)
+    if ansatz == "cz_melt":
+        return 3 * n
     raise ValueError("Parameters are not initialized. Check the q_ansatz value.")
 
 
@@ -278,8 +283,34 @@ def encode(x, n, encoding, cdtype):
     return state
 
 
+def cz_melt_state(x, params, n, cdtype=torch.complex128):
+    """Reference ``hybrid_testing/CG_HQPINN_IBMtest_16qubits.py:217-235``: RY(x_i) on wire i; per
+    layer and wire RZ(0.5 x_{(i+layer) % n}) then Rot(phi, theta, omega) = RZ(omega) RY(theta)
+    RZ(phi) with (phi, theta, omega) = weights[layer, i, :]; CZ on even pairs, odd pairs and
+    (n-1, 0).  ``params``: (L, 3n) = the reference's (L, n, 3) weights flattened."""
+    b = x.shape[0]
+    state = torch.zeros(b, 2 ** n, dtype=cdtype)
+    state[:, 0] = 1.0
+    cz = torch.diag(torch.tensor([1, 1, 1, -1], dtype=cdtype))
+    for i in range(n):
+        state = apply_matrix(state, ry_matrix(x[:, i], cdtype), [i], n)
+    for layer in range(params.shape[0]):
+        row = params[layer]
+        for i in range(n):
+            state = apply_matrix(state, rz_matrix(0.5 * x[:, (i + layer) % n], cdtype), [i], n)
+            state = apply_matrix(state, rz_matrix(row[3 * i], cdtype), [i], n)
+            state = apply_matrix(state, ry_matrix(row[3 * i + 1], cdtype), [i], n)
+            state = apply_matrix(state, rz_matrix(row[3 * i + 2], cdtype), [i], n)
+        pairs = [(i, i + 1) for i in range(0, n - 1, 2)] + [(i, i + 1) for i in range(1, n - 1, 2)]
+        for a, c in pairs + [(n - 1, 0)]:
+            state = apply_matrix(state, cz, [a, c], n)
+    return state
+
+
 def final_state(x, params, ansatz, n, encoding="angle", haar=None, cdtype=torch.complex128):
     """State just before measurement: encoding -> L x ansatz -> [Haar] -> H(last wire)."""
+    if ansatz == "cz_melt":
+        return cz_melt_state(x, params, n, cdtype)
     state = encode(x, n, encoding, cdtype)
     for layer in range(params.shape[0]):
         row = params[layer]

@@ -786,9 +786,10 @@ int qcp_plan_create(qcp_plan_t** out, int n_qubits, int encoding, int dtype, int
     set_error("qcp_plan_create: 2..%d qubits are supported, got %d", kMaxQubitsSv, n_qubits);
     return 1;
   }
-  if (encoding != QCP_ENC_ANGLE && encoding != QCP_ENC_AMPLITUDE) {
+  if (encoding != QCP_ENC_ANGLE && encoding != QCP_ENC_AMPLITUDE && encoding != QCP_ENC_NONE) {
     set_error("qcp_plan_create: bad encoding %d", encoding); return 1;
   }
+  bool sample_gates = encoding == QCP_ENC_NONE;
   if (dtype != QCP_F32 && dtype != QCP_F64) { set_error("qcp_plan_create: bad dtype %d", dtype); return 1; }
   if (hidden < 1 || hidden > kMaxHidden) {
     set_error("qcp_plan_create: hidden width %d outside 1..%d", hidden, kMaxHidden); return 1;
@@ -797,10 +798,14 @@ int qcp_plan_create(qcp_plan_t** out, int n_qubits, int encoding, int dtype, int
   for (int g = 0; g < n_ops; ++g) {
     const int32_t* o = ops + 4 * g;
     const int kind = o[0];
-    const bool two = kind == QCP_GATE_CRX || kind == QCP_GATE_CRZ || kind == QCP_GATE_CNOT || kind == QCP_GATE_U4;
+    const bool two = kind == QCP_GATE_CRX || kind == QCP_GATE_CRZ || kind == QCP_GATE_CNOT ||
+                     kind == QCP_GATE_U4 || kind == QCP_GATE_CZ;
     const bool par = kind == QCP_GATE_RX || kind == QCP_GATE_RY || kind == QCP_GATE_RZ ||
                      kind == QCP_GATE_CRX || kind == QCP_GATE_CRZ;
-    if (kind < 0 || kind > QCP_GATE_U4 || o[1] < 0 || o[1] >= n_qubits ||
+    const bool smp = kind == QCP_GATE_RY_IN || kind == QCP_GATE_RZ_IN;
+    if (smp || kind == QCP_GATE_CZ) sample_gates = true;
+    if (kind < 0 || kind > QCP_GATE_CZ || o[1] < 0 || o[1] >= n_qubits ||
+        (smp && (o[2] < 0 || o[2] >= n_qubits || o[3] < 1 || o[3] > 64)) ||
         (two && (o[2] < 0 || o[2] >= n_qubits || o[2] == o[1])) ||
         (par && (o[3] < 0 || o[3] >= n_theta)) ||
         (kind == QCP_GATE_U4 && (o[3] < 0 || o[3] >= n_consts))) {
@@ -815,7 +820,8 @@ int qcp_plan_create(qcp_plan_t** out, int n_qubits, int encoding, int dtype, int
   memset(p, 0, sizeof(*p));
   p->n = n_qubits; p->enc = encoding; p->dtype = dtype; p->H = hidden;
   p->n_ops = n_ops; p->n_consts = n_consts; p->n_theta = n_theta;
-  p->engine_l = n_qubits > kMaxQubitsFused;
+  // per-sample gates inside the program (and CZ) run on the gate-by-gate engine L, whatever n
+  p->engine_l = n_qubits > kMaxQubitsFused || sample_gates;
   {
     const char* ov = getenv("QCP_THETA_OVERLAP");
     p->overlap_theta = !(ov && ov[0] == '0');
@@ -856,7 +862,9 @@ int qcp_plan_create(qcp_plan_t** out, int n_qubits, int encoding, int dtype, int
     qcp_plan_destroy(p);
     return 1;
   }
-  if (p->engine_l && reg_supported(n_qubits, dtype)) {
+  if (sample_gates) {
+    // engine L only: the register / tiled planners move batch-shared gates
+  } else if (p->engine_l && reg_supported(n_qubits, dtype)) {
     p->reg = reg_create(n_qubits, encoding, dtype, reinterpret_cast<const GateOp*>(ops), n_ops, n_theta,
                         n_consts, p->d_ops, p->d_consts, p->num_sms);
     if (!p->reg) { qcp_plan_destroy(p); return 1; }

@@ -128,6 +128,16 @@ __device__ void apply_shared(Cx<T>* st, int NS, int n, const GateOp op, const M2
       }
       for (int j = 0; j < 4; ++j) base[idx[j]] = o[j];
     }
+  } else if (op.kind == QCP_GATE_CZ) {
+    // diag(1, 1, 1, -1) on (a, b): its own inverse
+    const int pa = n - 1 - op.a, pb = n - 1 - op.b;
+    const int both = (1 << pa) | (1 << pb);
+    for (int it = threadIdx.x; it < NS * M; it += blockDim.x) {
+      if (((it & (M - 1)) & both) == both) {
+        Cx<T>& v = st[it];
+        v = {-v.x, -v.y};
+      }
+    }
   } else {
     const bool ctl = op.kind == QCP_GATE_CRX || op.kind == QCP_GATE_CRZ || op.kind == QCP_GATE_CNOT;
     const int pt = n - 1 - (ctl ? op.b : op.a);
@@ -168,6 +178,32 @@ __device__ RxJet<T> make_rx_jet(const T* zj /* S comps */) {
   for (int d = 0; d < 3; ++d) r.zd[d] = S == 6 ? zj[1 + d] : T(0);
   for (int e = 0; e < 2; ++e) r.zdd[e] = S == 6 ? zj[4 + e] : T(0);
   return r;
+}
+
+// Per-sample Pauli rotation exp(-i a P / 2) anywhere in the program, a = scale * z (jets scaled
+// alike).  Every Pauli rotation satisfies dG/da = (-i/2) P G, d2G = -G/4, d3G = -dG/4, which is all
+// rx_jet_forward / rx_jet_backward use, so the same two routines serve RY and RZ; the cotangents
+// they return are with respect to the jet of a and are scaled back by the caller.
+template <typename T, int S>
+__device__ RxJet<T> make_sample_jet(int kind, T scale, const T* zj /* S comps */) {
+  RxJet<T> r;
+  T s, c;
+  Math<T>::sincos_(T(0.5) * scale * zj[0], &s, &c);
+  const T hs = T(0.5) * s, hc = T(0.5) * c, Z = T(0);
+  if (kind == QCP_GATE_RY_IN) {
+    r.G = {{{c, Z}, {-s, Z}, {s, Z}, {c, Z}}};
+    r.dG = {{{-hs, Z}, {-hc, Z}, {hc, Z}, {-hs, Z}}};
+  } else {   // QCP_GATE_RZ_IN: diag(e^{-ia/2}, e^{+ia/2})
+    r.G = {{{c, -s}, {Z, Z}, {Z, Z}, {c, s}}};
+    r.dG = {{{-hs, -hc}, {Z, Z}, {Z, Z}, {-hs, hc}}};
+  }
+  for (int d = 0; d < 3; ++d) r.zd[d] = S == 6 ? scale * zj[1 + d] : T(0);
+  for (int e = 0; e < 2; ++e) r.zdd[e] = S == 6 ? scale * zj[4 + e] : T(0);
+  return r;
+}
+
+__device__ __forceinline__ bool is_sample_gate(int kind) {
+  return kind == QCP_GATE_RY_IN || kind == QCP_GATE_RZ_IN;
 }
 
 template <typename T>
@@ -351,7 +387,7 @@ template <typename T>
 __device__ void build_table(M2<T>* table, const SvArgs<T>& a) {
   for (int g = threadIdx.x; g < a.n_ops; g += blockDim.x) {
     const GateOp op = a.ops[g];
-    if (op.kind != QCP_GATE_U4)
+    if (op.kind != QCP_GATE_U4 && op.kind != QCP_GATE_CZ && !is_sample_gate(op.kind))
       table[g] = gate_matrix<T>(op.kind, op.p >= 0 ? (double)a.theta[op.p] : 0.0);
   }
   __syncthreads();
@@ -364,7 +400,10 @@ __device__ void encode_forward(Cx<T>* psi, const SvArgs<T>& a, const T* zj /* [n
   const int n = a.n, M = 1 << n;
   for (int i = threadIdx.x; i < S * M; i += blockDim.x) psi[i] = {T(0), T(0)};
   __syncthreads();
-  if (a.enc == QCP_ENC_ANGLE) {
+  if (a.enc == QCP_ENC_NONE) {
+    if (threadIdx.x == 0) psi[0] = {T(1), T(0)};
+    __syncthreads();
+  } else if (a.enc == QCP_ENC_ANGLE) {
     if (threadIdx.x == 0) psi[0] = {T(1), T(0)};
     __syncthreads();
     for (int j = 0; j < n; ++j) {
@@ -392,6 +431,20 @@ __device__ void encode_forward(Cx<T>* psi, const SvArgs<T>& a, const T* zj /* [n
       }
     }
     __syncthreads();
+  }
+}
+
+// the gate program on the psi streams: batch-shared gates, and per-sample jet gates in place
+template <typename T, int S>
+__device__ void run_program_forward(Cx<T>* psi, const SvArgs<T>& a, const M2<T>* table, const T* zj) {
+  for (int g = 0; g < a.n_ops; ++g) {
+    const GateOp op = a.ops[g];
+    if (is_sample_gate(op.kind)) {
+      const RxJet<T> jg = make_sample_jet<T, S>(op.kind, T(0.25) * (T)op.p, zj + op.b * S);
+      rx_jet_forward<T, S>(psi, a.n, op.a, jg);
+    } else {
+      apply_shared<T>(psi, S, a.n, op, table[g], a.consts, false);
+    }
   }
 }
 
@@ -449,7 +502,7 @@ sv_forward_kernel(const SvArgs<T> a) {
     for (int e = threadIdx.x; e < n * S; e += blockDim.x) zj[e] = a.ws[(size_t)e * a.B + p];
     __syncthreads();
     encode_forward<T, S>(psi, a, zj, scratch);
-    for (int g = 0; g < a.n_ops; ++g) apply_shared<T>(psi, S, n, a.ops[g], table[g], a.consts, false);
+    run_program_forward<T, S>(psi, a, table, zj);
     measure<T, S>(psi, tmp, n, qj);
     for (int e = threadIdx.x; e < n * S; e += blockDim.x)
       a.ws_out[(size_t)(n * S + e) * a.B + p] = qj[e];
@@ -468,8 +521,9 @@ sv_backward_kernel(const SvArgs<T> a) {
   T* qb = zj + n * S;
   T* scratch = qb + n * S;
   double* gth = reinterpret_cast<double*>(scratch + 64);           // [n_theta]
+  double* zacc = gth + a.n_theta;                                  // [n*S] z cotangents of jet gates
   Cx<T>* base = a.slab ? a.slab + (size_t)blockIdx.x * a.slab_stride
-                       : reinterpret_cast<Cx<T>*>(gth + a.n_theta);
+                       : reinterpret_cast<Cx<T>*>(zacc + n * S);
   Cx<T>* psi = base;
   Cx<T>* lam = base + (size_t)S * M;
   build_table<T>(table, a);
@@ -480,11 +534,12 @@ sv_backward_kernel(const SvArgs<T> a) {
     for (int e = threadIdx.x; e < n * S; e += blockDim.x) {
       zj[e] = a.ws[(size_t)e * a.B + p];
       qb[e] = a.ws[(size_t)(n * S + e) * a.B + p];
+      zacc[e] = 0.0;
     }
     __syncthreads();
     // ---- recompute the forward state ------------------------------------------------------
     encode_forward<T, S>(psi, a, zj, scratch);
-    for (int g = 0; g < a.n_ops; ++g) apply_shared<T>(psi, S, n, a.ops[g], table[g], a.consts, false);
+    run_program_forward<T, S>(psi, a, table, zj);
     // ---- lambda streams from the q cotangents (lambda = 2 dL/d conj(psi)) --------------------
     for (int k = threadIdx.x; k < M; k += blockDim.x) {
       T zb[S];
@@ -522,6 +577,19 @@ sv_backward_kernel(const SvArgs<T> a) {
     // ---- gate program in reverse ------------------------------------------------------------
     for (int g = a.n_ops - 1; g >= 0; --g) {
       const GateOp op = a.ops[g];
+      if (is_sample_gate(op.kind)) {
+        const T scale = T(0.25) * (T)op.p;
+        const RxJet<T> jg = make_sample_jet<T, S>(op.kind, scale, zj + op.b * S);
+        double zb[S];
+        rx_jet_backward<T, S>(psi, lam, n, op.a, jg, zb);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const double tot = block_reduce(zb[s], red);
+          if (threadIdx.x == 0) zacc[op.b * S + s] += (double)scale * tot;
+        }
+        __syncthreads();
+        continue;
+      }
       if (op.p >= 0 && op.kind != QCP_GATE_U4) {
         const bool ctl = op.kind == QCP_GATE_CRX || op.kind == QCP_GATE_CRZ;
         const int pt = n - 1 - (ctl ? op.b : op.a);
@@ -550,7 +618,10 @@ sv_backward_kernel(const SvArgs<T> a) {
       apply_shared<T>(psi, 2 * S, n, op, table[g], a.consts, true);   // psi and lambda are contiguous
     }
     // ---- encoding in reverse -> cotangent jets of z --------------------------------------------
-    if (a.enc == QCP_ENC_ANGLE) {
+    if (a.enc == QCP_ENC_NONE) {
+      for (int e = threadIdx.x; e < n * S; e += blockDim.x) qb[e] = T(0);
+      __syncthreads();
+    } else if (a.enc == QCP_ENC_ANGLE) {
       for (int j = n - 1; j >= 0; --j) {
         const RxJet<T> g = make_rx_jet<T, S>(zj + j * S);
         double zb[S];
@@ -594,7 +665,8 @@ sv_backward_kernel(const SvArgs<T> a) {
       }
       __syncthreads();
     }
-    for (int e = threadIdx.x; e < n * S; e += blockDim.x) a.ws_out[(size_t)e * a.B + p] = qb[e];
+    for (int e = threadIdx.x; e < n * S; e += blockDim.x)
+      a.ws_out[(size_t)e * a.B + p] = (T)((double)qb[e] + zacc[e]);
     __syncthreads();
   }
   double* out = a.theta_partials + (size_t)blockIdx.x * a.n_theta;
@@ -616,7 +688,7 @@ __global__ void sv_reduce_theta_kernel(const double* partials, int grid, int n_t
 template <typename T>
 static size_t sv_small_smem(int n, int S, int n_ops, int n_theta, bool backward) {
   size_t b = sizeof(M2<T>) * (size_t)n_ops + sizeof(T) * ((size_t)2 * n * S + 64);
-  if (backward) b += sizeof(double) * (size_t)n_theta;
+  if (backward) b += sizeof(double) * ((size_t)n_theta + (size_t)n * S);
   return (b + 15) & ~size_t(15);
 }
 

@@ -20,7 +20,7 @@ import torch
 from torch.autograd.function import once_differentiable
 
 from . import _lib
-from .program import ENC_AMPLITUDE, ENC_ANGLE, CircuitProgram
+from .program import ENC_AMPLITUDE, ENC_ANGLE, ENC_NONE, CircuitProgram
 
 MODE_VALUE, MODE_RESIDUAL = 1, 6
 _DTYPE_CODE = {torch.float32: 0, torch.float64: 1}
@@ -51,6 +51,8 @@ class Plan:
             raise ValueError(f"qcpinn_b200 supports float32/float64 plans, got {dtype}")
         self.lib = _lib.require_cuda()
         self.program = program
+        if program.reupload:
+            encoding = ENC_NONE       # the program holds its own per-sample gates
         self.encoding = encoding
         self.dtype = dtype
         self.hidden = int(hidden)
@@ -76,10 +78,11 @@ class Plan:
                 self.n_theta)
         _lib.check(rc, "qcp_plan_create")
         self.num_features = self.lib.qcp_plan_num_features(self._handle)
-        self.fused_engine = self.n <= 4      # n > 4 runs on the per-sample statevector engines
         # "feature" (n <= 4) | "register" (5..10 qubits in registers) | "tiled" (up to 16 qubits,
-        # HBM slab swept through registers) | "global" (gate-by-gate fallback, QCP_ENGINE=L)
+        # HBM slab swept through registers) | "global" (gate by gate: QCP_ENGINE=L, and every
+        # program with per-sample gates inside the layers)
         self.engine = ("feature", "global", "register", "tiled")[self.lib.qcp_plan_engine(self._handle)]
+        self.fused_engine = self.engine == "feature"   # the others are per-sample statevector engines
         # element type of X / u / r / grad_u / grad_r / grad_X (weights, jets, grads stay `dtype`)
         self.io_dtype = dtype
         if io_dtype is not None and io_dtype != dtype and self.fused_engine and dtype == torch.float64:

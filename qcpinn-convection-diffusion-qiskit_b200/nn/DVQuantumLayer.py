@@ -60,6 +60,8 @@ class DVQuantumLayer(nn.Module):
         self._initialize_weights()
 
         seed = args.get("seed", None) if self.num_qubits >= 4 else None
+        if self.q_ansatz == "cz_melt":
+            seed = None          # the re-uploading family has no Haar blocks (reference 16-qubit script)
         self.haar_seed1 = seed
         self.haar_seed2 = seed + 1 if seed is not None else None
         self.use_batch_processing = True

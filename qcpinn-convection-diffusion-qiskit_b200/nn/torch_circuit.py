@@ -21,7 +21,7 @@ import math
 
 import torch
 
-from ..program import CNOT, CRX, CRZ, HAD, RX, RY, RZ, U4, CircuitProgram
+from ..program import CNOT, CRX, CRZ, CZ, HAD, RX, RY, RY_IN, RZ, RZ_IN, U4, CircuitProgram
 
 
 def _rot(kind: int, theta: torch.Tensor, cdtype) -> torch.Tensor:
@@ -73,7 +73,10 @@ def run_layer(program: CircuitProgram, encoding: str, x: torch.Tensor, theta: to
     x = x.to(rdtype)
     flat = theta.reshape(-1).to(rdtype)
     batch = x.shape[0]
-    if encoding == "amplitude":
+    if program.reupload:
+        state = torch.zeros((batch,) + (2,) * n, dtype=cdtype, device=x.device)
+        state[(slice(None),) + (0,) * n] = 1.0
+    elif encoding == "amplitude":
         feats = x
         if feats.shape[1] < 2 ** n:
             feats = torch.nn.functional.pad(feats, (0, 2 ** n - feats.shape[1]))
@@ -98,6 +101,11 @@ def run_layer(program: CircuitProgram, encoding: str, x: torch.Tensor, theta: to
             state = _apply_1q(state, had, a)
         elif kind == U4:
             state = _apply_u4(state, consts[p], a, b)
+        elif kind in (RY_IN, RZ_IN):          # per-sample rotation by (p / 4) * x[:, b]
+            state = _apply_1q(state, _rot(RY if kind == RY_IN else RZ, 0.25 * p * x[:, b], cdtype), a)
+        elif kind == CZ:
+            zflip = torch.tensor([[1, 0], [0, -1]], dtype=cdtype, device=x.device)
+            state = _apply_controlled(state, zflip, a, b)
         else:
             raise ValueError(f"unknown gate kind {kind}")
     probs = (state.real ** 2 + state.imag ** 2).reshape(batch, -1)

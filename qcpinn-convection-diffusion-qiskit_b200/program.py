@@ -14,8 +14,12 @@ from dataclasses import dataclass
 
 import numpy as np
 
-RX, RY, RZ, CRX, CRZ, CNOT, HAD, U4 = range(8)
-ENC_ANGLE, ENC_AMPLITUDE = 0, 1
+RX, RY, RZ, CRX, CRZ, CNOT, HAD, U4, RY_IN, RZ_IN, CZ = range(11)
+ENC_ANGLE, ENC_AMPLITUDE, ENC_NONE = 0, 1, 2
+
+# ansaetze whose per-sample gates live INSIDE the program (data re-uploading): no separate encoding
+# stage, no Haar blocks, no final Hadamard
+REUPLOAD_ANSATZ = ("cz_melt",)
 
 ANSATZ_PARAM_COUNT = {
     # reference nn/DVQuantumLayer.py:25-78
@@ -25,6 +29,8 @@ ANSATZ_PARAM_COUNT = {
     "farhi": lambda n: 2 * n - 2,
     "sim_circ_15": lambda n: 2 * n,
     "cross_mesh": lambda n: 4 * n + n * (n - 1),
+    # reference hybrid_testing/CG_HQPINN_IBMtest_16qubits.py:236 weight_shapes (n_layers, n_qubits, 3)
+    "cz_melt": lambda n: 3 * n,
 }
 
 
@@ -60,9 +66,31 @@ class _Emitter:
     def cnot(self, control: int, target: int):
         self.ops.append((CNOT, control, target, -1))
 
+    def cz(self, a: int, b: int):
+        self.ops.append((CZ, a, b, -1))
 
-def _emit_layer(ansatz: str, e: _Emitter, variant: str = "dv") -> None:
+    def sample_rot(self, kind: int, wire: int, input_index: int, quarters: int):
+        """Per-sample rotation by (quarters / 4) * z[input_index] (kind = RY_IN / RZ_IN)."""
+        self.ops.append((kind, wire, input_index, quarters))
+
+
+def _emit_layer(ansatz: str, e: _Emitter, variant: str = "dv", layer: int = 0) -> None:
     n = e.n
+    if ansatz == "cz_melt":
+        # reference hybrid_testing/CG_HQPINN_IBMtest_16qubits.py:224-234: per wire the re-upload
+        # RZ(0.5 * inputs[(i + layer) % n]) then Rot(phi, theta, omega) = RZ(omega) RY(theta) RZ(phi);
+        # CZ on even pairs, odd pairs, and the ring closure (n-1, 0)
+        for w in range(n):
+            e.sample_rot(RZ_IN, w, (w + layer) % n, 2)
+            e.rot(RZ, w)
+            e.rot(RY, w)
+            e.rot(RZ, w)
+        for w in range(0, n - 1, 2):
+            e.cz(w, w + 1)
+        for w in range(1, n - 1, 2):
+            e.cz(w, w + 1)
+        e.cz(n - 1, 0)
+        return
     if ansatz == "alternate" and variant == "single_file":
         # reference train_hybrid_qpinn.py:273-295: neighbour pairs WITHOUT the wrap-around pair, so
         # even qubit counts work (4n - 4 angles are exactly enough)
@@ -154,6 +182,11 @@ class CircuitProgram:
     def params_per_layer(self) -> int:
         return self.n_theta // max(self.n_layers, 1)
 
+    @property
+    def reupload(self) -> bool:
+        """True when the per-sample gates are part of the program (no separate encoding stage)."""
+        return self.ansatz in REUPLOAD_ANSATZ
+
 
 def compile_program(ansatz: str, n_qubits: int, n_layers: int, haar_seed=None,
                     variant: str = "dv") -> CircuitProgram:
@@ -164,6 +197,17 @@ def compile_program(ansatz: str, n_qubits: int, n_layers: int, haar_seed=None,
     """
     per_layer = params_per_layer(ansatz, n_qubits)
     ops: list[tuple[int, int, int, int]] = []
+    if ansatz in REUPLOAD_ANSATZ:
+        # RY(inputs[i]) on wire i (reference :220-221), the layers, measurement; nothing else
+        for w in range(n_qubits):
+            ops.append((RY_IN, w, w, 4))
+        for layer in range(n_layers):
+            em = _Emitter(n_qubits, layer * per_layer, per_layer)
+            _emit_layer(ansatz, em, variant, layer)
+            ops.extend(em.ops)
+        table = np.asarray(ops, dtype=np.int32).reshape(-1, 4)
+        return CircuitProgram(n_qubits, n_layers, ansatz, table,
+                              np.zeros((0, 4, 4), dtype=np.complex128), n_layers * per_layer)
     for layer in range(n_layers):
         em = _Emitter(n_qubits, layer * per_layer, per_layer)
         _emit_layer(ansatz, em, variant)

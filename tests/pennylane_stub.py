@@ -47,7 +47,7 @@ class Operation:
 
 def _make(name):
     def ctor(*args, wires=None, **kw):
-        if name in ("CNOT", "Hadamard", "PauliZ"):
+        if name in ("CNOT", "Hadamard", "PauliZ", "CZ"):
             if wires is None and args:
                 wires = args[0]
             return Operation(name, wires)
@@ -60,6 +60,14 @@ def _make(name):
 
 RX, RY, RZ, PhaseShift, CRX, CRZ = (_make(k) for k in ("RX", "RY", "RZ", "PhaseShift", "CRX", "CRZ"))
 CNOT, Hadamard, QubitUnitary = _make("CNOT"), _make("Hadamard"), _make("QubitUnitary")
+CZ = _make("CZ")
+
+
+def Rot(phi, theta, omega, wires=None):
+    """PennyLane: Rot(phi, theta, omega) = RZ(omega) RY(theta) RZ(phi) (RZ(phi) acts first)."""
+    Operation("RZ", wires, param=phi)
+    Operation("RY", wires, param=theta)
+    Operation("RZ", wires, param=omega)
 
 
 class PauliZ:
@@ -190,6 +198,9 @@ def execute(tape, n, batch):
             state = _apply_controlled(state, _rot_matrix(op.name[1:], op.param), *op.wires)
         elif op.name == "CNOT":
             state = _apply_controlled(state, xflip, *op.wires)
+        elif op.name == "CZ":
+            state = _apply_controlled(state, torch.tensor([[1, 0], [0, -1]], dtype=torch.complex128),
+                                      *op.wires)
         elif op.name == "Hadamard":
             state = _apply_1q(state, had, op.wires[0])
         elif op.name == "QubitUnitary":
@@ -220,7 +231,7 @@ class QNode:
             _TAPE = outer
         QNode.last_tape = tape
         n = self.device.num_wires
-        x = torch.as_tensor(args[0])
+        x = torch.as_tensor(args[0] if args else kw.get("inputs"))
         batched = x.dim() == 2
         batch = x.shape[0] if batched else 1
         state = execute(tape, n, batch)
@@ -232,6 +243,33 @@ class QNode:
             val = probs @ sign
             out.append(val if batched else val[0])
         return out
+
+
+def qnode(dev, interface="torch", diff_method="backprop", **kw):
+    """``@qml.qnode(device, ...)`` decorator form."""
+    def wrap(func):
+        return QNode(func, dev, interface=interface, diff_method=diff_method, **kw)
+    return wrap
+
+
+class _TorchLayer(torch.nn.Module):
+    """Minimal ``qml.qnn.TorchLayer``: owns one Parameter per entry of ``weight_shapes`` (uniform in
+    [0, 2 pi) like PennyLane's default init) and calls the QNode with ``inputs=`` plus the weights
+    as keyword arguments; the measurement list comes back stacked."""
+
+    def __init__(self, qnode_obj, weight_shapes):
+        super().__init__()
+        self.qnode = qnode_obj
+        for name, shape in weight_shapes.items():
+            self.register_parameter(name, torch.nn.Parameter(2 * math.pi * torch.rand(shape)))
+        self._names = list(weight_shapes)
+
+    def forward(self, inputs):
+        out = self.qnode(inputs=inputs, **{k: getattr(self, k) for k in self._names})
+        return torch.stack(list(out), dim=-1) if inputs.dim() == 2 else torch.stack(list(out))
+
+
+qnn = types.SimpleNamespace(TorchLayer=_TorchLayer)
 
 
 def install():

@@ -176,3 +176,61 @@ def test_reference_solver_and_residual_equal_oracle(ref, tmp_path, ansatz, n, la
         assert rel(p.grad, grads[k]) < 5e-5, k
     with pytest.raises(ValueError, match="Expected 2D input"):
         model(torch.zeros(3))
+
+
+# ---------------------------------------------------------------------------------------------------
+# data re-uploading circuit family: reference hybrid_testing/CG_HQPINN_IBMtest_16qubits.py
+# ---------------------------------------------------------------------------------------------------
+CZ_SCRIPT = os.path.join(REF, "hybrid_testing", "CG_HQPINN_IBMtest_16qubits.py")
+
+
+@pytest.fixture(scope="module")
+def cz_script(ref):
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("reference_cg_hqpinn_16q", CZ_SCRIPT)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = mod          # dataclasses resolve cls.__module__ through sys.modules
+    spec.loader.exec_module(mod)
+    yield mod
+    sys.modules.pop(spec.name, None)
+
+
+@pytest.mark.parametrize("n,layers", [(2, 1), (4, 1), (5, 3), (6, 2), (8, 2)])
+def test_reference_reupload_layer_equals_program_and_oracle(ref, cz_script, n, layers):
+    """The reference's own ``make_quantum_layer`` (RY encoding, RZ(0.5 x) re-upload inside every
+    layer, Rot, CZ brick + ring; :217-253), executed unmodified: its gate tape equals
+    ``compile_program("cz_melt")`` gate for gate (incl. which input feeds which re-upload gate and
+    the 0.5 scale) and its outputs / gradients equal the oracle extension."""
+    if ref[-1]:
+        pytest.skip("tape inspection needs the stub")
+    import pennylane as qml
+
+    layer = cz_script.make_quantum_layer(qml.device("default.qubit", wires=n), n, layers, "backprop").double()
+    g = torch.Generator().manual_seed(3 * n + layers)
+    x = torch.randn(4, n, generator=g, dtype=torch.float64).requires_grad_(True)
+    out = layer(x)                                                    # (B, n), one sample at a time
+    w = layer.layer.weights                                           # (L, n, 3)
+    assert out.shape == (4, n) and tuple(w.shape) == (layers, n, 3)
+    tape = pennylane_stub.QNode.last_tape                             # the last sample's circuit
+    prog = P.compile_program("cz_melt", n, layers)
+    assert prog.n_theta == w.numel() and prog.reupload
+    name = {P.RY: "RY", P.RZ: "RZ", P.CZ: "CZ", P.RY_IN: "RY", P.RZ_IN: "RZ"}
+    assert len(tape) == prog.ops.shape[0]
+    flat = w.detach().reshape(-1)
+    for op, (kind, a, b, p) in zip(tape, prog.ops.tolist()):
+        assert op.name == name[kind], (op, kind)
+        assert op.wires == ([a, b] if kind == P.CZ else [a])
+        if kind in (P.RY_IN, P.RZ_IN):
+            assert abs(float(op.param.detach()) - 0.25 * p * float(x[-1, b])) < 1e-15
+        elif kind != P.CZ:
+            assert float(op.param.detach()) == float(flat[p])
+    xo = x.detach().clone().requires_grad_(True)
+    wo = w.detach().reshape(layers, 3 * n).clone().requires_grad_(True)
+    want = oc.quantum_layer(xo, wo, "cz_melt", n)                    # (n, B)
+    assert float((out.T - want).abs().max()) < 1e-12
+    cot = torch.randn(4, n, generator=g, dtype=torch.float64)
+    (out * cot).sum().backward()
+    (want * cot.T).sum().backward()
+    assert float((x.grad - xo.grad).abs().max()) < 1e-11
+    assert float((w.grad.reshape(layers, 3 * n) - wo.grad).abs().max()) < 1e-11
