@@ -352,16 +352,16 @@ int reg_run(RegPlan* r, int S, bool backward, void* ws, long long B, void* state
   for (int q = 0; q < r->n; ++q) a.meas_pos[q] = r->meas_pos[q];
   a.rops = r->d_rops; a.gates = r->d_gates; a.consts = r->d_consts; a.theta = r->theta;
   a.diag = r->d_diag; a.ws = ws; a.B = B; a.state = state;
-  const int rows = grid * rg_warps(S, r->WV);      // one accumulator row per warp (deterministic sums)
+  const int rows = grid * rg_warps(S, r->WV);      // theta partials: one row per warp (deterministic sums)
   if (backward) {
     const int nt = r->n_theta > 0 ? r->n_theta : 1;
     if (grow((void**)&r->d_tpart, &r->tpart_bytes, sizeof(double) * (size_t)rows * nt)) return 1;
-    if (grow(&r->d_wpart, &r->wpart_bytes, es * ((size_t)rows * (r->n_blk > 0 ? r->n_blk : 1) << r->n))) return 1;
+    if (grow(&r->d_wpart, &r->wpart_bytes, es * ((size_t)grid * (r->n_blk > 0 ? r->n_blk : 1) << r->n))) return 1;
     a.theta_partials = r->d_tpart;
     a.w_partials = r->d_wpart;
     cudaError_t ez = cudaMemsetAsync(r->d_tpart, 0, sizeof(double) * (size_t)rows * nt, s);
     if (ez == cudaSuccess && r->n_blk > 0)
-      ez = cudaMemsetAsync(r->d_wpart, 0, es * ((size_t)rows * r->n_blk << r->n), s);
+      ez = cudaMemsetAsync(r->d_wpart, 0, es * ((size_t)grid * r->n_blk << r->n), s);
     if (ez != cudaSuccess) { set_error("engine R: cudaMemsetAsync failed: %s", cudaGetErrorString(ez)); return 1; }
   }
   const int rc = r->dtype == QCP_F64 ? rg_launch<double>(r->LB, r->WV, S, backward, a, grid, L.total, s)
@@ -374,13 +374,13 @@ int reg_run(RegPlan* r, int S, bool backward, void* ws, long long B, void* state
   if (r->dtype == QCP_F64) {
     if (tb) rg_reduce_theta_kernel<double><<<tb, 128, 0, s>>>(r->d_tpart, rows, r->n_theta, static_cast<double*>(grad_theta));
     if (total) {
-      rg_wsum_kernel<double><<<(total + 127) / 128, 128, 0, s>>>(static_cast<const double*>(r->d_wpart), rows, total, r->d_wsum);
+      rg_wsum_kernel<double><<<(total + 127) / 128, 128, 0, s>>>(static_cast<const double*>(r->d_wpart), grid, total, r->d_wsum);
       rg_diag_grad_kernel<double><<<r->n_dg, 256, 0, s>>>(r->n, r->LB, r->d_bpos, r->d_dg, r->d_wsum, static_cast<double*>(grad_theta));
     }
   } else {
     if (tb) rg_reduce_theta_kernel<float><<<tb, 128, 0, s>>>(r->d_tpart, rows, r->n_theta, static_cast<float*>(grad_theta));
     if (total) {
-      rg_wsum_kernel<float><<<(total + 127) / 128, 128, 0, s>>>(static_cast<const float*>(r->d_wpart), rows, total, r->d_wsum);
+      rg_wsum_kernel<float><<<(total + 127) / 128, 128, 0, s>>>(static_cast<const float*>(r->d_wpart), grid, total, r->d_wsum);
       rg_diag_grad_kernel<float><<<r->n_dg, 256, 0, s>>>(r->n, r->LB, r->d_bpos, r->d_dg, r->d_wsum, static_cast<float*>(grad_theta));
     }
   }

@@ -74,7 +74,7 @@ struct RgArgs {
   long long B;
   void* state;                   // final psi streams [B][S][2^n] complex, or null
   double* theta_partials;        // [grid * warps][n_theta]     one row per WARP: plain read-modify-
-  void* w_partials;              // T[grid * warps][n_blk << n]  write, summed in row order afterwards
+  void* w_partials;              // T[grid][n_blk << n]  one row per CTA, one writing thread per entry
 };
 
 template <typename T>
@@ -767,7 +767,7 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t wrow = (size_t)blockIdx.x * NW + warp;
   double* const gth = a.theta_partials + wrow * (a.n_theta > 0 ? a.n_theta : 1);
-  T* const wacc = static_cast<T*>(a.w_partials) + (wrow * a.n_blk << n);
+  T* const wacc = static_cast<T*>(a.w_partials) + ((size_t)blockIdx.x * a.n_blk << n);
   const int wv = WV == 2 ? warp & 1 : 0, vec = warp / WV;          // half of / index of this warp's vector
   const int lig = WV == 2 ? (wv << 5) | lane : lane & (G - 1), sub = WV == 2 ? 0 : lane / G;
   const int slot = S == 6 ? sub : vec * PP + sub;
@@ -927,15 +927,29 @@ rg_backward_kernel(const __grid_constant__ RgArgs a) {
           break;
         }
         case R_DIAG: {
-          T* wa = wacc + ((size_t)op.g << n) + lig;
+          // W[k] += Im(conj(lambda_k) psi_k), summed over the CTA's vectors in a FIXED order through
+          // the exchange buffer (the ops run in lockstep, nobody else uses it now), then one RED per
+          // table entry from the thread that always owns that entry: bit-reproducible, and 1/NV of
+          // the atomics of a per-vector accumulation
+          constexpr int NV = NW / WV;
+          const int M = 1 << n;
+          T* wb = reinterpret_cast<T*>(c.exch());                 // [NV][M] reals
 #pragma unroll
           for (int i = 0; i < NA; ++i) {
-            T w = fma(lx[i], ay[i], -ly[i] * ax[i]);             // Im(conj(lambda) psi)
-            // a warp carries 32 / G points when a vector needs fewer than 32 lanes: fold the
-            // copies that address the same table entry before the single write
+            T w = fma(lx[i], ay[i], -ly[i] * ax[i]);
+            // a warp carries 32 / G points when a vector needs fewer than 32 lanes: fold them
             for (int m = G; m < 32; m <<= 1) w += shx(w, m);
-            if (sub == 0) atomicAdd(wa + i * G, w);
+            if (sub == 0) wb[(size_t)vec * M + i * G + lig] = w;
           }
+          __syncthreads();
+          T* wa = wacc + ((size_t)op.g << n);
+          for (int e = threadIdx.x; e < M; e += blockDim.x) {
+            T sum = wb[e];
+#pragma unroll
+            for (int v = 1; v < NV; ++v) sum += wb[(size_t)v * M + e];
+            atomicAdd(wa + e, sum);
+          }
+          __syncthreads();
           const C2A<T>* tb = diag + ((size_t)op.g << n) + lig;
           diag_apply<T, LB>(ax, ay, tb, G, true);
           diag_apply<T, LB>(lx, ly, tb, G, true);
