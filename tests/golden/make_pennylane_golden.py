@@ -170,6 +170,40 @@ def build_case(mods, tmp_dir, name, ansatz, n, layers, enc, seed):
     }
 
 
+REUPLOAD_CASES = [("reupload6_l2", 6, 2), ("reupload4_l1", 4, 1)]
+
+
+def build_reupload_case(reference_root, name, n, layers):
+    """The data re-uploading layer of reference hybrid_testing/CG_HQPINN_IBMtest_16qubits.py:217-253
+    (its own ``make_quantum_layer``, unmodified): outputs (B, n) and the gradients of a fixed linear
+    functional with respect to the inputs and the (L, n, 3) weights, in float64."""
+    import importlib.util
+
+    import pennylane as qml
+
+    path = os.path.join(reference_root, "hybrid_testing", "CG_HQPINN_IBMtest_16qubits.py")
+    spec = importlib.util.spec_from_file_location("reference_cg_hqpinn_16q_gen", path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = mod
+    spec.loader.exec_module(mod)
+    torch.manual_seed(100 + n)
+    layer = mod.make_quantum_layer(qml.device("default.qubit", wires=n), n, layers, "backprop").double()
+    g = torch.Generator().manual_seed(7 + n)
+    x = torch.randn(5, n, generator=g, dtype=torch.float64).requires_grad_(True)
+    cot = torch.randn(5, n, generator=g, dtype=torch.float64)
+    out = layer(x)
+    (out * cot).sum().backward()
+    weights = layer.layer.weights
+    simulator = "pennylane_stub" if qml.__version__.endswith("stub") else "pennylane default.qubit"
+    return {"format": FORMAT_VERSION,
+            "meta": {"ansatz": "cz_melt", "n": n, "layers": layers, "simulator": simulator,
+                     "pennylane": qml.__version__,
+                     "source": "reference hybrid_testing/CG_HQPINN_IBMtest_16qubits.py make_quantum_layer"},
+            "x": x.detach().clone(), "cot": cot, "theta": weights.detach().reshape(layers, 3 * n).clone(),
+            "q": out.detach().clone(), "grad_x": x.grad.detach().clone(),
+            "grad_theta": weights.grad.detach().reshape(layers, 3 * n).clone()}
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
     ap.add_argument("--reference", default="/root/reference")
@@ -203,6 +237,10 @@ def main(argv=None):
             path = os.path.join(ns.out, prefix + case[0] + ".pt")
             torch.save(fix, path)
             print("wrote", path)
+    for name, n, layers in REUPLOAD_CASES:
+        path = os.path.join(ns.out, prefix + name + ".pt")
+        torch.save(build_reupload_case(ns.reference, name, n, layers), path)
+        print("wrote", path)
     return 0
 
 

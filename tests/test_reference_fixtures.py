@@ -23,8 +23,12 @@ from helpers import F, TOL, device_weights, mlp_list, rel_err
 from oracle import solver as osolver
 
 HERE = os.path.join(os.path.dirname(__file__), "golden")
-STUB = sorted(glob.glob(os.path.join(HERE, "refstub_*.pt")))
-REAL = sorted(glob.glob(os.path.join(HERE, "pennylane_*.pt")))
+_ALL_STUB = sorted(glob.glob(os.path.join(HERE, "refstub_*.pt")))
+_ALL_REAL = sorted(glob.glob(os.path.join(HERE, "pennylane_*.pt")))
+_is_reupload = lambda p: "reupload" in os.path.basename(p)     # noqa: E731
+STUB = [p for p in _ALL_STUB if not _is_reupload(p)]
+REAL = [p for p in _ALL_REAL if not _is_reupload(p)]
+REUPLOAD = [p for p in _ALL_STUB + _ALL_REAL if _is_reupload(p)]
 COEFFS = (1.0, 1.0, 1.0, -0.01, -0.01)
 
 
@@ -50,7 +54,7 @@ def _load(path):
 
 
 def test_stub_fixtures_are_committed():
-    assert len(STUB) == 9, "run tests/golden/make_pennylane_golden.py --stub"
+    assert len(STUB) == 9 and len(REUPLOAD) >= 2, "run tests/golden/make_pennylane_golden.py --stub"
 
 
 @pytest.mark.parametrize("path", ALL)
@@ -98,3 +102,36 @@ def test_cuda_matches_reference_fixture(path, dtype):
     assert rel_err(loss, fix["terms"]["loss"]) < 1e-5
     for k, g in fix["grads"].items():
         assert rel_err(dw[k].grad, g) < 2e-5, k
+
+
+@pytest.mark.parametrize("path", REUPLOAD, ids=_ids(REUPLOAD))
+def test_oracle_matches_reupload_fixture(path):
+    """Fixtures of the reference's re-uploading layer (make_quantum_layer executed unmodified)."""
+    from oracle import circuits as oc
+
+    fix = torch.load(path, weights_only=False)
+    m = fix["meta"]
+    x = fix["x"].clone().requires_grad_(True)
+    th = fix["theta"].clone().requires_grad_(True)
+    q = oc.quantum_layer(x, th, "cz_melt", m["n"])                 # (n, B)
+    assert rel_err(q.T, fix["q"]) < 1e-10
+    (q.T * fix["cot"]).sum().backward()
+    assert rel_err(x.grad, fix["grad_x"]) < 1e-10 and rel_err(th.grad, fix["grad_theta"]) < 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", REUPLOAD, ids=_ids(REUPLOAD))
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_cuda_matches_reupload_fixture(path, dtype):
+    fix = torch.load(path, weights_only=False)
+    m = fix["meta"]
+    dev = torch.device("cuda", 0)
+    prog = qb.program.compile_program("cz_melt", m["n"], m["layers"])
+    plan = F.Plan(prog, 0, dtype, 50, dev)
+    x = fix["x"].to(dev, dtype).requires_grad_(True)
+    th = fix["theta"].to(dev, dtype).requires_grad_(True)
+    q = F.layer_apply(plan, x, th)
+    (q.T * fix["cot"].to(dev, dtype)).sum().backward()
+    tol = TOL[dtype]
+    assert rel_err(q.T, fix["q"]) < tol
+    assert rel_err(x.grad, fix["grad_x"]) < 10 * tol and rel_err(th.grad, fix["grad_theta"]) < 10 * tol
