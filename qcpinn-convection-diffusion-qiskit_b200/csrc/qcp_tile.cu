@@ -102,6 +102,8 @@ struct TilePlan {
   void* d_slab;
   size_t slab_bytes;
   double* d_tpart;
+  void* d_cot = nullptr;       // cotangent-pass scratch (per-warp table cotangents, contributions)
+  size_t cot_bytes = 0;
   size_t tpart_bytes;
   const void* theta;
 };
@@ -460,7 +462,7 @@ TilePlan* tile_create(int n, int enc, int dtype, const GateOp* host_ops, int n_o
 void tile_destroy(TilePlan* r) {
   if (!r) return;
   cudaFree(r->d_rops); cudaFree(r->d_sweeps); cudaFree(r->d_slab); cudaFree(r->d_tpart);
-  cudaFree(r->d_dg); cudaFree(r->d_doff); cudaFree(r->d_diag); cudaFree(r->d_wpart); cudaFree(r->d_wsum);
+  cudaFree(r->d_dg); cudaFree(r->d_doff); cudaFree(r->d_diag); cudaFree(r->d_wpart); cudaFree(r->d_wsum); cudaFree(r->d_cot);
   delete r;
 }
 
@@ -527,15 +529,22 @@ int tile_run(TilePlan* r, int S, bool backward, void* ws, long long B, void* sta
   a.n_blk = r->n_blk; a.doff = r->d_doff; a.diag = r->d_diag;
   if (backward) {
     const int nt = r->n_theta > 0 ? r->n_theta : 1;
-    if (grow((void**)&r->d_tpart, &r->tpart_bytes, sizeof(double) * (size_t)grid * nt)) return 1;
+    const int rows = grid * tl_warps(true);           // theta partials: one row per warp
+    if (grow((void**)&r->d_tpart, &r->tpart_bytes, sizeof(double) * (size_t)rows * nt)) return 1;
     a.theta_partials = r->d_tpart;
+    {
+      const int NA = 1 << r->LB, NE = NA + 32 + (1 << (r->n - (r->LB + 5)));
+      a.cot_stride = (size_t)tl_warps(true) * NE * S + (size_t)NE * kMaxOther * S;
+      if (grow(&r->d_cot, &r->cot_bytes, es * a.cot_stride * (size_t)grid)) return 1;
+      a.cot_scratch = r->d_cot;
+    }
     const size_t wbytes = es * ((size_t)grid * (r->n_blk > 0 ? r->n_blk : 1) << r->n);
     if (grow(&r->d_wpart, &r->wpart_bytes, wbytes)) return 1;
     a.w_partials = r->d_wpart;
     if (r->n_blk > 0 && cudaMemsetAsync(r->d_wpart, 0, wbytes, s) != cudaSuccess) {
       set_error("engine T: cudaMemsetAsync failed"); return 1;
     }
-    cudaError_t ez = cudaMemsetAsync(r->d_tpart, 0, sizeof(double) * (size_t)grid * nt, s);
+    cudaError_t ez = cudaMemsetAsync(r->d_tpart, 0, sizeof(double) * (size_t)rows * nt, s);
     if (ez != cudaSuccess) { set_error("engine T: cudaMemsetAsync failed: %s", cudaGetErrorString(ez)); return 1; }
   }
   const int rc = r->dtype == QCP_F64 ? tl_launch<double>(r->LB, S, backward, a, grid, L.total, s)
@@ -545,9 +554,9 @@ int tile_run(TilePlan* r, int S, bool backward, void* ws, long long B, void* sta
   const int tb = (r->n_theta + 127) / 128;
   if (tb) {
     if (r->dtype == QCP_F64)
-      tl_reduce_theta_kernel<double><<<tb, 128, 0, s>>>(r->d_tpart, grid, r->n_theta, static_cast<double*>(grad_theta));
+      tl_reduce_theta_kernel<double><<<tb, 128, 0, s>>>(r->d_tpart, grid * tl_warps(true), r->n_theta, static_cast<double*>(grad_theta));
     else
-      tl_reduce_theta_kernel<float><<<tb, 128, 0, s>>>(r->d_tpart, grid, r->n_theta, static_cast<float*>(grad_theta));
+      tl_reduce_theta_kernel<float><<<tb, 128, 0, s>>>(r->d_tpart, grid * tl_warps(true), r->n_theta, static_cast<float*>(grad_theta));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("engine T: reduction launch failed: %s", cudaGetErrorString(e)); return 1; }
   }

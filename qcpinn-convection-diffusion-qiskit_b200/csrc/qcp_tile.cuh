@@ -73,7 +73,10 @@ struct TlArgs {
   void* state;                   // optional per-POINT psi storage [B][S][2^n]: the forward works in it
                                  // (and leaves the final psi there), the backward starts from it
                                  // instead of recomputing the forward
-  double* theta_partials;        // [grid][n_theta]
+  double* theta_partials;        // [grid * warps][n_theta]: one row per warp (single writer)
+  void* cot_scratch;             // per CTA: [warps][NE*S] table cotangents + [NE][kMaxOther][S]
+                                 // leave-one-out contributions of the cotangent pass (backward)
+  size_t cot_stride;             // elements of T per CTA
 };
 
 __host__ __device__ constexpr int tl_warps(bool backward) { return backward ? 12 : 16; }
@@ -91,7 +94,7 @@ __host__ __device__ inline TlLayout tl_layout(size_t es, int LB, int S, int n, i
   L.qj = o; o = rg::rg_align(o + es * (size_t)n * S);
   L.rj = o; o = rg::rg_align(o + es * (size_t)n * 2 * S);
   L.tab = o; o = rg::rg_align(o + es * (size_t)NE * S);
-  L.qacc = o; o = rg::rg_align(o + sizeof(double) * (size_t)n * S);
+  L.qacc = o; o = rg::rg_align(o + sizeof(double) * (size_t)n * S * NW);   // one row per warp
   // per-warp scratch of the cotangent pass (rho tile + LT components).  The sweeps move qubits
   // with shuffle SWAPs only: the shared-memory PERM of engine R measured slower here (one CTA per
   // SM, issue-bound), so the planner never emits it for this engine.
@@ -121,7 +124,7 @@ struct Ctx {
   __device__ __forceinline__ T* qj() const { return at<T>(a.lay.qj); }                          // [n*S]
   __device__ __forceinline__ Jet<T, S>* rj() const { return at<Jet<T, S>>(a.lay.rj); }          // [n][2]
   __device__ __forceinline__ Jet<T, S>* tab() const { return at<Jet<T, S>>(a.lay.tab); }        // [NA | 32 | NT]
-  __device__ __forceinline__ double* qacc() const { return at<double>(a.lay.qacc); }            // [n*S]
+  __device__ __forceinline__ double* qacc() const { return at<double>(a.lay.qacc); }            // [NW][n*S]
   // this warp's private cotangent-pass scratch
   __device__ __forceinline__ T* scr() const { return at<T>(a.lay.scr + (threadIdx.x >> 5) * a.lay.warp_bytes); }
   __device__ __forceinline__ Jet<T, S>* tabbar() const { return at<Jet<T, S>>(a.lay.tabbar); }
@@ -499,7 +502,9 @@ tl_forward_kernel(const __grid_constant__ TlArgs a) {
   const size_t M = (size_t)1 << n;
   __syncthreads();
   for (long long p = blockIdx.x; p < a.B; p += gridDim.x) {
-    for (int e = threadIdx.x; e < nS; e += blockDim.x) c.qacc()[e] = 0.0;
+    // measurement sums: one accumulator row per warp (its items arrive in program order), rows
+    // added in warp order afterwards -> bit-reproducible expectation values
+    for (int e = threadIdx.x; e < nS * NW; e += blockDim.x) c.qacc()[e] = 0.0;
     C2A<T>* slab = a.state ? static_cast<C2A<T>*>(a.state) + (size_t)p * S * M : cta_slab;
     forward_point<T, LB, S, DG>(c, a, slab, p);
     // ---- measure pass (canonical mapping over the final layout) --------------------------------
@@ -544,11 +549,15 @@ tl_forward_kernel(const __grid_constant__ TlArgs a) {
           for (int x = 1; x < LB; ++x) v = (fb - 5) == x ? sx[x] : v;
         }
         for (int m = 16; m > 0; m >>= 1) v += shx(v, m);
-        if (lane == 0) atomicAdd(c.qacc() + q * S + s, (double)v);
+        if (lane == 0) c.qacc()[(size_t)warp * nS + q * S + s] += (double)v;
       }
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < nS; e += blockDim.x) ws_out[(size_t)(nS + e) * a.B + p] = (T)c.qacc()[e];
+    for (int e = threadIdx.x; e < nS; e += blockDim.x) {
+      double tot = 0.0;
+      for (int w = 0; w < NW; ++w) tot += c.qacc()[(size_t)w * nS + e];
+      ws_out[(size_t)(nS + e) * a.B + p] = (T)tot;
+    }
     __syncthreads();
   }
 }
@@ -567,10 +576,16 @@ tl_backward_kernel(const __grid_constant__ TlArgs a) {
   C2A<T>* cta_slab = static_cast<C2A<T>*>(a.slab) + (size_t)blockIdx.x * a.slab_stride;
   const T* ws = static_cast<const T*>(a.ws);
   T* ws_out = static_cast<T*>(a.ws);
-  double* const gth = a.theta_partials + (size_t)blockIdx.x * (a.n_theta > 0 ? a.n_theta : 1);
+  // one dL/dtheta row per warp: every address has a single writing thread (lane 0 of that warp),
+  // whose RED.ADDs apply in program order; rows are summed in order by tl_reduce_theta_kernel
+  double* const gth = a.theta_partials +
+                      ((size_t)blockIdx.x * NW + warp) * (a.n_theta > 0 ? a.n_theta : 1);
   T* const wacc = static_cast<T*>(a.w_partials) + ((size_t)blockIdx.x * a.n_blk << n);
   const size_t M = (size_t)1 << n;
   C2A<T>* lam = cta_slab + (size_t)S * M;
+  // cotangent-pass scratch of this CTA (global: per-warp copies do not fit shared memory in float64)
+  T* const tbw = static_cast<T*>(a.cot_scratch) + (size_t)blockIdx.x * a.cot_stride;   // [NW][NE*S]
+  T* const contrib = tbw + (size_t)NW * NE * S;                                        // [NE][kMaxOther][S]
   __syncthreads();
 
   for (long long p = blockIdx.x; p < a.B; p += gridDim.x) {
@@ -589,7 +604,7 @@ tl_backward_kernel(const __grid_constant__ TlArgs a) {
       forward_point<T, LB, S, DG>(c, a, slab, p);
     }
     for (int e = threadIdx.x; e < nS; e += blockDim.x) c.qj()[e] = ws[(size_t)(nS + e) * a.B + p];
-    for (int e = threadIdx.x; e < NE * S; e += blockDim.x) reinterpret_cast<T*>(c.tabbar())[e] = T(0);
+    for (int e = threadIdx.x; e < NW * NE * S; e += blockDim.x) tbw[e] = T(0);
     for (int e = threadIdx.x; e < n * 2 * S; e += blockDim.x) reinterpret_cast<T*>(c.rbar())[e] = T(0);
     __syncthreads();
     // ---- lambda-init pass: lambda streams from the q cotangents ---------------------------------
@@ -669,8 +684,14 @@ tl_backward_kernel(const __grid_constant__ TlArgs a) {
     for (int k = a.n_sweeps - 1; k >= 0; --k) {
       const Sweep& sw = a.sweeps[k];
       const int ld_lane = sw.ld_lane[lane], st_lane = sw.st_lane[lane];
-      for (int it = warp; it < S * NT; it += NW) {
-        const int s = it / NT, t = it % NT;
+      // With diagonal blocks the W sums of a tile are accumulated from all S streams: the streams
+      // of one tile then run on the SAME warp one after the other (single writer per address, program
+      // order) instead of being dealt round-robin over the warps.
+      const int n_items = DG ? NT * S : S * NT;
+      for (int it0 = DG ? warp * S : warp; it0 < n_items; it0 += DG ? NW * S : NW)
+      for (int sub = 0; sub < (DG ? S : 1); ++sub) {
+        const int it = it0 + sub;
+        const int s = DG ? it % S : it / NT, t = DG ? it / S : it % NT;
         const int tb = tile_base(sw, t);
         C2A<T>* vp = slab + (size_t)s * M + tb;
         C2A<T>* vl = lam + (size_t)s * M + tb;
@@ -688,6 +709,9 @@ tl_backward_kernel(const __grid_constant__ TlArgs a) {
       T* rho = c.scr();                                     // [32][33] rho, then LT components [32][4]
       T* ltc = rho + 32 * 33;
       const Jet<T, S>* tab = c.tab();
+      // this warp's private copy of the table cotangents (every entry below has one writing lane per
+      // warp): plain read-modify-writes, copies summed in warp order after the pass
+      Jet<T, S>* tbar = reinterpret_cast<Jet<T, S>*>(tbw + (size_t)warp * NE * S);
       for (int it = warp; it < S * NT; it += NW) {
         const int s = it / NT, t = it % NT;
         T lx[NA], ly[NA];
@@ -726,10 +750,10 @@ tl_backward_kernel(const __grid_constant__ TlArgs a) {
         jmul_pull_acc(tb, ltb, Lj);
 #pragma unroll
         for (int k = 0; k < S; ++k) {
-          if (lb.c[k] != T(0)) atomicAdd(&c.tabbar()[NA + lane].c[k], lb.c[k]);
+          tbar[NA + lane].c[k] += lb.c[k];
           T v = tb.c[k];
           for (int m = 16; m > 0; m >>= 1) v += shx(v, m);
-          if (lane == 0 && v != T(0)) atomicAdd(&c.tabbar()[NA + 32 + t].c[k], v);
+          if (lane == 0) tbar[NA + 32 + t].c[k] += v;
         }
         __syncwarp();
         // local-entry sums over the lanes: this lane handles local index i = lane (NA <= 32)
@@ -741,11 +765,17 @@ tl_backward_kernel(const __grid_constant__ TlArgs a) {
             rs = fma(r, ltc[l * 4 + 1], rs);
             rp = fma(r, ltc[l * 4 + 2], rp);
           }
-          Jet<T, S>& dst = c.tabbar()[lane];
-          atomicAdd(&dst.c[0], r0);
-          if (S == 6 && s > 0) atomicAdd(&dst.c[s], rs);
-          if (S == 6 && s >= 4) atomicAdd(&dst.c[s - 2], rp);
+          Jet<T, S>& dst = tbar[lane];
+          dst.c[0] += r0;
+          if (S == 6 && s > 0) dst.c[s] += rs;
+          if (S == 6 && s >= 4) dst.c[s - 2] += rp;
         }
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < NE * S; e += blockDim.x) {
+        T tot = tbw[e];
+        for (int w = 1; w < NW; ++w) tot += tbw[(size_t)w * NE * S + e];
+        reinterpret_cast<T*>(c.tabbar())[e] = tot;
       }
       __syncthreads();
       // table entries -> one-qubit jets (leave-one-out products)
@@ -766,11 +796,34 @@ tl_backward_kernel(const __grid_constant__ TlArgs a) {
           Jet<T, S> fb;
           jzero(fb);
           jmul_pull_acc(fb, eb, other);
-          Jet<T, S>& dst = c.rbar()[jq * 2 + bit];
+          // contribution of this table entry to the jet cotangent of (qubit jq, bit): parked, then
+          // summed per destination in entry order (no atomics: reproducible)
+          T* slot = contrib + ((size_t)ent * kMaxOther + k) * S;
 #pragma unroll
-          for (int m = 0; m < S; ++m) atomicAdd(&dst.c[m], fb.c[m]);
+          for (int m = 0; m < S; ++m) slot[m] = fb.c[m];
+          (void)bit;
           pre = jmul(pre, c.rj()[jq * 2 + bit]);
         }
+      }
+      __syncthreads();
+      for (int d = threadIdx.x; d < n * 2; d += blockDim.x) {
+        const int jq = d >> 1, bit = d & 1;
+        // the table group that holds qubit jq, and jq's position k inside it (see table_group)
+        int e0, cnt, K, q0;
+        if (jq >= n - 5) { e0 = NA; cnt = 32; K = 5; q0 = n - 1; }
+        else if (jq >= n - TB) { e0 = 0; cnt = NA; K = LB; q0 = n - 6; }
+        else { e0 = NA + 32; cnt = NT; K = n - TB; q0 = n - TB - 1; }
+        const int k = q0 - jq;
+        (void)K;
+        Jet<T, S> acc;
+        jzero(acc);
+        for (int idx = 0; idx < cnt; ++idx) {
+          if (((idx >> k) & 1) != bit) continue;
+          const T* slot = contrib + ((size_t)(e0 + idx) * kMaxOther + k) * S;
+#pragma unroll
+          for (int m = 0; m < S; ++m) acc.c[m] += slot[m];
+        }
+        c.rbar()[d] = acc;
       }
       __syncthreads();
       for (int j = threadIdx.x; j < n; j += blockDim.x) {

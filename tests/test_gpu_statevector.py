@@ -287,3 +287,28 @@ def test_register_engine_gradients_are_bit_reproducible(case, dtype):
     for other in runs[1:]:
         for k, g in runs[0].items():
             assert torch.equal(g, other[k]), k
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f64", "f32"])
+@pytest.mark.parametrize("case", [("sim_circ_15", 12, 1, "angle", None), ("cross_mesh", 11, 1, "angle", None),
+                                  ("layered", 11, 1, "amplitude", 1)], ids=_ids)
+def test_tiled_engine_is_bit_reproducible(case, dtype):
+    """Engine T: measurement sums, table cotangents and dL/dtheta are accumulated per warp and
+    combined in a fixed order (diagonal-block sums: all streams of a tile on one warp), so repeated
+    passes over the same batch give bit-identical outputs and gradients."""
+    ansatz, n, layers, enc, seed = case
+    w, _, prog = make_case(ansatz, n, layers, enc, seed)
+    plan = F.Plan(prog, F.encoding_code(enc), dtype, 50, DEV)
+    assert plan.engine == "tiled"
+    X = points(300, seed=9).to(DEV, dtype)
+    runs = []
+    for _ in range(3):
+        dw = device_weights(w, dtype, DEV, requires_grad=True)
+        u, r = F.solver_residual(plan, X, dw["theta"], mlp_list(dw), (1, 1, 1, -0.01, -0.01))
+        ((u ** 2).sum() + (r ** 2).sum()).backward()
+        out = {k: v.grad.detach().clone() for k, v in dw.items()}
+        out["u"], out["r"] = u.detach().clone(), r.detach().clone()
+        runs.append(out)
+    for other in runs[1:]:
+        for k, g in runs[0].items():
+            assert torch.equal(g, other[k]), k
