@@ -71,6 +71,9 @@ namespace qcp {
 #ifndef QCP_VALUE_PPT
 #define QCP_VALUE_PPT 4
 #endif
+#ifndef QCP_VALUE_PPT_CONTRACT
+#define QCP_VALUE_PPT_CONTRACT 2      // the contraction adjoint carries more state per point
+#endif
 #ifndef QCP_ROLL_I
 #define QCP_ROLL_I 0
 #endif
@@ -706,6 +709,75 @@ __device__ __forceinline__ void angle_backward(const T* sC, const Jet<T, S> (&z)
   }
 }
 
+// Value mode (S = 1) with K points per thread: the d C contributions of the K points are added in
+// registers before they are staged (same push order as angle_backward), the C rows are fetched once.
+template <typename T, int NQ, int K>
+__device__ __forceinline__ void angle_backward_value(const T* sC, const Jet<T, 1> (&z)[K][NQ],
+                                                     const AngleFeat<T, NQ, 1> (&f)[K],
+                                                     const Jet<T, 1> (&qb)[K][NQ],
+                                                     Jet<T, 1> (&zb)[K][NQ], Stager<T>& st) {
+  using A = AngleShape<NQ>;
+  constexpr int S = 1;
+  Jet<T, S> yb[K][NQ], wb[K][NQ], Qb[K][A::FB];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      jzero(yb[k][j]);
+      jzero(wb[k][j]);
+    }
+#pragma unroll
+    for (int b = 0; b < A::FB; ++b) jzero(Qb[k][b]);
+  }
+  auto body = [&](int a, int t0, int t1) {
+    PA<T, NQ, S> pa[K];
+    Jet<T, S> pab[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      pa[k].set2(f[k], t0, t1);
+      jzero(pab[k]);
+    }
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      CRow<T, NQ> c;
+      c.load(sC, a, i);
+      T dc[A::FB];
+#pragma unroll
+      for (int b = 0; b < A::FB; ++b) dc[b] = T(0);
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        Jet<T, S> D;
+        jzero(D);
+        jmul_pull_acc(D, qb[k][i], pa[k].p);
+        const Jet<T, S> t = contract_row<T, NQ, S>(c, f[k].Q);
+        jmul_pull_acc(pab[k], qb[k][i], t);
+        dc[0] += D.c[0];
+#pragma unroll
+        for (int b = 1; b < A::FB; ++b) {
+          dc[b] = fma(D.c[0], f[k].Q[b].c[0], dc[b]);
+          jaxpy(Qb[k][b], c.at(b), D);
+        }
+      }
+      st.reserve(A::FB);
+#pragma unroll
+      for (int b = 0; b < A::FB; ++b) st.put(dc[b]);          // d C[i, a, b]
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) pa[k].pull(pab[k], yb[k], wb[k]);
+  };
+  st.flush();
+  for_each_a<T, NQ, S>(body, [&]() { st.flush(); });
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    prod_pull<T, S, A::NB>(Qb[k], f[k].y + A::NA, f[k].w + A::NA, yb[k] + A::NA, wb[k] + A::NA);
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      jfunc_pull_acc(zb[k][j], yb[k][j], z[k][j], -f[k].cs[j], f[k].sn[j], f[k].cs[j]);
+      jfunc_pull_acc(zb[k][j], wb[k][j], z[k][j], -f[k].sn[j], -f[k].cs[j], f[k].sn[j]);
+    }
+  }
+}
+
 template <typename T, int NQ, int S>
 __device__ __forceinline__ void amp_backward(const T* sC, const Jet<T, S> (&z)[NQ],
                                              const AmpFeat<T, NQ, S>& f,
@@ -1325,6 +1397,40 @@ contract_backward_kernel(const SolverArgs a) {
   Stager<T> st = make_stager<T>(acc_all, tile_all, nacc);
 
   T* wsg = static_cast<T*>(a.ws);
+  if constexpr (S == 1 && ENC == QCP_ENC_ANGLE && QCP_VALUE_PPT_CONTRACT > 1) {
+    constexpr int K = QCP_VALUE_PPT_CONTRACT;
+    const long long chunk = (long long)blockDim.x * K;
+    for (long long b0 = (long long)blockIdx.x * chunk; b0 < a.B; b0 += (long long)gridDim.x * chunk) {
+      long long pts[K];
+      bool ok[K];
+      Jet<T, 1> z[K][NQ], qb[K][NQ], zb[K][NQ];
+      AngleFeat<T, NQ, 1> f[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const long long p0 = b0 + (long long)k * blockDim.x + threadIdx.x;
+        ok[k] = p0 < a.B;
+        pts[k] = ok[k] ? p0 : a.B - 1;
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+          z[k][j].c[0] = wsg[(size_t)j * a.B + pts[k]];                               // slot 0
+          qb[k][j].c[0] = ok[k] ? wsg[(size_t)(NQ + j) * a.B + pts[k]] : T(0);        // slot 1
+          jzero(zb[k][j]);
+        }
+        angle_forward<T, NQ, 1>(z[k], f[k]);
+      }
+      st.begin();
+      angle_backward_value<T, NQ, K>(sC, z, f, qb, zb, st);
+      st.flush();
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if (ok[k]) {
+#pragma unroll
+          for (int j = 0; j < NQ; ++j) wsg[(size_t)j * a.B + pts[k]] = zb[k][j].c[0];
+        }
+    }
+    write_partials<T>(acc_all, nacc, static_cast<T*>(a.partials));
+    return;
+  }
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long Bpad = (a.B + 31) & ~31LL;
   // the loop bound is uniform over the block (warps past the end run with valid == false), so the
