@@ -138,9 +138,10 @@ int qcp_solver_forward(qcp_plan_t* plan, const qcp_mlp_t* weights, const void* X
                        void* save, void* stream);
 
 /* Elements (of the plan dtype) of the optional ``save`` workspace of a (batch, mode) call:
- * 2 * n_qubits * mode * batch (+ 2 * hidden * batch for float64 plans with n <= 4).  When ``save`` is given, the forward
+ * 2 * n_qubits * mode * batch (+ (2 * hidden + 2 * n_qubits) * batch for float64 plans with n <= 4).  When ``save`` is given, the forward
  * stores the Taylor jets of the pre-MLP outputs z and of the expectation values q in it
- * (component-major, coalesced), in that case also the tanh values of both hidden layers, and the
+ * (component-major, coalesced), in that case also the tanh values of both hidden layers and the
+ * sin / cos of the encoding angles, and the
  * backward runs as three lean kernels over them instead of recomputing the forward. */
 long long qcp_solver_workspace_elems(const qcp_plan_t* plan, long long batch, int mode);
 

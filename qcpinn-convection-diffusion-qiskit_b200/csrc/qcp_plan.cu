@@ -1158,8 +1158,9 @@ static int check_mode(int mode, const double* coeffs, const char* who) {
 long long qcp_solver_workspace_elems(const qcp_plan_t* p, long long B, int mode) {
   if (!p || B < 0 || (mode != QCP_MODE_VALUE && mode != QCP_MODE_RESIDUAL)) return -1;
   long long e = 2LL * p->n * mode * B;
-  // fused engine, float64: saved tanh values of both MLPs (SaveAct<T>, qcp_common.cuh)
-  if (!p->engine_l && p->dtype == QCP_F64) e += 2LL * p->H * B;
+  // fused engine, float64: saved tanh values of both MLPs and sin / cos of the pre-MLP outputs
+  // (SaveAct<T>, qcp_common.cuh)
+  if (!p->engine_l && p->dtype == QCP_F64) e += (2LL * p->H + 2LL * p->n) * B;
   if (p->reg && !p->no_state_save) e += reg_state_elems(p->reg, B, mode);   // engines R / T also save
   if (p->tile && !p->no_state_save) e += tile_state_elems(p->tile, B, mode);  // the final psi streams
   return e;

@@ -563,7 +563,10 @@ struct Stager {
 // reader keeps kActAhead values in flight so the HBM latency of act[k * B] hides behind the
 // adjoint steps of the previous hidden units.
 // ------------------------------------------------------------------------------------------
-constexpr int kActAhead = 4;
+#ifndef QCP_ACT_AHEAD
+#define QCP_ACT_AHEAD 4
+#endif
+constexpr int kActAhead = QCP_ACT_AHEAD;
 
 template <typename T>
 __device__ __forceinline__ void tanh_derivs_saved(T f0, T& f1, T& f2, T& f3) {
@@ -893,12 +896,19 @@ __device__ __forceinline__ void feature_backward(const T* sC, const Jet<T, S> (&
 // are taken first) is written by the last pass from the sum of the partial value cotangents.
 template <typename T, int NQ, int MODE = -1>
 __device__ __forceinline__ void angle_backward_ws(const T* sC, T* ws, long long B, long long p,
-                                                  bool valid, Stager<T>& st) {
+                                                  bool valid, Stager<T>& st, const T* trig = nullptr) {
   constexpr int S = 6;
   T* zrow = ws + p;                                   // slot 0, component-major
   const T* qrow = ws + (size_t)NQ * S * B + p;        // slot 1
   T sn[NQ], cs[NQ], zb0[NQ];
-  {
+  if (SaveAct<T>::value && trig) {
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      sn[j] = trig[(size_t)j * B];
+      cs[j] = trig[(size_t)(NQ + j) * B];
+      zb0[j] = T(0);
+    }
+  } else {
     T z0[NQ];
 #pragma unroll
     for (int j = 0; j < NQ; ++j) { z0[j] = zrow[(size_t)(j * S) * B]; zb0[j] = T(0); }
@@ -947,12 +957,23 @@ __device__ __forceinline__ void angle_backward_ws(const T* sC, T* ws, long long 
   st.base = base0 + nacc_contract(NQ, QCP_ENC_ANGLE);
 }
 
+// `trig` (optional, angle encoding): sin z_j / cos z_j are stored at trig[j * B] / trig[(NQ + j) * B]
+// (pointer already offset by the point), so the contraction adjoint need not evaluate four
+// double-precision sincos per point again (workspace slot 3, float64 plans: SaveAct<T>)
 template <typename T, int NQ, int ENC, int S>
 __device__ __forceinline__ void feature_forward(const T* sC, const Jet<T, S> (&z)[NQ],
-                                                Jet<T, S> (&q)[NQ]) {
+                                                Jet<T, S> (&q)[NQ], T* trig = nullptr,
+                                                long long B = 0) {
   if constexpr (ENC == QCP_ENC_ANGLE) {
     AngleFeat<T, NQ, S> f;
     angle_forward<T, NQ, S>(z, f);
+    if (trig) {
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) {
+        trig[(size_t)j * B] = f.sn[j];
+        trig[(size_t)(NQ + j) * B] = f.cs[j];
+      }
+    }
     angle_contract<T, NQ, S>(sC, f, q);
   } else {
     AmpFeat<T, NQ, S> f;
@@ -1168,6 +1189,12 @@ __device__ __forceinline__ const T* ws_act(const T* ws, long long B) {
   return ws + (size_t)2 * NQ * S * B;
 }
 
+// slot 3: saved sin / cos of the pre-MLP outputs, trig[2 NQ][B], behind the 2 H tanh rows
+template <typename T, int NQ, int S>
+__device__ __forceinline__ T* ws_trig(T* ws, long long B, int H) {
+  return ws + (size_t)(2 * NQ * S + 2 * H) * B;
+}
+
 // cotangent seed of the outputs: (grad_u, grad_r) -> jet cotangent of u
 template <typename T, int S, typename TIO = T>
 __device__ __forceinline__ Jet<T, S> seed_cotangent(const SolverArgs& a, long long p, bool valid) {
@@ -1244,7 +1271,8 @@ solver_forward_kernel(const SolverArgs a) {
     T* act = (SaveAct<T>::value && wsg) ? ws_act<T, NQ, S>(wsg, a.B) + p : nullptr;
     pre_forward<T, NQ, S>(sw, H, X, z, act, a.B);
     if (wsg) ws_store<T, NQ, S>(wsg, a.B, 0, p, z);
-    feature_forward<T, NQ, ENC, S>(sw.C, z, q);
+    feature_forward<T, NQ, ENC, S>(sw.C, z, q,
+                                   act ? ws_trig<T, NQ, S>(wsg, a.B, H) + p : nullptr, a.B);
     if (wsg) ws_store<T, NQ, S>(wsg, a.B, 1, p, q);
     post_forward<T, NQ, S>(sw, H, q, u, act ? act + (size_t)H * a.B : nullptr, a.B);
     ug[p] = (TIO)u.c[0];
@@ -1416,7 +1444,18 @@ contract_backward_kernel(const SolverArgs a) {
           qb[k][j].c[0] = ok[k] ? wsg[(size_t)(NQ + j) * a.B + pts[k]] : T(0);        // slot 1
           jzero(zb[k][j]);
         }
-        angle_forward<T, NQ, 1>(z[k], f[k]);
+        if constexpr (SaveAct<T>::value) {
+          const T* trig = ws_trig<T, NQ, 1>(wsg, a.B, a.H) + pts[k];
+          T sn[NQ], cs[NQ];
+#pragma unroll
+          for (int j = 0; j < NQ; ++j) {
+            sn[j] = trig[(size_t)j * a.B];
+            cs[j] = trig[(size_t)(NQ + j) * a.B];
+          }
+          angle_features<T, NQ, 1>(z[k], sn, cs, f[k]);
+        } else {
+          angle_forward<T, NQ, 1>(z[k], f[k]);
+        }
       }
       st.begin();
       angle_backward_value<T, NQ, K>(sC, z, f, qb, zb, st);
@@ -1442,7 +1481,8 @@ contract_backward_kernel(const SolverArgs a) {
     if (p0 + stride < a.B) ws_prefetch<T>(wsg + p0 + stride, a.B, 2 * NQ * S);   // z and qb rows
     st.begin();
     if constexpr (ENC == QCP_ENC_ANGLE && S == 6 && Tune<T, S>::kTwoPass && QCP_STREAM_PASSES) {
-      angle_backward_ws<T, NQ, MODE>(sC, wsg, a.B, p, valid, st);
+      angle_backward_ws<T, NQ, MODE>(sC, wsg, a.B, p, valid, st,
+                                     SaveAct<T>::value ? ws_trig<T, NQ, S>(wsg, a.B, a.H) + p : nullptr);
       st.flush();
     } else {
       Jet<T, S> z[NQ], qb[NQ], zb[NQ];
