@@ -74,6 +74,9 @@ namespace qcp {
 #ifndef QCP_VALUE_PPT_CONTRACT
 #define QCP_VALUE_PPT_CONTRACT 2      // the contraction adjoint carries more state per point
 #endif
+#ifndef QCP_PUT_AUTO
+#define QCP_PUT_AUTO 1
+#endif
 #ifndef QCP_ROLL_I
 #define QCP_ROLL_I 0
 #endif
@@ -556,6 +559,13 @@ struct Stager {
   __device__ __forceinline__ void reserve(int rows) {
     if (cnt + rows > kStageRows) flush();
   }
+  // put() that closes the tile exactly when it is full (in fully unrolled code the row counter is a
+  // compile-time constant, so the test folds away): tiles of 32 rows instead of 27 in the
+  // contraction adjoint, i.e. 11 instead of 12 row-sum rounds per pass
+  __device__ __forceinline__ void put_auto(T v) {
+    if (cnt == kStageRows) flush();
+    put(v);
+  }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -681,12 +691,24 @@ __device__ __forceinline__ void angle_backward(const T* sC, const Jet<T, S> (&z)
       jmul_pull_acc(D, qbi, pa.p);
       const Jet<T, S> t = contract_row<T, NQ, S>(c, f.Q);
       jmul_pull_acc(pab, qbi, t);
-      st.reserve(A::FB);
-      st.put(D.c[0]);                                      // d C[i, a, 0]  (Q[0] == 1)
+      if constexpr (QCP_PUT_AUTO != 0 && sizeof(T) == 4) {
+        // float32 (rolled A-half loop, runtime row counter anyway): full 32-row tiles, -1.6 %.
+        // In float64 the same change made the unrolled kernel 70 % slower (the row counter stops
+        // being a compile-time constant across the two passes), so it keeps reserve().
+        st.put_auto(D.c[0]);                               // d C[i, a, 0]  (Q[0] == 1)
 #pragma unroll
-      for (int b = 1; b < A::FB; ++b) {
-        st.put(jdot(D, f.Q[b]));                           // d C[i, a, b]
-        jaxpy(Qb[b], c.at(b), D);
+        for (int b = 1; b < A::FB; ++b) {
+          st.put_auto(jdot(D, f.Q[b]));                    // d C[i, a, b]
+          jaxpy(Qb[b], c.at(b), D);
+        }
+      } else {
+        st.reserve(A::FB);
+        st.put(D.c[0]);                                    // d C[i, a, 0]  (Q[0] == 1)
+#pragma unroll
+        for (int b = 1; b < A::FB; ++b) {
+          st.put(jdot(D, f.Q[b]));                         // d C[i, a, b]
+          jaxpy(Qb[b], c.at(b), D);
+        }
       }
     };
     if constexpr (RollI<T>::value && S != 1) {
