@@ -639,3 +639,32 @@ def test_opt_in_autograd_mode_is_differentiable_to_any_order(tmp_path):
         qb.DVQuantumLayer(dict(ARGS, diff_mode="autograd"))(torch.zeros(2, 4))
     with pytest.raises(ValueError, match="diff_mode"):
         qb.DVQuantumLayer(dict(ARGS, diff_mode="nope"))
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("batch", [0, 1, 31, 127, 128, 129, 255, 511, 513, 1000, 4097])
+def test_value_mode_ragged_batches_with_several_points_per_thread(batch, dtype):
+    """Value mode (IC / BC points) runs the post / pre adjoints with four and the contraction
+    adjoint with two points per thread: every chunk boundary (128 x K points per block iteration),
+    the saved tanh / sin / cos rows and grad_X against the oracle, for sizes around those boundaries."""
+    w, oracle, prog = make_case("cascade", 4, 1, "angle", 1)
+    plan = F.Plan(prog, 0, dtype, 50, DEV)
+    dw = device_weights(w, dtype, DEV, requires_grad=True)
+    X = points(max(batch, 1), seed=batch + 1)[:batch]
+    Xd = X.to(DEV, dtype).requires_grad_(True)
+    u = F.solver_value(plan, Xd, dw["theta"], mlp_list(dw))
+    assert u.shape == (batch, 1)
+    g = torch.Generator().manual_seed(batch)
+    cot = torch.randn(batch, 1, generator=g, dtype=torch.float64)
+    (u * cot.to(DEV, dtype)).sum().backward()
+    if batch == 0:
+        assert float(dw["w3"].grad.abs().max()) == 0.0
+        return
+    Xo = X.clone().requires_grad_(True)
+    uo = oracle.forward(Xo)
+    (uo * cot).sum().backward()
+    tol = TOL[dtype]
+    assert rel_err(u, uo) < tol
+    assert rel_err(Xd.grad, Xo.grad) < 20 * tol
+    for k in osolver.WEIGHT_NAMES:
+        assert rel_err(dw[k].grad, oracle.w[k].grad) < 20 * tol, k
