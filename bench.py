@@ -171,7 +171,7 @@ def measure_other_configs(torch, qb, device, peaks, hbm_gbs):
             torch.manual_seed(0)
             logger = qb.Logging(os.path.join(tempfile.gettempdir(), "qcpinn_bench_cfg"))
             model = qb.DVPDESolver(args, logger, device=device)
-            step = TrainStep(model, pts, None, use_graph=None if n <= 4 else False)
+            step = TrainStep(model, pts, None, use_graph=None if n <= 4 else False, host_sync=False)
             torch.manual_seed(1234)
             for _ in range(5 if n <= 4 else 2):     # n <= 4: three eager steps, then graph replays
                 step()
@@ -272,8 +272,11 @@ def run_ours(ns):
         torch.manual_seed(0)                       # identical weights on every rank
         logger = qb.Logging(os.path.join(tempfile.gettempdir(), f"qcpinn_bench_r{rank}"))
         model = qb.DVPDESolver(model_args(dtype_name), logger, device=device)
+        # like trainer.diffusion_train.train(): the step never waits for the GPU (the plateau
+        # scheduler and the loss record run inside the captured step); the e2e leg below switches
+        # the per-step loss read-back on
         step = TrainStep(model, pts_rank, _make_averager(model),
-                         use_graph=False if ns.no_graph else None)
+                         use_graph=False if ns.no_graph else None, host_sync=False)
         return model, step
 
     def measure(dtype_name, with_e2e):
@@ -366,6 +369,7 @@ def run_ours(ns):
                 step.prefetch(ring[state["i"] % len(ring)])
                 return step(host)
 
+            step.host_sync = True                       # one loss read-back (D2H) per step
             while not step.steady(host_batches=True):   # capture of the host-fed step: start-up
                 e2e_step()
             ms_e, _ = timed_steps(e2e_step, ns.steps, min(ns.warmup, 3), torch, dist, world, device)

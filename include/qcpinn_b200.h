@@ -195,6 +195,26 @@ int qcp_mse_seed(const float* pred, const float* target, long long n, double wei
 int qcp_clip_grads(float* flat, int n_grad, int n_extra, double pre_scale, double max_norm,
                    void* stream);
 
+/* Gradient vector of the adjoint kernels (``dtype`` = the plan's, n_grad values in ``parameters()``
+ * order) -> the optimizer's float32 flat buffer, with the objective behind it: flat[n_grad] =
+ * w_r terms[0] + w_bc terms[1] + w_ic terms[2] (reference trainer/diffusion_train.py:48), flat[n_grad
+ * + 1 .. + 3] = terms (DEVICE doubles written by qcp_mse_seed).  One launch instead of five. */
+int qcp_pack_step(const void* grads, int dtype, int n_grad, const double* terms, double w_r,
+                  double w_bc, double w_ic, float* flat, void* stream);
+
+/* ``scheduler.step(loss)`` of the reference loop (trainer/diffusion_train.py:88-89;
+ * torch.optim.lr_scheduler.ReduceLROnPlateau, nn/DVPDESolver.py:62) without a host round trip: one
+ * thread repeats the scheduler's double arithmetic on DEVICE state = double[QCP_PLATEAU_STATE]
+ * {best, num_bad_epochs, cooldown_counter, last_epoch, recorded, reductions}, multiplies the
+ * device-resident float32 learning rate *lr by ``factor`` when patience runs out, and (history !=
+ * NULL) appends *metric to history[recorded++] while recorded < history_cap (the loss history the
+ * host drains later).  mode_max / threshold_abs select the scheduler's mode / threshold_mode. */
+#define QCP_PLATEAU_STATE 6
+int qcp_plateau_step(const float* metric, double* state, float* lr, float* history,
+                     long long history_cap, int mode_max, int threshold_abs, double threshold,
+                     double factor, long long patience, long long cooldown, double min_lr,
+                     double eps, void* stream);
+
 /* Host-only self check of the statevector-engine planners (no CUDA device needed; used by the CPU
  * tests): plans the gate list like qcp_plan_create() would for (n_qubits >= 5, dtype), runs the
  * logical circuit and the planned physical program on the CPU over a random statevector and

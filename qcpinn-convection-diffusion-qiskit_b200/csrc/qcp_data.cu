@@ -123,6 +123,57 @@ __global__ void clip_grads_kernel(float* __restrict__ flat, int n_grad, int n_ex
   for (int i = threadIdx.x; i < n_extra; i += blockDim.x) flat[n_grad + i] *= pre_scale;
 }
 
+// gradient vector of the adjoint kernels (plan dtype) -> float32 flat buffer of the optimizer, with the
+// weighted objective and its three terms behind it: flat = [grads | loss | loss_r | loss_bc | loss_ic]
+template <typename T>
+__global__ void pack_step_kernel(const T* __restrict__ grads, int n_grad, const double* __restrict__ terms,
+                                 double w_r, double w_bc, double w_ic, float* __restrict__ flat) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_grad; i += gridDim.x * blockDim.x)
+    flat[i] = (float)grads[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const double t0 = terms[0], t1 = terms[1], t2 = terms[2];
+    flat[n_grad] = (float)(t0 * w_r + t1 * w_bc + t2 * w_ic);
+    flat[n_grad + 1] = (float)t0;
+    flat[n_grad + 2] = (float)t1;
+    flat[n_grad + 3] = (float)t2;
+  }
+}
+
+// torch.optim.lr_scheduler.ReduceLROnPlateau.step(metric) on the device, in the same double
+// arithmetic as the Python original; state = {best, num_bad_epochs, cooldown_counter, last_epoch,
+// recorded, reductions}
+__global__ void plateau_step_kernel(const float* __restrict__ metric, double* __restrict__ state,
+                                    float* __restrict__ lr, float* __restrict__ history,
+                                    long long history_cap, int mode_max, int threshold_abs,
+                                    double threshold, double factor, double patience, double cooldown,
+                                    double min_lr, double eps) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const double cur = (double)metric[0];
+  double best = state[0], bad = state[1], cool = state[2];
+  state[3] += 1.0;
+  bool better;
+  if (!mode_max && !threshold_abs) better = cur < best * (1.0 - threshold);
+  else if (!mode_max) better = cur < best - threshold;
+  else if (!threshold_abs) better = cur > best * (threshold + 1.0);
+  else better = cur > best + threshold;
+  if (better) { best = cur; bad = 0.0; } else { bad += 1.0; }
+  if (cool > 0.0) { cool -= 1.0; bad = 0.0; }
+  if (bad > patience) {
+    const double old_lr = (double)lr[0];
+    const double scaled = old_lr * factor;
+    const double new_lr = scaled > min_lr ? scaled : min_lr;       // Python max(a, b)
+    if (old_lr - new_lr > eps) { lr[0] = (float)new_lr; state[5] += 1.0; }
+    cool = cooldown;
+    bad = 0.0;
+  }
+  state[0] = best; state[1] = bad; state[2] = cool;
+  if (history) {
+    const long long k = (long long)state[4];
+    if (k < history_cap) history[k] = metric[0];
+    state[4] = (double)(k + 1);
+  }
+}
+
 }  // namespace qcp
 
 extern "C" int qcp_mse_seed(const float* pred, const float* target, long long n, double weight,
@@ -147,5 +198,42 @@ extern "C" int qcp_clip_grads(float* flat, int n_grad, int n_extra, double pre_s
                                                                        (float)max_norm);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("qcp_clip_grads: launch failed: %s", cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+
+extern "C" int qcp_pack_step(const void* grads, int dtype, int n_grad, const double* terms, double w_r,
+                             double w_bc, double w_ic, float* flat, void* stream) {
+  using namespace qcp;
+  if ((!grads && n_grad > 0) || !terms || !flat || n_grad < 0 || (dtype != QCP_F32 && dtype != QCP_F64)) {
+    set_error("qcp_pack_step: bad argument");
+    return 1;
+  }
+  const int blocks = n_grad > 4096 ? 8 : 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == QCP_F64)
+    pack_step_kernel<double><<<blocks, 1024, 0, st>>>(static_cast<const double*>(grads), n_grad, terms, w_r,
+                                                      w_bc, w_ic, flat);
+  else
+    pack_step_kernel<float><<<blocks, 1024, 0, st>>>(static_cast<const float*>(grads), n_grad, terms, w_r,
+                                                     w_bc, w_ic, flat);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("qcp_pack_step: launch failed: %s", cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+
+extern "C" int qcp_plateau_step(const float* metric, double* state, float* lr, float* history,
+                                long long history_cap, int mode_max, int threshold_abs, double threshold,
+                                double factor, long long patience, long long cooldown, double min_lr,
+                                double eps, void* stream) {
+  using namespace qcp;
+  if (!metric || !state || !lr || (history && history_cap <= 0)) {
+    set_error("qcp_plateau_step: bad argument");
+    return 1;
+  }
+  plateau_step_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      metric, state, lr, history, history_cap, mode_max, threshold_abs, threshold, factor, (double)patience,
+      (double)cooldown, min_lr, eps);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("qcp_plateau_step: launch failed: %s", cudaGetErrorString(e)); return 1; }
   return 0;
 }

@@ -1277,6 +1277,10 @@ static int backward_add_impl(qcp_plan_t* p, const qcp_mlp_t* w, const void* X, c
     if (gr.post > want_blocks) gr.post = (int)want_blocks;
     if (gr.contract > want_blocks) gr.contract = (int)want_blocks;
     if (gr.pre > want_blocks) gr.pre = (int)want_blocks;
+    // the pre-MLP adjoint is persistent and fills every SM (registers and shared memory both): one
+    // CTA less leaves a slot where the single-CTA theta_grad of the auxiliary stream can run next
+    // to it instead of waiting for its tail
+    else if (p->overlap_theta && gr.pre > p->num_sms) gr.pre -= 1;
     const size_t e0 = (size_t)gr.post * n0, e1 = (size_t)gr.contract * n1, e2 = (size_t)gr.pre * n2;
     if (check_partials_room(p, e0 + e1 + e2, "qcp_solver_backward_add")) return 1;
     void* p0 = base; void* p1 = base + e0 * es; void* p2 = base + (e0 + e1) * es;

@@ -22,16 +22,30 @@ class Sampler:
         self.name = name
         self.device = device
 
-    def sample(self, N):
-        pts = torch.rand(N, self.dim, device=self.device)
-        fused = self._fused(pts)
+    def draw(self, N):
+        """The uniform random numbers of one ``sample(N)`` call (to be passed back as ``rnd``)."""
+        return torch.rand(N, self.dim, device=self.device)
+
+    def sample(self, N, out=None, rnd=None):
+        """``out`` = (points, targets) of an earlier call to overwrite in place (static buffers of a
+        captured train step), ``rnd`` = numbers drawn earlier by :meth:`draw`; the reference
+        signature is ``sample(N)``."""
+        pts = self.draw(N) if rnd is None else rnd
+        if pts.shape != (N, self.dim):
+            raise ValueError(f"Sampler.sample: rnd has shape {tuple(pts.shape)}, expected {(N, self.dim)}")
+        fused = self._fused(pts, out)
         if fused is not None:
             return fused
         lo, hi = self.coords[0:1, :], self.coords[1:2, :]
         pts = lo + (hi - lo) * pts
-        return pts, self.func(pts.to(self.device))
+        vals = self.func(pts.to(self.device))
+        if out is not None:
+            out[0].copy_(pts)
+            out[1].copy_(vals)
+            return out[0], out[1]
+        return pts, vals
 
-    def _fused(self, rnd):
+    def _fused(self, rnd, out=None):
         """CUDA fast path for the two analytic targets of this module: one kernel maps the random
         numbers into the box and evaluates ``u`` / ``r`` (instead of ~15 / ~30 torch launches)."""
         kind = _FUSED_KIND.get(self.func)
@@ -45,8 +59,15 @@ class Sampler:
             box = self.coords.detach().to("cpu", torch.float32).reshape(-1).tolist()
             self._lo_hi = (ctypes.c_float * 6)(*box)
         lib = _lib.require_cuda()
-        X = torch.empty_like(rnd)
-        y = torch.empty((rnd.shape[0], 1), dtype=torch.float32, device=rnd.device)
+        if out is not None:
+            X, y = out
+            if X.shape != rnd.shape or y.numel() != rnd.shape[0] or X.dtype != torch.float32 \
+                    or y.dtype != torch.float32 or not (X.is_contiguous() and y.is_contiguous()) \
+                    or X.device != rnd.device or y.device != rnd.device:
+                raise ValueError("Sampler.sample(out=...): buffers do not match this draw")
+        else:
+            X = torch.empty_like(rnd)
+            y = torch.empty((rnd.shape[0], 1), dtype=torch.float32, device=rnd.device)
         with torch.cuda.device(rnd.device):
             stream = ctypes.c_void_p(torch.cuda.current_stream(rnd.device).cuda_stream)
             rc = lib.qcp_sample_targets(

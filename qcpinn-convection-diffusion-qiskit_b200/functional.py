@@ -310,11 +310,12 @@ def _flat_grad_views(plan: Plan, mlp, theta):
     return flat, views
 
 
-def solver_backward_many(plan: Plan, items, mlp, theta):
+def solver_backward_many(plan: Plan, items, mlp, theta, after_adjoints=None):
     """Adjoint kernels of several model calls, ONE partial reduction and ONE theta-gradient kernel.
     ``items`` = [(X, grad_u, grad_r, mode, coeffs, save, need_gx[, stream]), ...]; an item's adjoint
     kernels run on its ``stream`` (a torch stream already ordered after the producers of its
-    inputs) and the reduction waits for it.  Returns (views, [gx])."""
+    inputs) and the reduction waits for it.  ``after_adjoints()`` runs between the joined adjoint
+    launches and the reduction.  Returns (views, [gx])."""
     lib = plan.lib
     flat, views = _flat_grad_views(plan, mlp, theta)
     m = plan._mlp(mlp)
@@ -344,6 +345,8 @@ def solver_backward_many(plan: Plan, items, mlp, theta):
                 _count(3 if save is not None else 1)
         for side in joins:
             main.wait_stream(side)
+        if after_adjoints is not None:
+            after_adjoints()
         rc = lib.qcp_solver_backward_finish(
             plan._handle, ctypes.c_void_p(theta.data_ptr()), ctypes.byref(g),
             ctypes.c_void_p(views[8].data_ptr()), stream)
@@ -366,6 +369,43 @@ def mse_seed(plan: Plan, pred, target, weight, grad_out, loss_slot):
             ctypes.c_void_p(grad_out.data_ptr()), ctypes.c_void_p(loss_slot.data_ptr()),
             plan._stream())
     _lib.check(rc, "qcp_mse_seed")
+    _count(1)
+
+
+def pack_step(plan: Plan, grads, terms, weights, flat, n_grad):
+    """flat[:n_grad] = float32(grads); flat[n_grad] = weights . terms; flat[n_grad+1 : n_grad+4] = terms
+    (``grads`` in the plan dtype, ``terms`` three device doubles).  One launch."""
+    if grads.numel() != n_grad or not grads.is_contiguous() or grads.dtype != plan.dtype:
+        raise ValueError("pack_step: gradient vector does not match the flat buffer")
+    w_r, w_bc, w_ic = (float(w) for w in weights)
+    with torch.cuda.device(plan.device):
+        rc = plan.lib.qcp_pack_step(
+            ctypes.c_void_p(grads.data_ptr()), _DTYPE_CODE[plan.dtype],
+            int(n_grad), ctypes.c_void_p(terms.data_ptr()), w_r, w_bc, w_ic,
+            ctypes.c_void_p(flat.data_ptr()), plan._stream())
+    _lib.check(rc, "qcp_pack_step")
+    _count(1)
+
+
+PLATEAU_STATE = 6     # best, num_bad_epochs, cooldown_counter, last_epoch, recorded, reductions
+
+
+def plateau_step(plan: Plan, metric, state, lr, history, cfg):
+    """Device-side ``ReduceLROnPlateau.step(metric)``; ``cfg`` = dict(mode_max, threshold_abs,
+    threshold, factor, patience, cooldown, min_lr, eps); ``history`` float32 ring or None."""
+    if state.dtype != torch.float64 or state.numel() != PLATEAU_STATE or lr.dtype != torch.float32 \
+            or metric.dtype != torch.float32:
+        raise ValueError("plateau_step: state float64[6], lr / metric float32 expected")
+    with torch.cuda.device(plan.device):
+        rc = plan.lib.qcp_plateau_step(
+            ctypes.c_void_p(metric.data_ptr()), ctypes.c_void_p(state.data_ptr()),
+            ctypes.c_void_p(lr.data_ptr()),
+            ctypes.c_void_p(history.data_ptr() if history is not None else 0),
+            int(history.numel()) if history is not None else 0,
+            int(cfg["mode_max"]), int(cfg["threshold_abs"]), float(cfg["threshold"]),
+            float(cfg["factor"]), int(cfg["patience"]), int(cfg["cooldown"]), float(cfg["min_lr"]),
+            float(cfg["eps"]), plan._stream())
+    _lib.check(rc, "qcp_plateau_step")
     _count(1)
 
 

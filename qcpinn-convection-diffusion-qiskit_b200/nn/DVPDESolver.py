@@ -31,8 +31,25 @@ class _RankConsistentPlateau(torch.optim.lr_scheduler.ReduceLROnPlateau):
 
     _qcp_group = None
     _qcp_enabled = False
+    # callables that bring this object up to date with a device-resident twin (the CUDA-graph
+    # train step advances best / num_bad_epochs / cooldown_counter / last_epoch on the device,
+    # ``trainer.diffusion_train.DevicePlateau``); run before anything reads or changes the state
+    _qcp_flushers = ()
+
+    def _qcp_flush(self):
+        for f in tuple(self._qcp_flushers):
+            f()
+
+    def state_dict(self):
+        self._qcp_flush()
+        return {k: v for k, v in super().state_dict().items() if not k.startswith("_qcp_")}
+
+    def load_state_dict(self, state_dict):
+        self._qcp_flush()
+        return super().load_state_dict(state_dict)
 
     def step(self, metrics, *a, **kw):
+        self._qcp_flush()
         if self._qcp_enabled and torch.is_tensor(metrics):
             import torch.distributed as dist
 
@@ -54,6 +71,7 @@ class DVPDESolver(nn.Module):
         self.epochs = self.args["epochs"]
         self.optimizer = None
         self.scheduler = None
+        self._lazy_flushers = []      # see loss_history
         self.loss_history = []
         self.encoding = self.args.get("encoding", "angle")
         self.draw_quantum_circuit_flag = True
@@ -104,6 +122,21 @@ class DVPDESolver(nn.Module):
         self.log_path = self.logger.get_output_dir()
         self._initialize_weights()
         self._dp = None
+
+    # ``loss_history`` is the reference's plain list attribute.  The CUDA-graph train step records
+    # the per-step loss on the device and drains it in batches (no host round trip per step), so
+    # every read first runs the registered flushers.
+    @property
+    def loss_history(self):
+        for f in tuple(self.__dict__.get("_lazy_flushers", ())):
+            f()
+        return self.__dict__["_loss_history"]
+
+    @loss_history.setter
+    def loss_history(self, value):
+        for f in tuple(self.__dict__.get("_lazy_flushers", ())):
+            f()
+        self.__dict__["_loss_history"] = value
 
     # construction hooks (the single-file trainer's HybridQPINN overrides them)
     def _build_quantum_layer(self, args):
@@ -280,13 +313,15 @@ class DVPDESolver(nn.Module):
         tt, _ = plan.typed_weights(self.quantum_layer.params, self._mlp_tensors(), key)
         plan.prepare(tt, key)
 
-    def train_step_grads(self, batch, coeffs, weights=(2.0, 4.0, 2.0)):
+    def train_step_grads(self, batch, coeffs, weights=(2.0, 4.0, 2.0), after_adjoints=None):
         """The reference objective ``w_r MSE_r + w_bc MSE_bc + w_ic MSE_ic`` (reference
         trainer/diffusion_train.py:30-49) and ALL its parameter gradients without an autograd
         graph: forward kernels -> MSE seeds -> adjoint kernels -> one cast into the flat gradient
-        buffer.  ``batch`` = (X_ics, u_ics, X_bcs, u_bcs, X_res, r_res), float32 on the model's
+        buffer (``qcp_pack_step``).  ``batch`` = (X_ics, u_ics, X_bcs, u_bcs, X_res, r_res), float32 on the model's
         device.  Returns the flat buffer and the number of gradient elements; the buffer's last
-        four slots hold (loss, loss_r, loss_bc, loss_ic)."""
+        four slots hold (loss, loss_r, loss_bc, loss_ic).  ``after_adjoints()`` is called once every
+        kernel that reads the batch has been issued and joined on the current stream (a trainer
+        refills its static batch there, next to the reductions)."""
         X_ics, u_ics, X_bcs, u_bcs, X_res, r_res = batch
         dev = self._device_of(X_res)
         plan = self._plan(dev)
@@ -319,15 +354,11 @@ class DVPDESolver(nn.Module):
         F.mse_seed(plan, r_r, t_r, w_r, gr, terms[0:1])
         views, _ = F.solver_backward_many(
             plan, [(X_val, gu_v, None, F.MODE_VALUE, None, ws_v, False, side),
-                   (X_r, None, gr, F.MODE_RESIDUAL, coeffs, ws_r, False, None)], mt, tt)
+                   (X_r, None, gr, F.MODE_RESIDUAL, coeffs, ws_r, False, None)], mt, tt,
+            after_adjoints=after_adjoints)
         flat, numel = self.flat_grad_buffer()
-        flat[:numel].copy_(views[0]._base)                                   # one cast kernel
-        wvec = getattr(self, "_loss_weights", None)
-        if wvec is None or wvec.device != dev:
-            wvec = torch.tensor([w_r, w_bc, w_ic], dtype=torch.float64, device=dev)
-            self._loss_weights = wvec
-        flat[numel + 1:numel + 4].copy_(terms)
-        flat[numel:numel + 1].copy_((terms * wvec).sum().reshape(1))
+        # cast into the optimizer's float32 buffer + weighted objective and its terms: one launch
+        F.pack_step(plan, views[0]._base, terms, (w_r, w_bc, w_ic), flat, numel)
         return flat, numel
 
     def _value_stream(self, dev):
