@@ -292,8 +292,12 @@ def run_ours(ns):
         ms, wall_ms = timed_steps(step, ns.steps, 0, torch, dist, world, device)
         clocks = clk.stop()
         launches = F.launch_counter - launches0
+        step.flush()               # drains the device-side loss ring; raises if a rank missed an exchange
         res = {"ms": ms, "wall_ms": wall_ms, "clocks": clocks, "launches": launches,
                "value": pts_total * ns.steps / (ms * 1e-3)}
+        if world > 1:
+            res["exchange"] = ("qcp_peer_allreduce_clip (one kernel per rank over NVLink peer memory)"
+                               if step._peer else "NCCL all-reduce + qcp_clip_grads")
 
         # dominant kernels: the residual backward (post + contraction + pre adjoint kernels over the
         # jets saved by the forward), timed alone with CUDA events on the launch stream
@@ -392,10 +396,19 @@ def run_ours(ns):
             raise                              # ... but a collective mismatch must not hang silently
         dp = {"error": f"{type(exc).__name__}: {exc}"}
 
+    def teardown():
+        # captured graphs (they hold NCCL kernels on the NCCL route) and peer-memory buffers must be
+        # gone before the process group is: measure() dropped its model and step, collect the rest
+        import gc
+
+        gc.collect()
+        torch.cuda.synchronize(device)
+        dist.barrier()
+        dist.destroy_process_group()
+
     if rank != 0:
         if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+            teardown()
         return
 
     fl_pt, f_fwd, f_mlp = flops_per_point(N_QUBITS, N_LAYERS, ANSATZ, haar=False, hidden=HIDDEN)
@@ -425,6 +438,7 @@ def run_ours(ns):
         "config": {"workload": WORKLOAD, "residual_points_per_step": pts_total,
                    "ic_points": (pts_rank // 3) * world, "bc_points": (pts_rank // 3) * world,
                    "parallelism": f"dp{world}",
+                   **({"gradient_exchange": primary["exchange"]} if "exchange" in primary else {}),
                    "l2": "inputs resampled on the device every step; per-step footprint > 126 MB L2"},
         "e2e": primary.get("e2e"),
         "gpu_launches": primary["launches"],
@@ -456,8 +470,7 @@ def run_ours(ns):
     if world == 1 and not ns.no_cpu:
         line["cpu_baseline"] = cpu_baseline(ns.cpu_points, ns.cpu_steps)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        teardown()
         time.sleep(0.5)        # let the other ranks' NCCL teardown lines out first
     print(json.dumps(line), flush=True)
 
@@ -638,6 +651,7 @@ def run_reference(ns):
         "config": {"workload": WORKLOAD, "residual_points_per_step": pts_rank * world,
                    "ic_points": (pts_rank // 3) * world, "bc_points": (pts_rank // 3) * world,
                    "parallelism": f"dp{world}",
+                   **({"gradient_exchange": primary["exchange"]} if "exchange" in primary else {}),
                    "l2": "inputs resampled on the device every step; per-step footprint > 126 MB L2"},
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port",
                          "sample": sample, "sample_points_per_step": points, "sizing": sizing,

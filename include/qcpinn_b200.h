@@ -215,6 +215,21 @@ int qcp_plateau_step(const float* metric, double* state, float* lr, float* histo
                      double factor, long long patience, long long cooldown, double min_lr,
                      double eps, void* stream);
 
+/* Data-parallel gradient exchange fused with the clip, over NVLink peer memory (one node; SURVEY.md
+ * section 8e; the clip is reference trainer/diffusion_train.py:85).  ``peer_bufs`` = HOST array of
+ * ``world`` DEVICE pointers, entry r = rank r's symmetric buffer of qcp_peer_allreduce_floats(n_grad +
+ * n_extra, world) floats, zero-filled before the first call and mapped for peer access on this device
+ * (torch.distributed._symmetric_memory).  One single-CTA launch per rank: store flat[0 .. n_grad +
+ * n_extra) into every rank's buffer, exchange sequence-numbered flags (``seq`` = DEVICE counter, 0 at
+ * the start, the same number of calls on every rank), sum the ranks' vectors in rank order (bit-
+ * identical result on every rank), divide by world and clip the first n_grad values to max_norm like
+ * torch.nn.utils.clip_grad_norm_ -- in place.  A peer that does not arrive within timeout_s sets
+ * *error (DEVICE int, 1 + its rank) and the kernel returns. */
+long long qcp_peer_allreduce_floats(int n_values, int world);
+int qcp_peer_allreduce_clip(float* flat, int n_grad, int n_extra, const void* const* peer_bufs, int rank,
+                            int world, unsigned int* seq, double max_norm, int* error,
+                            double timeout_s, void* stream);
+
 /* Host-only self check of the statevector-engine planners (no CUDA device needed; used by the CPU
  * tests): plans the gate list like qcp_plan_create() would for (n_qubits >= 5, dtype), runs the
  * logical circuit and the planned physical program on the CPU over a random statevector and

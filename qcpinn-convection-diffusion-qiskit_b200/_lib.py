@@ -71,6 +71,10 @@ SIGNATURES = {
     "qcp_plateau_step": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_int, _c_int,
                                   ctypes.c_double, ctypes.c_double, _c_ll, _c_ll, ctypes.c_double,
                                   ctypes.c_double, _c_void_p]),
+    "qcp_peer_allreduce_floats": (_c_ll, [_c_int, _c_int]),
+    "qcp_peer_allreduce_clip": (_c_int, [_c_void_p, _c_int, _c_int, ctypes.POINTER(_c_void_p), _c_int,
+                                         _c_int, _c_void_p, ctypes.c_double, _c_void_p,
+                                         ctypes.c_double, _c_void_p]),
     "qcp_debug_check_plan": (_c_int, [_c_int, _c_int, ctypes.POINTER(ctypes.c_int32), _c_int, _dptr,
                                       _c_int, _dptr, _c_int, _dptr, ctypes.POINTER(_c_int),
                                       ctypes.POINTER(_c_int)]),

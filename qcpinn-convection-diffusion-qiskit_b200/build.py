@@ -22,7 +22,7 @@ LIB_PATH = PKG_DIR / "libqcpinn_b200.so"
 SOURCES = ["qcp_plan.cu", "qcp_point_f32.cu", "qcp_point_f64.cu", "qcp_data.cu", "qcp_state.cu",
            "qcp_reg.cu", "qcp_reg_f32.cu", "qcp_reg_f64.cu", "qcp_tile.cu", "qcp_tile_f32.cu",
            "qcp_tile_f64.cu", "qcp_plancheck.cu",
-           "qcp_mlp.cu"]
+           "qcp_mlp.cu", "qcp_peer.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH_FLAGS + [
     "-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr",

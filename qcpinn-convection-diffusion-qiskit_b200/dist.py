@@ -100,3 +100,124 @@ class GradientAverager:
         if extras is not None:
             return self.flat[self.numel:self.numel + len(extras)]
         return None
+
+
+class PeerAllReduce:
+    """Average + clip of the flat float32 gradient over the ranks of ONE node in a single kernel per
+    rank (``qcp_peer_allreduce_clip``: P2P stores into every rank's symmetric buffer, flag exchange,
+    rank-ordered sum, 1 / world, clip) instead of NCCL all-reduce + clip kernel -- the exchange is
+    3 KB, i.e. pure latency.  Buffers come from ``torch.distributed._symmetric_memory`` (peer-mapped
+    over NVLink / NVSwitch).  ``PeerAllReduce.create`` returns None when anything it needs is missing
+    (no CUDA, one rank, symmetric memory unavailable, self test against NCCL fails): callers then
+    keep the NCCL route.  ``QCP_PEER_ALLREDUCE=0`` disables it.
+    """
+
+    TIMEOUT_S = 2.0
+
+    def __init__(self, n_values, device, group):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _lib
+
+        self.lib = _lib.require_cuda()
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.device = torch.device(device)
+        self.n_values = int(n_values)
+        floats = self.lib.qcp_peer_allreduce_floats(self.n_values, self.world)
+        if floats <= 0:
+            raise RuntimeError(f"peer all-reduce supports up to 16 ranks, got {self.world}")
+        self.buf = symm.empty(int(floats), dtype=torch.float32, device=self.device)
+        self.handle = symm.rendezvous(self.buf, self.group)
+        self.buf.zero_()
+        self.seq = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.error = torch.zeros(1, dtype=torch.int32, device=self.device)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)                       # nobody pushes into a buffer not yet zeroed
+        ptrs = list(self.handle.buffer_ptrs)
+        if len(ptrs) != self.world or not all(ptrs):
+            raise RuntimeError("symmetric memory rendezvous returned no peer pointers")
+        self._ptrs = (ctypes.c_void_p * self.world)(*ptrs)
+        self.calls = 0
+
+    @classmethod
+    def create(cls, n_values, device, group=None, max_norm=1.0):
+        if os.environ.get("QCP_PEER_ALLREDUCE", "1") == "0":
+            return None
+        if not (dist.is_available() and dist.is_initialized()) or torch.device(device).type != "cuda":
+            return None
+        if dist.get_world_size(group) < 2 or dist.get_backend(group) != "nccl":
+            return None
+        ok = torch.ones(1, dtype=torch.int32, device=device)
+        peer = None
+        try:
+            peer = cls(n_values, device, group)
+            ok.fill_(1 if peer.self_test(max_norm) else 0)
+        except Exception as exc:                            # symmetric memory unavailable on this box
+            ok.fill_(0)
+            peer = None
+            cls.last_failure = f"{type(exc).__name__}: {exc}"
+        # all ranks must agree: a mixed NCCL / peer exchange would deadlock
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        return peer if int(ok.item()) == 1 else None
+
+    last_failure = None
+
+    def reduce_clip(self, flat, n_grad, n_extra, max_norm):
+        """In place on ``flat[: n_grad + n_extra]`` (float32): mean over the ranks, then the first
+        ``n_grad`` values clipped to ``max_norm``.  Stream-ordered, CUDA-graph capturable."""
+        import ctypes
+
+        from . import _lib
+
+        if n_grad + n_extra != self.n_values or flat.dtype != torch.float32 or not flat.is_contiguous():
+            raise ValueError("PeerAllReduce.reduce_clip: buffer does not match the exchange plan")
+        with torch.cuda.device(self.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            rc = self.lib.qcp_peer_allreduce_clip(
+                ctypes.c_void_p(flat.data_ptr()), int(n_grad), int(n_extra), self._ptrs, self.rank,
+                self.world, ctypes.c_void_p(self.seq.data_ptr()), float(max_norm),
+                ctypes.c_void_p(self.error.data_ptr()), float(self.TIMEOUT_S), stream)
+        _lib.check(rc, "qcp_peer_allreduce_clip")
+        self.calls += 1
+
+    def close(self):
+        """Release the symmetric buffer (collective-free; call before destroy_process_group)."""
+        if self.buf is not None:
+            torch.cuda.synchronize(self.device)
+            self.handle = None
+            self.buf = None
+            self._ptrs = None
+
+    def check(self):
+        """Raises if a peer ever failed to arrive (synchronises)."""
+        code = int(self.error.item())
+        if code:
+            raise RuntimeError(f"peer all-reduce: rank {code - 1} did not arrive within "
+                               f"{self.TIMEOUT_S} s (rank {self.rank})")
+
+    def self_test(self, max_norm=1.0):
+        """Two exchanges of rank-dependent vectors (both slot parities) against NCCL + the clip
+        formula; True when they agree to float32 rounding and no peer timed out."""
+        n = self.n_values
+        n_grad = max(n - 1, 1) if n > 1 else 1
+        n_extra = n - n_grad
+        good = True
+        for trial in range(2):
+            g = torch.Generator(device="cpu").manual_seed(1000 * trial + self.rank)
+            v = (torch.randn(n, generator=g) * (3.0 if trial else 0.01)).to(self.device)
+            want = v.clone()
+            dist.all_reduce(want, op=dist.ReduceOp.SUM, group=self.group)
+            want /= self.world
+            norm = want[:n_grad].double().norm().float()
+            coef = torch.clamp(max_norm / (norm + 1e-6), max=1.0)
+            want[:n_grad] *= coef
+            got = v.clone()
+            self.reduce_clip(got, n_grad, n_extra, max_norm)
+            torch.cuda.synchronize(self.device)
+            err = float((got - want).abs().max() / want.abs().max().clamp_min(1e-30))
+            good = good and err < 1e-5 and int(self.error.item()) == 0
+        return good

@@ -191,6 +191,7 @@ class TrainStep:
         self._plateau = None       # DevicePlateau the captured graphs were built with
         self._plateau_config = None
         self._capture_stream = None
+        self._peer = None          # PeerAllReduce | False (unavailable) | None (not tried yet)
 
     def draw(self):
         """The random numbers of one :meth:`sample` call, in its order (pass back as ``rnd``)."""
@@ -209,9 +210,33 @@ class TrainStep:
         return X_ics, u_ics, X_bcs, u_bcs, X_res, r_res
 
     def flush(self):
-        """Bring ``model.loss_history`` and the scheduler object up to date (no-op when current)."""
+        """Bring ``model.loss_history`` and the scheduler object up to date (no-op when current);
+        raises if a rank ever missed a peer-memory gradient exchange."""
         if self._plateau is not None:
             self._plateau.flush()
+        if self._peer:
+            self._peer.check()
+
+    def close(self):
+        """Drain pending host state and release the captured graphs and the peer-memory buffer
+        (do this before ``torch.distributed.destroy_process_group()``: graphs of the NCCL route hold
+        kernels of the communicator)."""
+        self.flush()
+        self._graphs.clear()
+        if self._peer:
+            self._peer.close()
+        self._peer = None
+
+    def _peer_exchange(self, n_values):
+        """The node-local peer-memory exchange (created collectively on first use), or None when the
+        NCCL all-reduce has to do it."""
+        if self._peer is None:
+            from ..dist import PeerAllReduce
+
+            made = PeerAllReduce.create(n_values, self.model.quantum_layer.params.device,
+                                        self.averager.group, self.max_norm)
+            self._peer = made if made is not None else False
+        return self._peer or None
 
     def objective(self, batch=None):
         """Returns (loss, seconds, loss_r, loss_bc, loss_ic) like the reference's objective_fn."""
@@ -305,15 +330,23 @@ class TrainStep:
         if self.averager is not None:
             import torch.distributed as dist
 
-            # gradients and the scheduler metric share one all-reduce; the local terms are kept
+            # gradients and the scheduler metric share one exchange; the local terms are kept
             local_terms = flat[numel + 1:numel + 4].clone()
-            dist.all_reduce(flat[:numel + 1], op=dist.ReduceOp.SUM, group=self.averager.group)
-            world = self.averager.world
+            peer = self._peer_exchange(numel + 1)
             self.averager.calls += 1
+            if peer is not None:
+                # one kernel per rank over NVLink peer memory: exchange, ordered sum, mean, clip
+                peer.reduce_clip(flat, numel, 1, self.max_norm)
+                F._count(1)
+                world = 0
+            else:
+                dist.all_reduce(flat[:numel + 1], op=dist.ReduceOp.SUM, group=self.averager.group)
+                world = self.averager.world
         else:
             local_terms = flat[numel + 1:numel + 4]
-        plan = model._plan(model.quantum_layer.params.device)
-        F.clip_grads(plan, flat, numel, 1, 1.0 / world, self.max_norm)
+        if world:
+            plan = model._plan(model.quantum_layer.params.device)
+            F.clip_grads(plan, flat, numel, 1, 1.0 / world, self.max_norm)
         model.optimizer.step()
         if side is not None:
             torch.cuda.current_stream(model.quantum_layer.params.device).wait_stream(side)
@@ -519,7 +552,7 @@ def train(model, nIter=10000, batch_size=128, log_NTK=False, update_lam=False):
             if it > 0 and it % every == 0 and rank0:
                 model.save_state()
 
-    step.flush()                                 # loss history / scheduler object complete (and synced)
+    step.close()                                 # loss history / scheduler object complete (and synced)
     if model.device is not None and torch.device(model.device).type == "cuda":
         torch.cuda.synchronize(model.device)
     total = time.time() - t0
