@@ -22,6 +22,15 @@ constexpr int kMaxBlocksPerSm = 8;   // persistent grids never exceed this many 
 // than the extra 8 H bytes per point of traffic (measured: float64 +5.6 % points/s, float32 -4 %).
 template <typename T> struct SaveAct { static constexpr bool value = false; };
 template <> struct SaveAct<double> { static constexpr bool value = true; };
+// ... per mode: with one stream per point (value mode, S = 1) a hidden unit's adjoint is ~15 FMAs, so
+// re-evaluating its tanh (16 FP64-pipe instructions with the exp table) is cheaper than 16 bytes
+// of workspace traffic per unit and point (QCP_SAVE_ACT_VALUE=1 saves them like residual mode does)
+#ifndef QCP_SAVE_ACT_VALUE
+#define QCP_SAVE_ACT_VALUE 1
+#endif
+template <typename T, int S> struct SaveActS {
+  static constexpr bool value = SaveAct<T>::value && (S != 1 || QCP_SAVE_ACT_VALUE != 0);
+};
 constexpr int kStageRows = 32;       // rows of the per-warp gradient staging tile
 constexpr int kStagePitch = 33;      // +1 padding: column sums are bank-conflict free
 

@@ -1290,11 +1290,12 @@ solver_forward_kernel(const SolverArgs a) {
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < a.B; p += stride) {
     T X[3] = {(T)Xg[3 * p], (T)Xg[3 * p + 1], (T)Xg[3 * p + 2]};
     Jet<T, S> z[NQ], q[NQ], u;
-    T* act = (SaveAct<T>::value && wsg) ? ws_act<T, NQ, S>(wsg, a.B) + p : nullptr;
+    T* act = (SaveActS<T, S>::value && wsg) ? ws_act<T, NQ, S>(wsg, a.B) + p : nullptr;
     pre_forward<T, NQ, S>(sw, H, X, z, act, a.B);
     if (wsg) ws_store<T, NQ, S>(wsg, a.B, 0, p, z);
     feature_forward<T, NQ, ENC, S>(sw.C, z, q,
-                                   act ? ws_trig<T, NQ, S>(wsg, a.B, H) + p : nullptr, a.B);
+                                   (SaveAct<T>::value && wsg) ? ws_trig<T, NQ, S>(wsg, a.B, H) + p : nullptr,
+                                   a.B);
     if (wsg) ws_store<T, NQ, S>(wsg, a.B, 1, p, q);
     post_forward<T, NQ, S>(sw, H, q, u, act ? act + (size_t)H * a.B : nullptr, a.B);
     ug[p] = (TIO)u.c[0];
@@ -1399,7 +1400,7 @@ post_backward_kernel(const SolverArgs a) {
       }
       st.begin();
       st.put(db4);                                         // d b4
-      post_backward_value<T, NQ, K, SaveAct<T>::value>(sw, H, q, ub, qb, st, act, a.B, pts);
+      post_backward_value<T, NQ, K, SaveActS<T, 1>::value>(sw, H, q, ub, qb, st, act, a.B, pts);
       st.flush();
 #pragma unroll
       for (int j = 0; j < K; ++j)
@@ -1422,7 +1423,7 @@ post_backward_kernel(const SolverArgs a) {
     if (p0 + stride < a.B) ws_prefetch<T>(wsg + (size_t)NQ * S * a.B + p0 + stride, a.B, NQ * S);
     st.begin();
     st.put(ub.c[0]);                                       // d b4
-    post_backward<T, NQ, S, SaveAct<T>::value>(sw, H, q, ub, qb, st,
+    post_backward<T, NQ, S, SaveActS<T, S>::value>(sw, H, q, ub, qb, st,
                                   ws_act<T, NQ, S>(wsg, a.B) + (size_t)H * a.B + p, a.B);
     st.flush();
     if (valid) ws_store<T, NQ, S>(wsg, a.B, 1, p, qb);
@@ -1559,7 +1560,7 @@ pre_backward_kernel(const SolverArgs a) {
         for (int i = 0; i < NQ; ++i) zb[j][i] = ok[j] ? wsg[(size_t)i * a.B + pts[j]] : T(0);   // slot 0
       }
       st.begin();
-      pre_backward_value<T, NQ, K, SaveAct<T>::value>(sw, H, X, zb, Xb, st, act, a.B, pts);
+      pre_backward_value<T, NQ, K, SaveActS<T, 1>::value>(sw, H, X, zb, Xb, st, act, a.B, pts);
       st.flush();
       if (gXg) {
 #pragma unroll
@@ -1588,7 +1589,7 @@ pre_backward_kernel(const SolverArgs a) {
     }
     T Xb[3];
     st.begin();
-    pre_backward<T, NQ, S, SaveAct<T>::value>(sw, H, X, zb, Xb, st,
+    pre_backward<T, NQ, S, SaveActS<T, S>::value>(sw, H, X, zb, Xb, st,
                                               ws_act<T, NQ, S>(wsg, a.B) + p, a.B);
     st.flush();
     if (gXg && valid) {
