@@ -438,10 +438,10 @@ def run_ours(ns):
         "config": {"workload": WORKLOAD, "residual_points_per_step": pts_total,
                    "ic_points": (pts_rank // 3) * world, "bc_points": (pts_rank // 3) * world,
                    "parallelism": f"dp{world}",
-                   **({"gradient_exchange": primary["exchange"]} if "exchange" in primary else {}),
                    "l2": "inputs resampled on the device every step; per-step footprint > 126 MB L2"},
         "e2e": primary.get("e2e"),
         "gpu_launches": primary["launches"],
+        **({"gradient_exchange": primary["exchange"]} if "exchange" in primary else {}),
         "clocks": {k: primary["clocks"][k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
         "wall_ms_per_step": primary["wall_ms"] / ns.steps,
         "roofline": roof(primary, ns.dtype),
@@ -651,7 +651,6 @@ def run_reference(ns):
         "config": {"workload": WORKLOAD, "residual_points_per_step": pts_rank * world,
                    "ic_points": (pts_rank // 3) * world, "bc_points": (pts_rank // 3) * world,
                    "parallelism": f"dp{world}",
-                   **({"gradient_exchange": primary["exchange"]} if "exchange" in primary else {}),
                    "l2": "inputs resampled on the device every step; per-step footprint > 126 MB L2"},
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port",
                          "sample": sample, "sample_points_per_step": points, "sizing": sizing,
