@@ -167,6 +167,13 @@ int qcp_solver_backward_add(qcp_plan_t* plan, const qcp_mlp_t* weights, const vo
 int qcp_solver_backward_finish(qcp_plan_t* plan, const void* theta, const qcp_mlp_t* grads,
                                void* grad_theta, void* stream);
 
+/* Between two qcp_solver_backward_add() calls on DIFFERENT streams: make ``stream`` wait until the
+ * post-MLP adjoint kernel of the call added last has finished (no-op if that call launched none).
+ * The train step uses it to hold the IC/BC adjoints (low-priority side stream) back until the
+ * residual chain's contraction adjoint is ready to start, so they fill that kernel's tail instead
+ * of slipping in front of it. */
+int qcp_solver_backward_after_post(qcp_plan_t* plan, void* stream);
+
 /* Reverse mode for operators that are NONLINEAR in the Taylor streams (reference nn/pde.py:2-25,
  * navier_stokes_2D_operator: products like u * u_x): the caller differentiates its own residual
  * with respect to the six streams of qcp_solver_forward(..., streams) and passes

@@ -57,6 +57,7 @@ SIGNATURES = {
     "qcp_solver_backward_add": (_c_int, [_c_void_p, ctypes.POINTER(QcpMlp), _c_void_p, _c_void_p,
                                          _c_void_p, _c_ll, _c_int, _dptr, _c_void_p, _c_void_p,
                                          _c_void_p]),
+    "qcp_solver_backward_after_post": (_c_int, [_c_void_p, _c_void_p]),
     "qcp_solver_backward_finish": (_c_int, [_c_void_p, _c_void_p, ctypes.POINTER(QcpMlp),
                                             _c_void_p, _c_void_p]),
     "qcp_sample_targets": (_c_int, [_c_void_p, _c_ll, ctypes.POINTER(ctypes.c_float), _c_int,

@@ -119,7 +119,8 @@ int solver_split_grids(int n, int enc, int mode, int H, int num_sms, SplitGrids*
 template <typename T>
 int launch_solver_backward_split(int n, int enc, int mode, const SolverArgs& a, const SplitGrids& g,
                                  void* part_post, void* part_contract, void* part_pre,
-                                 cudaStream_t s, cudaEvent_t after_contract = nullptr);
+                                 cudaStream_t s, cudaEvent_t after_contract = nullptr,
+                                 cudaEvent_t after_post = nullptr);
 template <typename T>
 size_t solver_backward_smem(int n, int enc, int H);
 template <typename T>

@@ -674,6 +674,8 @@ struct qcp_plan {
   // theta_grad (single-CTA, latency bound) run on `aux` next to the pre-MLP adjoints
   cudaStream_t aux;
   cudaEvent_t ev_contract[kMaxPending];
+  cudaEvent_t ev_post[kMaxPending];      // behind the post-MLP adjoint of pending item k
+  bool post_recorded[kMaxPending];
   cudaEvent_t ev_theta;
   bool pend_split[kMaxPending];
   bool overlap_theta;       // QCP_THETA_OVERLAP != 0 (default on)
@@ -852,6 +854,8 @@ int qcp_plan_create(qcp_plan_t** out, int n_qubits, int encoding, int dtype, int
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->aux, cudaStreamNonBlocking);
     for (int k = 0; k < kMaxPending && e == cudaSuccess; ++k)
       e = cudaEventCreateWithFlags(&p->ev_contract[k], cudaEventDisableTiming);
+    for (int k = 0; k < kMaxPending && e == cudaSuccess; ++k)
+      e = cudaEventCreateWithFlags(&p->ev_post[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_theta, cudaEventDisableTiming);
   }
   if (e == cudaSuccess && n_ops) e = cudaMemcpy(p->d_ops, ops, sizeof(GateOp) * n_ops, cudaMemcpyHostToDevice);
@@ -884,6 +888,7 @@ int qcp_plan_destroy(qcp_plan_t* p) {
   cudaFree(p->d_theta); cudaFree(p->d_ws); cudaFree(p->d_slab); cudaFree(p->d_theta_partials);
   if (p->aux) cudaStreamDestroy(p->aux);
   for (int k = 0; k < kMaxPending; ++k) if (p->ev_contract[k]) cudaEventDestroy(p->ev_contract[k]);
+  for (int k = 0; k < kMaxPending; ++k) if (p->ev_post[k]) cudaEventDestroy(p->ev_post[k]);
   if (p->ev_theta) cudaEventDestroy(p->ev_theta);
   reg_destroy(p->reg);
   tile_destroy(p->tile);
@@ -1211,6 +1216,16 @@ int qcp_solver_backward_begin(qcp_plan_t* p) {
   if (!p) { set_error("qcp_solver_backward_begin: NULL plan"); return 1; }
   p->pending = 0;
   p->pending_used = 0;
+  for (int k = 0; k < kMaxPending; ++k) p->post_recorded[k] = false;
+  return 0;
+}
+
+int qcp_solver_backward_after_post(qcp_plan_t* p, void* stream) {
+  if (!p) { set_error("qcp_solver_backward_after_post: NULL plan"); return 1; }
+  const int k = p->pending - 1;
+  // nothing to wait for when the previous call launched no split adjoints (empty batch, fused path)
+  if (k < 0 || !p->post_recorded[k]) return 0;
+  QCP_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), p->ev_post[k], 0));
   return 0;
 }
 
@@ -1285,9 +1300,10 @@ static int backward_add_impl(qcp_plan_t* p, const qcp_mlp_t* w, const void* X, c
     if (check_partials_room(p, e0 + e1 + e2, "qcp_solver_backward_add")) return 1;
     void* p0 = base; void* p1 = base + e0 * es; void* p2 = base + (e0 + e1) * es;
     cudaEvent_t ev = p->overlap_theta ? p->ev_contract[k] : nullptr;
-    int rc = f64 ? launch_solver_backward_split<double>(p->n, p->enc, mode, a, gr, p0, p1, p2, s, ev)
-                 : launch_solver_backward_split<float>(p->n, p->enc, mode, a, gr, p0, p1, p2, s, ev);
+    int rc = f64 ? launch_solver_backward_split<double>(p->n, p->enc, mode, a, gr, p0, p1, p2, s, ev, p->ev_post[k])
+                 : launch_solver_backward_split<float>(p->n, p->enc, mode, a, gr, p0, p1, p2, s, ev, p->ev_post[k]);
     if (rc) return rc;
+    p->post_recorded[k] = true;
     p->pend_split[k] = true;
     p->pend_ptr[k][0] = p0; p->pend_grid[k][0] = gr.post;
     p->pend_ptr[k][1] = p1; p->pend_grid[k][1] = gr.contract;

@@ -1822,9 +1822,11 @@ struct ContractSmall {
 template <typename T>
 int launch_solver_backward_split(int n, int enc, int mode, const SolverArgs& a, const SplitGrids& g,
                                  void* part_post, void* part_contract, void* part_pre,
-                                 cudaStream_t s, cudaEvent_t after_contract) {
+                                 cudaStream_t s, cudaEvent_t after_contract, cudaEvent_t after_post) {
   // after_contract (optional) is recorded between the contraction adjoint and the pre-MLP adjoint:
-  // d C is complete there, so the caller can reduce it and run theta_grad next to pre_backward
+  // d C is complete there, so the caller can reduce it and run theta_grad next to pre_backward.
+  // after_post (optional) is recorded behind the post-MLP adjoint: another chain's adjoints can be
+  // held back until then (qcp_solver_backward_after_post)
   SolverArgs a0 = a, a1 = a, a2 = a;
   a0.partials = part_post; a1.partials = part_contract; a2.partials = part_pre;
   const size_t m0 = split_smem<T>(0, n, enc, a.H), m1 = split_smem<T>(1, n, enc, a.H),
@@ -1832,6 +1834,7 @@ int launch_solver_backward_split(int n, int enc, int mode, const SolverArgs& a, 
   QCP_DISPATCH_NQ_ENC(n, enc, {
     if (mode == QCP_MODE_RESIDUAL) {
       if (QCP_IO_LAUNCH(post_backward_kernel, 6, g.post, m0, "post_backward", a0)) return 1;
+      if (after_post && cudaEventRecord(after_post, s) != cudaSuccess) { set_error("cudaEventRecord failed"); return 1; }
       // few iterations per thread: the fully unrolled body (336 KB of SASS in float64) is fetched
       // cold at every launch and the first pass over it costs as much as several warm ones, so a
       // variant with the outer A-half trit loop rolled (3x less code) wins below ~20 iterations
@@ -1844,6 +1847,7 @@ int launch_solver_backward_split(int n, int enc, int mode, const SolverArgs& a, 
       return QCP_IO_LAUNCH(pre_backward_kernel, 6, g.pre, m2, "pre_backward", a2);
     }
     if (QCP_IO_LAUNCH(post_backward_kernel, 1, g.post, m0, "post_backward", a0)) return 1;
+    if (after_post && cudaEventRecord(after_post, s) != cudaSuccess) { set_error("cudaEventRecord failed"); return 1; }
     if (launch_checked(&contract_backward_kernel<T, NQ, ENC, 1>, g.contract, m1, s, "contract_backward", a1)) return 1;
     if (after_contract && cudaEventRecord(after_contract, s) != cudaSuccess) { set_error("cudaEventRecord failed"); return 1; }
     return QCP_IO_LAUNCH(pre_backward_kernel, 1, g.pre, m2, "pre_backward", a2);

@@ -312,9 +312,10 @@ def _flat_grad_views(plan: Plan, mlp, theta):
 
 def solver_backward_many(plan: Plan, items, mlp, theta, after_adjoints=None):
     """Adjoint kernels of several model calls, ONE partial reduction and ONE theta-gradient kernel.
-    ``items`` = [(X, grad_u, grad_r, mode, coeffs, save, need_gx[, stream]), ...]; an item's adjoint
-    kernels run on its ``stream`` (a torch stream already ordered after the producers of its
-    inputs) and the reduction waits for it.  ``after_adjoints()`` runs between the joined adjoint
+    ``items`` = [(X, grad_u, grad_r, mode, coeffs, save, need_gx[, stream[, gate]]), ...]; an item's
+    adjoint kernels run on its ``stream`` (a torch stream already ordered after the producers of its
+    inputs) and the reduction waits for it; with ``gate`` they also wait for the post-MLP adjoint of
+    the PREVIOUS item (``qcp_solver_backward_after_post``).  ``after_adjoints()`` runs between the joined adjoint
     launches and the reduction.  Returns (views, [gx])."""
     lib = plan.lib
     flat, views = _flat_grad_views(plan, mlp, theta)
@@ -332,6 +333,9 @@ def solver_backward_many(plan: Plan, items, mlp, theta, after_adjoints=None):
             gx = torch.empty_like(X) if need_gx else None
             gxs.append(gx)
             c = (ctypes.c_double * 5)(*coeffs) if coeffs is not None else None
+            if len(rest) > 1 and rest[1] and side is not None:
+                _lib.check(lib.qcp_solver_backward_after_post(plan._handle, item_stream),
+                           "qcp_solver_backward_after_post")
             rc = lib.qcp_solver_backward_add(
                 plan._handle, ctypes.byref(m), ctypes.c_void_p(X.data_ptr()),
                 ctypes.c_void_p(gu.data_ptr() if gu is not None else None),

@@ -352,9 +352,15 @@ class DVPDESolver(nn.Module):
         _, r_r, _ = plan.solver_forward(X_r, mt, F.MODE_RESIDUAL, coeffs, save=ws_r)
         gr = torch.empty_like(r_r)
         F.mse_seed(plan, r_r, t_r, w_r, gr, terms[0:1])
+        # residual chain first; the IC/BC adjoints (side stream) are held back until its post-MLP
+        # adjoint is done, i.e. until its contraction adjoint is ready too: the block scheduler then
+        # places that one first (higher stream priority in the captured step) and the IC/BC kernels
+        # fill its tail.  Without the gate a 2 us race at the end of post_backward decides whether
+        # they slip in front instead (+90 us per step at 524 288 points, profiles/r02_timeline_8gpu*)
+        gate = os.environ.get("QCP_GATE_VALUE", "1") != "0"
         views, _ = F.solver_backward_many(
-            plan, [(X_val, gu_v, None, F.MODE_VALUE, None, ws_v, False, side),
-                   (X_r, None, gr, F.MODE_RESIDUAL, coeffs, ws_r, False, None)], mt, tt,
+            plan, [(X_r, None, gr, F.MODE_RESIDUAL, coeffs, ws_r, False, None),
+                   (X_val, gu_v, None, F.MODE_VALUE, None, ws_v, False, side, gate)], mt, tt,
             after_adjoints=after_adjoints)
         flat, numel = self.flat_grad_buffer()
         # cast into the optimizer's float32 buffer + weighted objective and its terms: one launch
