@@ -112,7 +112,7 @@ class PeerAllReduce:
     keep the NCCL route.  ``QCP_PEER_ALLREDUCE=0`` disables it.
     """
 
-    TIMEOUT_S = 2.0
+    TIMEOUT_S = 5.0
 
     def __init__(self, n_values, device, group):
         import ctypes
