@@ -3,15 +3,18 @@
 ``train(model, nIter=10000, batch_size=128, log_NTK=False, update_lam=False)`` keeps the reference
 contract: ``batch_size`` residual points plus ``batch_size // 3`` initial-condition and
 ``batch_size // 3`` x=0 boundary points per step, loss ``2 MSE_r + 4 MSE_bc + 2 MSE_ic``,
-``clip_grad_norm_(1.0)`` (0.1 for the CV solver), Adam, ``ReduceLROnPlateau.step(loss)`` and a
-``loss.item()`` per step; ``model.epochs + 1`` iterations; a log line and a checkpoint every
-``args["print_every"]`` steps (logged / saved right AFTER that step's parameter update; the
-reference does it just before).  ``nIter``, ``log_NTK`` and ``update_lam`` are accepted and unused,
-as in the reference.
+``clip_grad_norm_(1.0)`` (0.1 for the CV solver), Adam, ``ReduceLROnPlateau.step(loss)`` and the
+loss appended to ``model.loss_history`` every step (in the captured step both happen on the device
+and the host objects are brought up to date when they are read: same decisions and values, no
+``loss.item()`` round trip per step, :class:`DevicePlateau`); ``model.epochs + 1`` iterations; a log
+line and a checkpoint every ``args["print_every"]`` steps (logged / saved right AFTER that step's
+parameter update; the reference does it just before).  ``nIter``, ``log_NTK`` and ``update_lam`` are
+accepted and unused, as in the reference.
 
 The step itself is exposed as :class:`TrainStep` so ``bench.py`` times exactly what ``train`` runs.
 Under ``torch.distributed`` (world size > 1) every rank draws its own points and the gradients and
-loss terms ride in one flat all-reduce before clipping.
+the loss ride in one exchange before clipping: one peer-memory kernel per rank on an NVLink node
+(``dist.PeerAllReduce``), one flat NCCL / gloo all-reduce otherwise.
 """
 
 import os
@@ -183,7 +186,7 @@ class TrainStep:
                           and getattr(model, "supports_fused_step", lambda: False)()
                           and model.optimizer is not None)
         self._eager_calls = 0
-        self._graphs = {}          # "device" / "host" -> (graph, static outputs, static batch)
+        self._graphs = {}          # "device" / "host" -> (graph, outputs, static batch, launches, ahead)
         self.last_terms = None     # (loss, loss_r, loss_bc, loss_ic) tensors of the last step
         self._stages = []          # two device staging slots for prefetched host batches
         self._copy_stream = None
